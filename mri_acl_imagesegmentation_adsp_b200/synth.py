@@ -1,0 +1,75 @@
+"""Seeded synthetic k-space and sampling masks.
+
+Host-side input generation for tests, ``bench.py`` and the golden-vector script.
+Not on the hot path: nothing here runs inside a timed region.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+KNEE_SHAPE = (15, 640, 368)          # coils, readout, phase-encode  (BASELINE.json configs[0..1])
+PROSTATE_SHAPE = (3, 30, 16, 640, 451)  # averages, slices, coils, readout, phase-encode (configs[2])
+PROSTATE_PAD = (94, 95)              # 451 -> 640
+CROP = (320, 320)
+
+
+def gaussian_kspace(shape: Tuple[int, ...], seed: int) -> np.ndarray:
+    """complex64 ``N(0,1) + i N(0,1)`` of ``shape`` from ``default_rng(seed)``."""
+    rng = np.random.default_rng(seed)
+    re = rng.standard_normal(shape, dtype=np.float32)
+    im = rng.standard_normal(shape, dtype=np.float32)
+    out = np.empty(shape, dtype=np.complex64)
+    out.real = re
+    out.imag = im
+    return out
+
+
+def phantom_kspace(shape: Tuple[int, int, int], seed: int) -> np.ndarray:
+    """Structured (C, H, W) case: centred orthonormal FFT of an ellipse phantom times
+    smooth Gaussian coil sensitivities, so the RSS image has image-like dynamic range."""
+    c, h, w = shape
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.linspace(-1, 1, h, dtype=np.float32),
+                         np.linspace(-1, 1, w, dtype=np.float32), indexing="ij")
+    body = ((xx / 0.62) ** 2 + (yy / 0.42) ** 2 <= 1).astype(np.float32)
+    body += 0.6 * (((xx + 0.2) / 0.2) ** 2 + ((yy - 0.05) / 0.12) ** 2 <= 1)
+    body -= 0.4 * (((xx - 0.25) / 0.15) ** 2 + ((yy + 0.1) / 0.1) ** 2 <= 1)
+    body *= 1.0 + 0.05 * np.sin(9 * xx) * np.cos(7 * yy)
+    ang = 2 * np.pi * np.arange(c) / c + rng.uniform(0, 0.3)
+    imgs = np.empty((c, h, w), dtype=np.complex64)
+    for i in range(c):
+        cx, cy = 0.9 * np.cos(ang[i]), 0.9 * np.sin(ang[i])
+        sens = np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / 0.9).astype(np.float32)
+        phase = np.exp(1j * (0.8 * xx * np.cos(ang[i]) + 0.8 * yy * np.sin(ang[i]))).astype(np.complex64)
+        imgs[i] = body * sens * phase
+    ax = (-2, -1)
+    k = np.fft.fftshift(np.fft.fft2(np.fft.ifftshift(imgs, axes=ax), norm="ortho"), axes=ax)
+    noise = 1e-3 * gaussian_kspace((c, h, w), seed + 7919)
+    return (k + noise).astype(np.complex64)
+
+
+def equispaced_mask(width: int, acceleration: int, center_fraction: float, offset: int = 0) -> np.ndarray:
+    """0/1 float32 mask along the phase-encode axis.
+
+    The reference has no mask code; this is the rule
+    this build defines and freezes: every ``acceleration``-th column from
+    ``offset``, plus ``round(width * center_fraction)`` centred low-frequency columns
+    starting at ``(width - n_low + 1) // 2``.  (368, 4, 0.08) keeps 114 columns."""
+    m = np.zeros(width, dtype=np.float32)
+    m[offset::acceleration] = 1.0
+    n_low = int(round(width * center_fraction))
+    lo = (width - n_low + 1) // 2
+    m[lo:lo + n_low] = 1.0
+    return m
+
+
+def knee_mask() -> np.ndarray:
+    """configs[0..1]: W=368, 4x equispaced + 29 ACS columns (114 kept)."""
+    return equispaced_mask(368, 4, 0.08)
+
+
+def prostate_mask() -> np.ndarray:
+    """configs[2]: PE=451, 8x equispaced + round(451*0.04)=18 ACS columns."""
+    return equispaced_mask(451, 8, 0.04)

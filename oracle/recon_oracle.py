@@ -1,0 +1,368 @@
+"""CPU (numpy) restatement of the reference's k-space -> image input stage.
+
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  The product path never
+imports this module; the CUDA library has no CPU fallback.
+
+Every function cites the reference lines it restates.  ``REF`` = the read-only
+checkout of bonhchi/mri_acl_imagesegmentation_adsp, ``ZIP!`` = a member of
+``REF/reference/fastMRI_prostate-main.zip`` (the vendored cai2r/fastMRI_prostate
+tree that holds the multicoil pieces of the path).
+
+Pinning: the reference ships no tests, golden vectors or
+fixtures for this path.  The pin is therefore made by this build:
+``oracle/make_golden.py`` imports the reference's own functions (through
+``oracle/ref_shim.py``) in the build container, runs them on seeded synthetic
+k-space and freezes their outputs under ``tests/golden/``;
+``tests/test_oracle_golden.py`` checks this restatement against those frozen
+reference outputs.  Two pieces have no reference implementation at all and are
+"parity unpinned" in the reference's own terms: the undersampling-mask
+*generator* (`equispaced_mask`; no mask code exists in the reference) and the
+FFT library result itself (numpy's pocketfft / torch.fft are third-party
+dependencies, ``numpy>=2.0.0`` at REF/src/requirements.txt:20).  Mask
+*application* and crop indexing are pinned exactly.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# a1/a2  centred 2-D FFT pair            REF/src/utils/kspace.py:4-16
+# --------------------------------------------------------------------------
+
+_AX = (-2, -1)
+
+
+def fft2c(x: np.ndarray) -> np.ndarray:
+    """Centred, orthonormal 2-D FFT over the last two axes (kspace.py:4-9)."""
+    shifted = np.fft.ifftshift(x, axes=_AX)
+    spec = np.fft.fft2(shifted, norm="ortho")
+    return np.fft.fftshift(spec, axes=_AX)
+
+
+def ifft2c(x: np.ndarray) -> np.ndarray:
+    """Centred, orthonormal 2-D inverse FFT over the last two axes (kspace.py:11-16).
+
+    complex64 in -> complex64 out on numpy >= 2 (pocketfft keeps single precision).
+    """
+    shifted = np.fft.ifftshift(x, axes=_AX)
+    img = np.fft.ifft2(shifted, norm="ortho")
+    return np.fft.fftshift(img, axes=_AX)
+
+
+# --------------------------------------------------------------------------
+# a4  magnitude                           REF/src/utils/kspace.py:18-20
+#                                         ZIP!/DL_reconstruction/math_fn.py:55-86
+# --------------------------------------------------------------------------
+
+
+def complex_abs(x: np.ndarray) -> np.ndarray:
+    """sqrt(re^2 + im^2) of a complex array (kspace.py:18-20)."""
+    re, im = x.real, x.imag
+    return np.sqrt(re * re + im * im)
+
+
+def complex_abs_sq_ri(data: np.ndarray) -> np.ndarray:
+    """re^2+im^2 on the fastMRI real-view layout (..., 2) (math_fn.py:72-86)."""
+    if data.shape[-1] != 2:
+        raise ValueError("Tensor does not have separate complex dim.")
+    return (data ** 2).sum(axis=-1)
+
+
+def complex_abs_ri(data: np.ndarray) -> np.ndarray:
+    """|z| on the real-view layout (..., 2) (math_fn.py:55-69)."""
+    return np.sqrt(complex_abs_sq_ri(data))
+
+
+# --------------------------------------------------------------------------
+# a3  single-coil magnitude recon         REF/src/preprocess/mri_preprocess.py:149-160,177-180
+# --------------------------------------------------------------------------
+
+
+def ifft2c_single(kspace_2d: np.ndarray) -> np.ndarray:
+    """|ifft2c(k)| as float32 for ONE (H, W) complex slice.
+
+    ValueError when ``ndim != 2`` (``_ensure_2d``, mri_preprocess.py:177-180).
+    """
+    if kspace_2d.ndim != 2:
+        raise ValueError(f"kspace must be (H,W), got {kspace_2d.shape}")
+    img = np.fft.fftshift(
+        np.fft.ifft2(np.fft.ifftshift(kspace_2d, axes=_AX), norm="ortho"), axes=_AX
+    )
+    return np.abs(img).astype(np.float32)
+
+
+# --------------------------------------------------------------------------
+# a6  centre crop (three reference spellings, identical indices when n >= out)
+# --------------------------------------------------------------------------
+
+
+def crop_start(n: int, out: int) -> int:
+    """First kept index of a centred window: (n - out) // 2.
+
+    kspace.py:27-28, transforms.py:62-63 and utils.py:70-73 all reduce to this
+    for ``n >= out`` (the float form ``int(n/2 - out/2)`` truncates x.5 down).
+    """
+    return (n - out) // 2
+
+
+def center_crop_or_pad(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """Crop or zero-pad the last two axes about the centre (kspace.py:22-31)."""
+    h, w = img.shape[-2:]
+    canvas = np.zeros(img.shape[:-2] + (out_h, out_w), dtype=img.dtype)
+    keep_h, keep_w = min(h, out_h), min(w, out_w)
+    sh, sw = (h - keep_h) // 2, (w - keep_w) // 2
+    dh, dw = (out_h - keep_h) // 2, (out_w - keep_w) // 2
+    canvas[..., dh:dh + keep_h, dw:dw + keep_w] = img[..., sh:sh + keep_h, sw:sw + keep_w]
+    return canvas
+
+
+def center_crop(data: np.ndarray, shape: Tuple[int, int]) -> np.ndarray:
+    """fastMRI centre crop of the last two axes (transforms.py:45-67).
+
+    ValueError("Invalid shapes.") when the crop exceeds the data (:59-60).
+    """
+    if not (0 < shape[0] <= data.shape[-2] and 0 < shape[1] <= data.shape[-1]):
+        raise ValueError("Invalid shapes.")
+    r0 = crop_start(data.shape[-2], shape[0])
+    c0 = crop_start(data.shape[-1], shape[1])
+    return data[..., r0:r0 + shape[0], c0:c0 + shape[1]]
+
+
+def center_crop_im(im_3d: np.ndarray, crop_to_size: Sequence[int]) -> np.ndarray:
+    """Prostate centre crop of (slices, y, x) (ZIP!/fastmri_prostate/reconstruction/utils.py:54-73)."""
+    x0 = im_3d.shape[-1] / 2 - crop_to_size[0] / 2
+    y0 = im_3d.shape[-2] / 2 - crop_to_size[1] / 2
+    return im_3d[:, int(y0):int(crop_to_size[1] + y0), int(x0):int(crop_to_size[0] + x0)]
+
+
+# --------------------------------------------------------------------------
+# a5  root-sum-of-squares coil combine
+# --------------------------------------------------------------------------
+
+
+def rss(data: np.ndarray, dim: int = 0) -> np.ndarray:
+    """sqrt(sum(data**2, dim)) for REAL data (ZIP!/DL_reconstruction/coil_combine.py:12-25)."""
+    return np.sqrt((data ** 2).sum(axis=dim))
+
+
+def rss_complex_ri(data: np.ndarray, dim: int = 0) -> np.ndarray:
+    """RSS on the real-view layout (..., 2) (coil_combine.py:28-41)."""
+    return np.sqrt(complex_abs_sq_ri(data).sum(axis=dim))
+
+
+def rss_np(sig: np.ndarray, axis: int = -1) -> np.ndarray:
+    """sqrt(sum(|sig|^2, axis)) for complex numpy data
+    (ZIP!/fastmri_prostate/reconstruction/t2/prostate_t2_recon.py:105-121)."""
+    return np.sqrt(np.sum(np.abs(sig) ** 2, axis))
+
+
+# --------------------------------------------------------------------------
+# a7  normalisation                        ZIP!/DL_reconstruction/data/transforms.py:120-162
+# --------------------------------------------------------------------------
+
+
+def normalize(data, mean, stddev, eps=0.0):
+    """(data - mean) / (stddev + eps) (transforms.py:120-140)."""
+    return (data - mean) / (stddev + eps)
+
+
+def normalize_instance(data: np.ndarray, eps: float = 0.0):
+    """Instance normalise with torch semantics: ``std`` is UNBIASED (N-1)
+    (transforms.py:143-162: ``data.mean()``, ``data.std()``).
+
+    Returns (normalised, mean, std); float32 in -> float32 out.
+    """
+    mean = data.mean(dtype=data.dtype)
+    std = data.std(ddof=1, dtype=data.dtype)
+    return normalize(data, mean, std, data.dtype.type(eps)), mean, std
+
+
+# --------------------------------------------------------------------------
+# a8  fastMRI real-view centred transforms  ZIP!/DL_reconstruction/fftc.py:14-65,93-165
+# --------------------------------------------------------------------------
+
+
+def to_real_view(data: np.ndarray) -> np.ndarray:
+    """complex (...) -> real (..., 2) (``to_tensor``, transforms.py:14-29)."""
+    if np.iscomplexobj(data):
+        return np.stack((data.real, data.imag), axis=-1)
+    return data
+
+
+def _roll(x: np.ndarray, shifts: Sequence[int], dims: Sequence[int]) -> np.ndarray:
+    """fftc.py:69-115 -- roll built from two narrows and a cat, one dim at a time."""
+    if len(shifts) != len(dims):
+        raise ValueError("len(shift) must match len(dim)")
+    for s, d in zip(shifts, dims):
+        n = x.shape[d]
+        s %= n
+        if s:
+            head = np.take(x, range(0, n - s), axis=d)
+            tail = np.take(x, range(n - s, n), axis=d)
+            x = np.concatenate((tail, head), axis=d)
+    return x
+
+
+def _fftshift_ri(x, dims):   # fftc.py:118-140: shift n // 2
+    return _roll(x, [x.shape[d] // 2 for d in dims], dims)
+
+
+def _ifftshift_ri(x, dims):  # fftc.py:143-165: shift (n + 1) // 2
+    return _roll(x, [(x.shape[d] + 1) // 2 for d in dims], dims)
+
+
+def _c2ri(z: np.ndarray) -> np.ndarray:
+    return np.stack((z.real, z.imag), axis=-1)
+
+
+def ifft2c_new(data: np.ndarray) -> np.ndarray:
+    """Centred ortho inverse FFT on (..., H, W, 2) float data (fftc.py:41-65)."""
+    if data.shape[-1] != 2:
+        raise ValueError("Tensor does not have separate complex dim.")
+    data = _ifftshift_ri(data, [-3, -2])
+    z = data[..., 0] + 1j * data[..., 1]
+    z = np.fft.ifftn(z.astype(np.complex64, copy=False), axes=_AX, norm="ortho")
+    return _fftshift_ri(_c2ri(z).astype(data.dtype, copy=False), [-3, -2])
+
+
+def fft2c_new(data: np.ndarray) -> np.ndarray:
+    """Forward twin of :func:`ifft2c_new` (fftc.py:14-38)."""
+    if data.shape[-1] != 2:
+        raise ValueError("Tensor does not have separate complex dim.")
+    data = _ifftshift_ri(data, [-3, -2])
+    z = data[..., 0] + 1j * data[..., 1]
+    z = np.fft.fftn(z.astype(np.complex64, copy=False), axes=_AX, norm="ortho")
+    return _fftshift_ri(_c2ri(z).astype(data.dtype, copy=False), [-3, -2])
+
+
+# --------------------------------------------------------------------------
+# a9-a11  prostate T2 chain (GRAPPA excluded -- SURVEY.md section 8a row a11)
+# --------------------------------------------------------------------------
+
+
+def ifftnd(kspace: np.ndarray, axes: Optional[Sequence[int]] = (-1,)) -> np.ndarray:
+    """Centred inverse FFT scaled to orthonormal by ``* sqrt(prod(shape[axes]))``
+    (ZIP!/fastmri_prostate/reconstruction/utils.py:7-29)."""
+    if axes is None:
+        axes = range(kspace.ndim)
+    axes = list(axes)
+    img = np.fft.fftshift(np.fft.ifftn(np.fft.ifftshift(kspace, axes=axes), axes=axes), axes=axes)
+    img *= np.sqrt(np.prod(np.take(img.shape, axes)))
+    return img
+
+
+def create_coil_combined_im(k: np.ndarray) -> np.ndarray:
+    """(S, C, RO, PE) complex -> (S, RO, PE) float64: per slice ifftnd over
+    (RO, PE), RSS over coils, ``np.flipud`` (prostate_t2_recon.py:80-102)."""
+    out = np.zeros((k.shape[0], k.shape[2], k.shape[3]))
+    for s in range(out.shape[0]):
+        coil_imgs = ifftnd(k[s], [1, 2])
+        out[s] = np.flipud(rss_np(coil_imgs, axis=0))
+    return out
+
+
+def padding_lr(enc_x: int, max_pe_index: int) -> Tuple[int, int]:
+    """Phase-encode zero-pad rule from the ISMRMRD header numbers
+    (ZIP!/fastmri_prostate/data/mri_data.py:63-85 ``get_padding`` and :150-157):
+    ``p = (enc_x - (max_pe_index + 1)) / 2``; floor/ceil when ``p % 2 != 0``.
+    451 -> 640 gives (94, 95)."""
+    p = (enc_x - (max_pe_index + 1)) / 2
+    if p % 2 != 0:
+        return int(np.floor(p)), int(np.ceil(p))
+    return int(p), int(p)
+
+
+def zero_pad_pe(k: np.ndarray, left: int, right: int) -> np.ndarray:
+    """np.pad on the last (PE) axis of a 4-D array (mri_data.py:158)."""
+    return np.pad(k, ((0, 0), (0, 0), (0, 0), (left, right)))
+
+
+def t2_average_combine(kspace: np.ndarray, pad: Tuple[int, int],
+                       crop: Tuple[int, int] = (320, 320)) -> np.ndarray:
+    """(A, S, C, RO, PE) -> (S, crop, crop) float64 (prostate_t2_recon.py:65-75):
+    for each average pad -> coil-combine; mean over averages AFTER the RSS; crop."""
+    n_avg, n_sl, _, n_ro, _ = kspace.shape
+    im = np.zeros((n_avg, n_sl, n_ro, n_ro))
+    for a in range(n_avg):
+        im[a] = create_coil_combined_im(zero_pad_pe(kspace[a], pad[0], pad[1]))
+    return center_crop_im(np.mean(im, axis=0), list(crop))
+
+
+# --------------------------------------------------------------------------
+# a12  undersampling mask -- NOT IN THE REFERENCE (parity unpinned for generation)
+# --------------------------------------------------------------------------
+
+
+def equispaced_mask(width: int, acceleration: int, center_fraction: float,
+                    offset: int = 0) -> np.ndarray:
+    """Builder-defined equispaced mask (SURVEY.md section 8c last row):
+    every ``acceleration``-th column from ``offset`` plus a centred block of
+    ``round(width * center_fraction)`` low-frequency columns starting at
+    ``(width - n_low + 1) // 2``.  float32 0/1 vector of length ``width``."""
+    m = np.zeros(width, dtype=np.float32)
+    m[offset::acceleration] = 1.0
+    n_low = int(round(width * center_fraction))
+    lo = (width - n_low + 1) // 2
+    m[lo:lo + n_low] = 1.0
+    return m
+
+
+def apply_mask(kspace: np.ndarray, mask_w: Optional[np.ndarray]) -> np.ndarray:
+    """fastMRI convention: multiply by a vector broadcast along the last axis."""
+    if mask_w is None:
+        return kspace
+    return kspace * mask_w.astype(np.float32).reshape((1,) * (kspace.ndim - 1) + (-1,))
+
+
+# --------------------------------------------------------------------------
+# Compositions the CUDA path is checked against (the three chains of BASELINE.md section 3)
+# --------------------------------------------------------------------------
+
+
+def knee_chain_numpy(kspace: np.ndarray, mask_w: Optional[np.ndarray],
+                     crop: Tuple[int, int] = (320, 320), normalize_mode: Optional[str] = "instance",
+                     eps: float = 0.0):
+    """(…, C, H, W) c64 -> (…, oh, ow) f32 via the ``src/utils/kspace.py`` functions:
+    mask -> ifft2c -> complex_abs -> sqrt(sum^2 over coils) -> center_crop_or_pad
+    (-> normalize_instance).  Returns (image, mean, std); mean/std are None when
+    ``normalize_mode`` is None."""
+    img = complex_abs(ifft2c(apply_mask(kspace, mask_w)))
+    comb = np.sqrt((img ** 2).sum(axis=-3))
+    comb = center_crop_or_pad(comb, crop[0], crop[1]).astype(np.float32, copy=False)
+    if normalize_mode is None:
+        return comb, None, None
+    if comb.ndim == 2:
+        return normalize_instance(comb, eps)
+    outs = [normalize_instance(c, eps) for c in comb.reshape((-1,) + comb.shape[-2:])]
+    lead = comb.shape[:-2]
+    return (np.stack([o[0] for o in outs]).reshape(comb.shape),
+            np.array([o[1] for o in outs], dtype=np.float32).reshape(lead),
+            np.array([o[2] for o in outs], dtype=np.float32).reshape(lead))
+
+
+def knee_chain_fastmri(kspace: np.ndarray, mask_w: Optional[np.ndarray],
+                       crop: Tuple[int, int] = (320, 320), eps: float = 0.0):
+    """(C, H, W) c64 -> (oh, ow) f32 via the vendored fastMRI functions:
+    to_tensor -> mask -> ifft2c_new -> rss_complex -> center_crop -> normalize_instance."""
+    ri = to_real_view(apply_mask(kspace, mask_w)).astype(np.float32, copy=False)
+    comb = rss_complex_ri(ifft2c_new(ri), dim=0)
+    return normalize_instance(np.ascontiguousarray(center_crop(comb, crop)), eps)
+
+
+def prostate_chain(kspace: np.ndarray, mask_w: Optional[np.ndarray], pad: Tuple[int, int],
+                   crop: Tuple[int, int] = (320, 320)) -> np.ndarray:
+    """(A, S, C, RO, PE) c64 -> (S, oh, ow) f64: mask -> :func:`t2_average_combine`."""
+    return t2_average_combine(apply_mask(kspace, mask_w), pad, crop)
+
+
+def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
+    """||a-b||_2 / ||b||_2 in float64 -- the parity metric of BASELINE.json."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    wide = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    d = (a.astype(wide) - b.astype(wide)).ravel()
+    den = math.sqrt(float(np.vdot(b.astype(wide).ravel(), b.astype(wide).ravel()).real))
+    return math.sqrt(float(np.vdot(d, d).real)) / (den if den > 0 else 1.0)
