@@ -1,0 +1,142 @@
+/*
+ * mriacl_recon.h -- C ABI of libmriacl_recon.so, the B200 (sm_100a) k-space -> image
+ * input stage for bonhchi/mri_acl_imagesegmentation_adsp.
+ *
+ * The reference has no FFI layer: its operator API for this path is a set of plain
+ * Python functions.  Each entry point below names the
+ * reference function(s) it replaces; REF = the reference checkout, ZIP! = a member of
+ * REF/reference/fastMRI_prostate-main.zip.  The Python side
+ * (mri_acl_imagesegmentation_adsp_b200/adapters/recon_cabi.py) binds these with ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ or torch types cross the boundary.
+ *  - every data pointer is a DEVICE pointer on the current CUDA device unless the
+ *    parameter says HOST; the caller owns all buffers, including the workspace.
+ *  - complex64 = interleaved (re, im) float32, i.e. numpy complex64 / torch complex64 /
+ *    the fastMRI real view (..., 2) -- all byte-identical.
+ *  - all work is enqueued on `cuda_stream` (a cudaStream_t; NULL = legacy default
+ *    stream) and returns without synchronising.  Sampling masks are HOST vectors: the
+ *    library turns each distinct mask into a device-resident plan once and caches it.
+ *  - return value: MRIACL_OK (0) or a negative MRIACL_ERR_* code; the message is
+ *    available from mriacl_last_error() (thread-local).  No C++ exception escapes.
+ *  - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef MRIACL_RECON_H
+#define MRIACL_RECON_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRIACL_ABI_VERSION 1
+
+/* return codes */
+#define MRIACL_OK               0
+#define MRIACL_ERR_INVALID     -1   /* bad shape / argument  -> Python ValueError  */
+#define MRIACL_ERR_UNSUPPORTED -2   /* size outside plan limits -> ValueError       */
+#define MRIACL_ERR_CUDA        -3   /* CUDA runtime failure  -> RuntimeError        */
+#define MRIACL_ERR_WORKSPACE   -4   /* workspace too small   -> RuntimeError        */
+
+/* flags for mriacl_recon_rss_f32 */
+#define MRIACL_FLIP_ROWS      0x1u  /* np.flipud of each combined image (ZIP!/fastmri_prostate/reconstruction/t2/prostate_t2_recon.py:101) */
+#define MRIACL_NORM_INSTANCE  0x2u  /* (x-mean)/(std+eps), unbiased std (ZIP!/DL_reconstruction/data/transforms.py:143-162) */
+#define MRIACL_FORCE_GENERIC  0x4u  /* testing: use the generic (any-size) kernels even where a fused plan exists */
+
+/* path selector reported by mriacl_supported */
+#define MRIACL_PATH_NONE    0
+#define MRIACL_PATH_GENERIC 1
+#define MRIACL_PATH_FUSED   2
+
+int         mriacl_abi_version(void);
+const char* mriacl_last_error(void);
+
+/* Which kernels serve a (H, W_padded) transform: MRIACL_PATH_FUSED for the shapes with a
+ * hand-scheduled fused plan (640x368 knee, 640x640 padded prostate), MRIACL_PATH_GENERIC
+ * for any other size up to MRIACL_MAX_LINE per axis, MRIACL_PATH_NONE beyond that. */
+#define MRIACL_MAX_LINE 4096
+int mriacl_supported(int H, int W_padded);
+
+/* Number of kernels this library has launched in the calling process (all threads).
+ * bench.py reports the delta over its timed region as "gpu_launches". */
+uint64_t mriacl_launch_count(void);
+
+/*
+ * The fused stage:  mask apply -> zero-pad PE -> centred 2-D iFFT per coil -> RSS over
+ * coils -> [flipud] -> mean over averages -> centre crop -> [instance normalise].
+ *
+ * Replaces, in one call per batch, the chain the reference spells three ways:
+ *   REF/src/utils/kspace.py:11-31 (ifft2c, complex_abs, center_crop_or_pad) + sqrt(sum^2);
+ *   ZIP!/DL_reconstruction/fftc.py:41-65 (ifft2c_new), coil_combine.py:28-41 (rss_complex),
+ *        data/transforms.py:45-67 (center_crop), :143-162 (normalize_instance);
+ *   ZIP!/fastmri_prostate/reconstruction/t2/prostate_t2_recon.py:65-75,80-121 and
+ *        fastmri_prostate/data/mri_data.py:123-160 (zero_pad_kspace_hdr).
+ *
+ * kspace   complex64, logical shape [B, A, C, H, W]; element (b,a,c,h,w) lives at
+ *          b*slice_stride + a*avg_stride + (c*H + h)*W + w   (strides in complex elements;
+ *          knee batches: A=1, slice_stride=C*H*W; prostate files (A,S,C,RO,PE):
+ *          slice_stride=C*H*W, avg_stride=S*C*H*W).
+ * mask_w   HOST float32[W] multiplied along the last axis, or NULL for all ones.
+ *          Columns whose mask value is exactly 0 are skipped (treated as exact zeros).
+ * pad_left, W_padded   zero-pad the PE axis to W_padded with pad_left zeros on the left
+ *          (W_padded == W and pad_left == 0 for no padding).
+ * out      float32 [B, out_h, out_w]; out_h <= H, out_w <= W_padded (centre crop,
+ *          start (n-out)/2).  mean_std: float32 [B, 2] (mean, unbiased std of the
+ *          un-normalised crop) or NULL.
+ * workspace  device scratch of at least mriacl_recon_rss_workspace_bytes(.., slices=1)
+ *          bytes, 256-byte aligned; a larger one lets more slices be in flight per launch.
+ */
+size_t mriacl_recon_rss_workspace_bytes(int slices, int A, int C, int H, int W, int pad_left, int W_padded,
+                                        int out_h, int out_w, const float* mask_w_host, unsigned flags);
+
+int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long long avg_stride,
+                         const float* mask_w_host, float* out, float* mean_std,
+                         int B, int A, int C, int H, int W, int pad_left, int W_padded,
+                         int out_h, int out_w, unsigned flags, float eps,
+                         void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* |ifft2c(k)| as float32 for B single-coil (H, W) slices.
+ * Replaces MRIKneePreprocessor.ifft2c_single, REF/src/preprocess/mri_preprocess.py:149-160.
+ * workspace: B*H*W*8 bytes (complex scratch) unless (H, W) has a fused plan, where
+ * mriacl_recon_rss_workspace_bytes(B,1,1,H,W,0,W,H,W,NULL,0) applies. */
+size_t mriacl_ifft2c_abs_workspace_bytes(int B, int H, int W);
+int mriacl_ifft2c_abs_f32(const void* kspace_c64, float* out, int B, int H, int W,
+                          void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Centred orthonormal 2-D FFT (inverse != 0: iFFT) over the last two axes of [B, H, W]
+ * complex64, out of place or in place (in == out).
+ * Replaces fft2c / ifft2c, REF/src/utils/kspace.py:4-16; fft2c_new / ifft2c_new,
+ * ZIP!/DL_reconstruction/fftc.py:14-65; ifftnd over two axes,
+ * ZIP!/fastmri_prostate/reconstruction/utils.py:7-29. */
+int mriacl_fft2c_c64(const void* in_c64, void* out_c64, int B, int H, int W, int inverse, void* cuda_stream);
+
+/* |z| (squared == 0) or |z|^2 (squared != 0) of n complex64 values.
+ * Replaces complex_abs, REF/src/utils/kspace.py:18-20; complex_abs / complex_abs_sq,
+ * ZIP!/DL_reconstruction/math_fn.py:55-86. */
+int mriacl_complex_abs_f32(const void* in_c64, float* out, size_t n, int squared, void* cuda_stream);
+
+/* Root-sum-of-squares over the middle axis of [outer, C, inner]:
+ * is_complex == 0: float32 input (rss, ZIP!/DL_reconstruction/coil_combine.py:12-25);
+ * is_complex != 0: complex64 input (rss_complex :28-41; rss, prostate_t2_recon.py:105-121). */
+int mriacl_rss_f32(const void* in, float* out, size_t outer, int C, size_t inner, int is_complex, void* cuda_stream);
+
+/* Centre crop or zero-pad the last two axes of [B, H, W] to [B, out_h, out_w];
+ * elem_bytes is 4 (float32) or 8 (complex64).
+ * Replaces center_crop_or_pad, REF/src/utils/kspace.py:22-31 (and, for out <= in,
+ * center_crop transforms.py:45-67 / center_crop_im utils.py:54-73). */
+int mriacl_center_crop_or_pad(const void* in, void* out, int B, int H, int W, int out_h, int out_w,
+                              int elem_bytes, void* cuda_stream);
+
+/* Per-image instance normalisation of [B, n] float32: out = (in-mean)/(std+eps) with the
+ * UNBIASED std; mean_std [B,2] or NULL; in == out allowed.
+ * Replaces normalize_instance, ZIP!/DL_reconstruction/data/transforms.py:143-162. */
+int mriacl_normalize_instance_f32(const float* in, float* out, float* mean_std, int B, size_t n, float eps,
+                                  void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRIACL_RECON_H */

@@ -1,0 +1,162 @@
+// butterflies.cuh -- register-level DFT butterflies (natural-order in, natural-order out).
+//
+// INV = true computes X[m] = sum_n x[n] e^{+2 pi i n m / R} (the inverse-transform sign used by
+// the k-space -> image path); INV = false the forward sign.  No scaling is applied here.
+#pragma once
+#include <utility>
+#include "common.cuh"
+#include "dft_consts.h"
+
+namespace mriacl {
+
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+// compile-time loop: f(integral_constant<int, 0>) ... f(integral_constant<int, N-1>)
+template <int N, class F> __device__ __forceinline__ void static_for(F&& f) {
+  static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+
+#define MRIACL_SQRT1_2 0.70710678118654752440f
+
+template <bool INV> __device__ __forceinline__ void radix2(cf& a, cf& b) {
+  cf t = a; a = cadd(t, b); b = csub(t, b);
+}
+
+// 4-point DFT of (a0,a1,a2,a3) in place
+template <bool INV> __device__ __forceinline__ void radix4(cf& a0, cf& a1, cf& a2, cf& a3) {
+  cf t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_i<INV>(csub(a1, a3));
+  a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+
+// 8-point DFT, v[0..7] in place, natural order
+template <bool INV> __device__ __forceinline__ void radix8(cf* v) {
+  // even / odd 4-point transforms
+  radix4<INV>(v[0], v[2], v[4], v[6]);   // E[0..3] in v[0],v[2],v[4],v[6]
+  radix4<INV>(v[1], v[3], v[5], v[7]);   // O[0..3] in v[1],v[3],v[5],v[7]
+  // O[m] * w8^m
+  const float c = MRIACL_SQRT1_2;
+  cf o0 = v[1];
+  cf o1 = INV ? cf_make(c * (v[3].x - v[3].y), c * (v[3].x + v[3].y))
+              : cf_make(c * (v[3].x + v[3].y), c * (v[3].y - v[3].x));
+  cf o2 = mul_i<INV>(v[5]);
+  cf o3 = INV ? cf_make(-c * (v[7].x + v[7].y), c * (v[7].x - v[7].y))
+              : cf_make(c * (v[7].y - v[7].x), -c * (v[7].x + v[7].y));
+  cf e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+// 5-point DFT in place
+template <bool INV> __device__ __forceinline__ void radix5(cf& a0, cf& a1, cf& a2, cf& a3, cf& a4) {
+  constexpr float c1 = DftConsts<5>::c(1), c2 = DftConsts<5>::c(2);
+  constexpr float s1 = DftConsts<5>::s(1), s2 = DftConsts<5>::s(2);
+  cf p1 = cadd(a1, a4), p2 = cadd(a2, a3), d1 = csub(a1, a4), d2 = csub(a2, a3);
+  cf r1 = cf_make(fmaf(c2, p2.x, fmaf(c1, p1.x, a0.x)), fmaf(c2, p2.y, fmaf(c1, p1.y, a0.y)));
+  cf r2 = cf_make(fmaf(c1, p2.x, fmaf(c2, p1.x, a0.x)), fmaf(c1, p2.y, fmaf(c2, p1.y, a0.y)));
+  cf i1 = cf_make(fmaf(s2, d2.x, s1 * d1.x), fmaf(s2, d2.y, s1 * d1.y));
+  cf i2 = cf_make(fmaf(-s1, d2.x, s2 * d1.x), fmaf(-s1, d2.y, s2 * d1.y));
+  a0 = cadd(a0, cadd(p1, p2));
+  cf j1 = mul_i<INV>(i1), j2 = mul_i<INV>(i2);
+  a1 = cadd(r1, j1); a4 = csub(r1, j1);
+  a2 = cadd(r2, j2); a3 = csub(r2, j2);
+}
+
+// 10-point DFT, v[0..9] in place, natural order (2 x radix-5 + radix-2 recombination)
+template <bool INV> __device__ __forceinline__ void radix10(cf* v) {
+  radix5<INV>(v[0], v[2], v[4], v[6], v[8]);   // E[m] in v[2m]
+  radix5<INV>(v[1], v[3], v[5], v[7], v[9]);   // O[m] in v[2m+1]
+  cf e[5] = {v[0], v[2], v[4], v[6], v[8]};
+  cf o[5];
+  o[0] = v[1];
+  static_for<4>([&](auto mm) {
+    constexpr int m = mm.value + 1;
+    // w10^m = exp(+-2 pi i m / 10) = (cos, sin)(2 pi 2m/20); take it from the radix-5 table:
+    // cos(2 pi m/10) = -cos(2 pi (m+5)/10) and 2 pi m/10 = 2 pi (m * 3 mod 5)... keep literals instead
+    constexpr float cw[5] = {1.0f, 0.80901699437494742410f, 0.30901699437494742410f,
+                             -0.30901699437494742410f, -0.80901699437494742410f};
+    constexpr float sw[5] = {0.0f, 0.58778525229247312917f, 0.95105651629515357212f,
+                             0.95105651629515357212f, 0.58778525229247312917f};
+    cf w = cf_make(cw[m], INV ? sw[m] : -sw[m]);
+    o[m] = cmul(v[2 * m + 1], w);
+  });
+  static_for<5>([&](auto mm) {
+    constexpr int m = mm.value;
+    v[m] = cadd(e[m], o[m]);
+    v[m + 5] = csub(e[m], o[m]);
+  });
+}
+
+// 16-point DFT, v[0..15] in place, natural order (4 x 4)
+template <bool INV> __device__ __forceinline__ void fft16(cf* v) {
+  // step 1: for each b, 4-point DFT over a of v[4a + b]  -> u[b][c] stored at v[4c + b]
+  static_for<4>([&](auto bb) { constexpr int b = bb.value; radix4<INV>(v[b], v[4 + b], v[8 + b], v[12 + b]); });
+  // step 2: u[b][c] *= w16^{b c}
+  constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;  // cos, sin(pi/8)
+  constexpr float h = MRIACL_SQRT1_2;
+  constexpr float cw[10] = {1.f, c1, h, s1, 0.f, -s1, -h, -c1, -1.f, -c1};
+  constexpr float sw[10] = {0.f, s1, h, c1, 1.f, c1, h, s1, 0.f, -s1};
+  static_for<3>([&](auto bb) {
+    constexpr int b = bb.value + 1;
+    static_for<3>([&](auto cc) {
+      constexpr int c = cc.value + 1;
+      constexpr int e = b * c;  // 1..9
+      cf w = cf_make(cw[e], INV ? sw[e] : -sw[e]);
+      v[4 * c + b] = cmul(v[4 * c + b], w);
+    });
+  });
+  // step 3: for each c, 4-point DFT over b of v[4c + b] -> X[c + 4d] at v[4c + d]
+  static_for<4>([&](auto cc) { constexpr int c = cc.value; radix4<INV>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]); });
+  // v[4c + d] = X[c + 4d]  -> transpose the 4x4 to natural order
+  static_for<4>([&](auto cc) {
+    constexpr int c = cc.value;
+    static_for<4>([&](auto dd) {
+      constexpr int d = dd.value;
+      if constexpr (d > c) { cf t = v[4 * c + d]; v[4 * c + d] = v[4 * d + c]; v[4 * d + c] = t; }
+    });
+  });
+}
+
+// P-point DFT for odd P by the symmetric direct method:
+//   a_n = x[n] + x[P-n], b_n = x[n] - x[P-n]  (n = 1..(P-1)/2)
+//   X[k], X[P-k] = x0 + sum a_n cos(2 pi n k/P)  +-  i sum b_n sin(2 pi n k/P)
+// ~ (P-1)^2 real FMAs with immediate constants.  Results are handed to emit(k, X[k]) as they
+// are produced so the caller can twiddle and store without keeping all P outputs live.
+template <int P, bool INV, class Emit>
+__device__ __forceinline__ void dft_odd_sym(const cf* x, Emit&& emit) {
+  constexpr int Hh = (P - 1) / 2;
+  cf a[Hh], b[Hh];
+  const cf x0 = x[0];
+  static_for<Hh>([&](auto nn) {
+    constexpr int n = nn.value + 1;
+    a[n - 1] = cadd(x[n], x[P - n]);
+    b[n - 1] = csub(x[n], x[P - n]);
+  });
+  {
+    cf s = x0;
+    static_for<Hh>([&](auto nn) { s = cadd(s, a[nn.value]); });
+    emit(std::integral_constant<int, 0>{}, s);
+  }
+  static_for<Hh>([&](auto kk) {
+    constexpr int k = kk.value + 1;
+    float ar = x0.x, ai = x0.y, br = 0.f, bi = 0.f;
+    static_for<Hh>([&](auto nn) {
+      constexpr int n = nn.value + 1;
+      constexpr float c = DftConsts<P>::c((n * k) % P);
+      constexpr float s = DftConsts<P>::s((n * k) % P);
+      ar = fmaf(a[n - 1].x, c, ar);
+      ai = fmaf(a[n - 1].y, c, ai);
+      br = fmaf(b[n - 1].x, s, br);
+      bi = fmaf(b[n - 1].y, s, bi);
+    });
+    // A + iB and A - iB
+    cf plus = cf_make(ar - bi, ai + br), minus = cf_make(ar + bi, ai - br);
+    emit(std::integral_constant<int, k>{}, INV ? plus : minus);
+    emit(std::integral_constant<int, P - k>{}, INV ? minus : plus);
+  });
+}
+
+}  // namespace mriacl

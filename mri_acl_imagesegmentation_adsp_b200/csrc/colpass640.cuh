@@ -1,0 +1,158 @@
+// colpass640.cuh -- fused column pass of the k-space -> image stage for H = 640.
+//
+// One work item = (frame, group of <= 8 sampled phase-encode columns).  The CTA gathers the
+// group's columns from all 640 readout rows of complex64 k-space (the only HBM read of the
+// path; every 32-byte sector of a row that holds a sampled column is touched exactly once),
+// multiplies by the mask value, and runs the 640-point inverse DFT of each column in shared
+// memory as three in-place decimation-in-frequency passes 8 x 8 x 10:
+//
+//   n = 80 n1 + 10 n2 + n3   ->   m = m1 + 8 m2 + 64 m3
+//   pass 1: radix-8 over n1, twiddle w640^{(10 n2 + n3) m1}
+//   pass 2: radix-8 over n2, twiddle w80^{n3 m2}
+//   pass 3: radix-10 over n3, results leave in natural order m
+//
+// The input ifftshift is the load index map (physical row h -> logical n = (h - 320) mod 640),
+// the output fftshift + centre crop + optional flipud is the store index map, so neither shift
+// moves data.  Only the out_h kept rows are written, to the intermediate T[frame][j][row]
+// (row-contiguous, so the row pass reads it coalesced with lane = row).
+//
+// Shared-memory layout per column: slot(m1, m2, n3) = 90 m1 + 10 m2 + n3 (each block of 80 is
+// padded to 90) and column pitch 722 complex.  With it pass 1 (lanes over 10 n2 + n3), pass 2
+// (lanes over 10 m1 + n3), the gather store (lanes = 8 columns x 4 rows) and pass 3's 128-bit
+// loads (lanes over m1, then m2) are all free of bank conflicts; see DESIGN.md.
+#pragma once
+#include "butterflies.cuh"
+
+namespace mriacl {
+
+constexpr int CP_N = 640;        // transform length
+constexpr int CP_T = 160;        // threads per CTA: 2 column subsets x 80 butterfly positions
+constexpr int CP_G = 8;          // columns per work item
+constexpr int CP_BLK = 90;       // padded size of one n1/m1 block of 80
+constexpr int CP_PITCH = 722;    // complex elements between columns in shared memory (== 2 mod 16)
+constexpr int CP_SMEM_BYTES = CP_G * CP_PITCH * 8;
+
+struct ColPassParams {
+  const cf* ksp;                 // k-space, element (b,a,c,h,w) at b*sb + a*sa + (c*H + h)*W + w
+  long long sb, sa;
+  int A, C, W;
+  const int* act_w;              // [n_act] physical (unpadded) column of active column j
+  const float* act_m;            // [n_act] mask value of active column j
+  int n_act;
+  int n_groups;                  // ceil(n_act / 8)
+  const cf* tw;                  // w640^k = exp(+2 pi i k / 640)
+  cf* T;                         // [n_frames][n_act][oh]
+  int oh, row0, flip;
+  int frame0;                    // first global frame of this launch (f = (b*A + a)*C + c)
+  int n_frames;
+};
+
+__device__ __forceinline__ int cp_slot(int i) {   // logical index 0..639 -> padded slot
+  const int blk = i / 80;
+  return i + blk * (CP_BLK - 80);
+}
+
+__global__ void __launch_bounds__(CP_T, 4) colpass640_kernel(ColPassParams p) {
+  MRIACL_DYN_SMEM(cf, sm);
+  const int tid = threadIdx.x;
+  const int sub = tid / 80, pos = tid - sub * 80;
+
+  // twiddles depend only on the butterfly position: keep them in registers across items
+  cf tw1[8], tw2[8];
+  const int base2 = (pos / 10) * CP_BLK + (pos % 10);     // pass 2: (m1, n3) = (pos/10, pos%10)
+  {
+    const int n3 = pos % 10;
+#pragma unroll
+    for (int m = 1; m < 8; ++m) {
+      tw1[m] = p.tw[(pos * m) % CP_N];
+      tw2[m] = p.tw[(8 * n3 * m) % CP_N];
+    }
+  }
+  // pass 3: thread r < 64 owns (m1, m2) = (r % 8, r / 8)
+  const int sub3 = tid / 64, r3 = tid - sub3 * 64;
+  const int base3 = (r3 % 8) * CP_BLK + (r3 / 8) * 10;
+
+  const int k_ld = tid & 7, h_ld = tid >> 3;               // gather: 8 columns x 20 rows per sweep
+  const int n_items = p.n_frames * p.n_groups;
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int fl = item / p.n_groups, g = item - fl * p.n_groups;
+    const int f = p.frame0 + fl;
+    const int b = f / (p.A * p.C), a = (f / p.C) % p.A, c = f % p.C;
+    const cf* frame = p.ksp + b * p.sb + a * p.sa + (long long)c * CP_N * p.W;
+    const int j0 = g * CP_G;
+    const int ncols = min(CP_G, p.n_act - j0);
+
+    // ---- gather + mask ---------------------------------------------------------------
+    if (k_ld < ncols) {
+      const int w = p.act_w[j0 + k_ld];
+      const float mv = p.act_m[j0 + k_ld];
+      const cf* src = frame + w;
+      cf* dst = sm + k_ld * CP_PITCH;
+#pragma unroll
+      for (int it = 0; it < 32; it += 8) {
+        cf v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ld_stream(src + (long long)((it + u) * 20 + h_ld) * p.W);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int h = (it + u) * 20 + h_ld;
+          dst[cp_slot(logical_of_phys(h, CP_N))] = cscale(v[u], mv);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- pass 1: radix-8 over n1 (stride 90), twiddle w640^{pos * m1} ---------------------
+    for (int k = sub; k < ncols; k += 2) {
+      cf* col = sm + k * CP_PITCH + pos;
+      cf v[8];
+#pragma unroll
+      for (int n1 = 0; n1 < 8; ++n1) v[n1] = col[n1 * CP_BLK];
+      radix8<true>(v);
+      col[0] = v[0];
+#pragma unroll
+      for (int m1 = 1; m1 < 8; ++m1) col[m1 * CP_BLK] = cmul(v[m1], tw1[m1]);
+    }
+    __syncthreads();
+
+    // ---- pass 2: radix-8 over n2 (stride 10), twiddle w80^{n3 * m2} -----------------------
+    for (int k = sub; k < ncols; k += 2) {
+      cf* col = sm + k * CP_PITCH + base2;
+      cf v[8];
+#pragma unroll
+      for (int n2 = 0; n2 < 8; ++n2) v[n2] = col[n2 * 10];
+      radix8<true>(v);
+      col[0] = v[0];
+#pragma unroll
+      for (int m2 = 1; m2 < 8; ++m2) col[m2 * 10] = cmul(v[m2], tw2[m2]);
+    }
+    __syncthreads();
+
+    // ---- pass 3: radix-10 over n3 (contiguous), crop/shift/flip on the way out ------------
+    if (tid < 128) {
+      for (int k = sub3; k < ncols; k += 2) {
+        const float4* col4 = reinterpret_cast<const float4*>(sm + k * CP_PITCH + base3);
+        cf v[10];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const float4 t = col4[q];
+          v[2 * q] = cf_make(t.x, t.y);
+          v[2 * q + 1] = cf_make(t.z, t.w);
+        }
+        radix10<true>(v);
+        cf* dst = p.T + ((long long)fl * p.n_act + j0 + k) * p.oh;
+#pragma unroll
+        for (int m3 = 0; m3 < 10; ++m3) {
+          const int m = r3 + 64 * m3;
+          const int rfull = phys_of_logical(m, CP_N);
+          const int rr = (p.flip ? CP_N - 1 - rfull : rfull) - p.row0;
+          if (rr >= 0 && rr < p.oh) dst[rr] = v[m3];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mriacl

@@ -1,0 +1,56 @@
+// common.cuh -- shared device helpers for libmriacl_recon (sm_100a).
+//
+// The kernel headers compile in two modes: under nvcc for the product library, and under
+// g++ with tests/emu/cuda_emu.h pre-included (MRIACL_EMU) for the CPU emulation tests that
+// check index maps and plans in the GPU-less build container.  The emulation is test
+// infrastructure; the product library has no CPU path.
+#pragma once
+
+#ifndef MRIACL_EMU
+#include <cuda_runtime.h>
+#define MRIACL_DYN_SMEM(type, name)                                        \
+  extern __shared__ __align__(16) unsigned char mriacl_dyn_smem_raw[];     \
+  type* name = reinterpret_cast<type*>(mriacl_dyn_smem_raw)
+#endif
+
+namespace mriacl {
+
+typedef float2 cf;  // complex64: x = re, y = im
+
+__device__ __forceinline__ cf cf_make(float re, float im) { return make_float2(re, im); }
+__device__ __forceinline__ cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cf cmul(cf a, cf b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// a * conj(b)
+__device__ __forceinline__ cf cmulc(cf a, cf b) {
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ cf cscale(cf a, float s) { return make_float2(a.x * s, a.y * s); }
+// multiply by +i (INV) or -i (!INV)
+template <bool INV> __device__ __forceinline__ cf mul_i(cf a) {
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+__device__ __forceinline__ float cnorm2(cf a) { return fmaf(a.x, a.x, a.y * a.y); }
+// acc + |a|^2
+__device__ __forceinline__ float cnorm2_acc(cf a, float acc) { return fmaf(a.x, a.x, fmaf(a.y, a.y, acc)); }
+
+// Streaming 8-byte global load: k-space is read exactly once, keep it out of L1.
+__device__ __forceinline__ cf ld_stream(const cf* p) {
+#if defined(MRIACL_EMU)
+  return *p;
+#else
+  cf v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+#endif
+}
+
+// physical index of logical (un-shifted) FFT index i, and back, for a centred transform
+// of length n:  ifftshift(x)[i] = x[(i + n/2) % n]  and  fftshift(y)[(m + n/2) % n] = y[m]
+// (np.fft.ifftshift / fftshift, REF/src/utils/kspace.py:6-8,13-15).
+__host__ __device__ __forceinline__ int phys_of_logical(int i, int n) { int p = i + n / 2; return p >= n ? p - n : p; }
+__host__ __device__ __forceinline__ int logical_of_phys(int p, int n) { int i = p - n / 2; return i < 0 ? i + n : i; }
+
+}  // namespace mriacl

@@ -1,0 +1,428 @@
+// mriacl_recon.cu -- C ABI of libmriacl_recon.so (see include/mriacl_recon.h) and the host
+// orchestration of the kernels.  Built for sm_100a only; no cuFFT, no CPU fallback.
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/mriacl_recon.h"
+#include "common.cuh"
+#include "rt.h"
+#include "plan.h"
+#include "generic_kernels.cuh"
+#include "colpass640.cuh"
+#include "rowpass.cuh"
+
+using namespace mriacl;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+std::mutex g_mu;
+
+// ---- per-device facts ----------------------------------------------------------------
+struct DeviceInfo { int sms = 0; bool smem_set = false; };
+std::map<int, DeviceInfo> g_dev;
+
+int device_sms(int dev) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceInfo& d = g_dev[dev];
+  if (!d.sms) d.sms = rt_sm_count(dev);
+  return d.sms;
+}
+
+constexpr int FUSED_P = 23, FUSED_Q = 16;
+constexpr int GEN_SMEM_BYTES = 2 * MRIACL_GEN_SMEM_ELEMS * 8;
+
+int ensure_smem_attrs(int dev) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceInfo& d = g_dev[dev];
+  if (d.smem_set) return 0;
+  int bad = 0;
+  bad |= rt_allow_smem((const void*)generic_fft_kernel, GEN_SMEM_BYTES);
+  bad |= rt_allow_smem((const void*)colpass640_kernel, CP_SMEM_BYTES);
+  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q>, 200 * 1024);
+  if (!bad) d.smem_set = true;
+  return bad;
+}
+
+// ---- device-resident tables, built once and cached -------------------------------------
+struct DeviceBuf {
+  void* p = nullptr;
+  ~DeviceBuf() { /* lives for the process; the driver reclaims at exit */ }
+};
+
+// forward twiddles w_N^k = exp(-2 pi i k/N) for the generic kernel, and inverse-sign tables
+// for the fused kernels; key = (device, N, sign)
+std::map<std::tuple<int, int, int>, cf*> g_tw;
+
+cf* get_twiddles(int dev, int n, int sign) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto key = std::make_tuple(dev, n, sign);
+  auto it = g_tw.find(key);
+  if (it != g_tw.end()) return it->second;
+  std::vector<HostCf> t = make_twiddles(n, sign);
+  void* d = nullptr;
+  if (rt_malloc(&d, sizeof(HostCf) * n) || rt_upload(d, t.data(), sizeof(HostCf) * n)) return nullptr;
+  g_tw[key] = (cf*)d;
+  return (cf*)d;
+}
+
+struct MaskDev { std::vector<float> host; float* dev = nullptr; };
+std::map<std::pair<int, uint64_t>, std::vector<MaskDev>> g_masks;
+
+// device copy of a host mask (generic path); nullptr mask -> nullptr
+int get_device_mask(int dev, const float* mask, int w, const float** out) {
+  *out = nullptr;
+  if (!mask) return 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int dims[1] = {w};
+  auto& bucket = g_masks[{dev, plan_key(dims, 1, mask, w)}];
+  for (auto& m : bucket)
+    if ((int)m.host.size() == w && !memcmp(m.host.data(), mask, sizeof(float) * w)) { *out = m.dev; return 0; }
+  MaskDev m;
+  m.host.assign(mask, mask + w);
+  void* d = nullptr;
+  if (rt_malloc(&d, sizeof(float) * w) || rt_upload(d, mask, sizeof(float) * w)) return 1;
+  m.dev = (float*)d;
+  bucket.push_back(m);
+  *out = m.dev;
+  return 0;
+}
+
+struct FusedPlanDev {
+  FusedPlanHost host;
+  std::vector<float> mask_copy;
+  bool has_mask = false;
+  int* act_w = nullptr;
+  float* act_m = nullptr;
+  int* sched = nullptr;
+  cf* twH = nullptr;
+  cf* twW = nullptr;
+};
+std::map<std::pair<int, uint64_t>, std::vector<std::shared_ptr<FusedPlanDev>>> g_fused;
+
+std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left, int Wp, int oh, int ow,
+                                             const float* mask, bool device_side) {
+  const int dims[6] = {H, W, pad_left, Wp, oh, ow};
+  const uint64_t key = plan_key(dims, 6, mask, W);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& pl : g_fused[{dev, key}]) {
+      const FusedPlanHost& h = pl->host;
+      if (h.H == H && h.W == W && h.pad_left == pad_left && h.Wp == Wp && h.oh == oh && h.ow == ow &&
+          pl->has_mask == (mask != nullptr) &&
+          (!mask || !memcmp(pl->mask_copy.data(), mask, sizeof(float) * W)) && (pl->act_w || !device_side))
+        return pl;
+    }
+  }
+  auto pl = std::make_shared<FusedPlanDev>();
+  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, FUSED_P, FUSED_Q, RP_NW, RP_MAX_SPARSE, pl->host);
+  pl->has_mask = mask != nullptr;
+  if (mask) pl->mask_copy.assign(mask, mask + W);
+  if (device_side) {
+    const FusedPlanHost& h = pl->host;
+    void *a = nullptr, *m = nullptr, *s = nullptr;
+    const size_t na = h.act_w.size();
+    if (rt_malloc(&a, sizeof(int) * na) || rt_malloc(&m, sizeof(float) * na) || rt_malloc(&s, sizeof(int) * h.sched.size()))
+      return nullptr;
+    if (na && (rt_upload(a, h.act_w.data(), sizeof(int) * na) || rt_upload(m, h.act_m.data(), sizeof(float) * na)))
+      return nullptr;
+    if (rt_upload(s, h.sched.data(), sizeof(int) * h.sched.size())) return nullptr;
+    pl->act_w = (int*)a; pl->act_m = (float*)m; pl->sched = (int*)s;
+    pl->twH = get_twiddles(dev, H, +1);
+    pl->twW = get_twiddles(dev, Wp, +1);
+    if (!pl->twH || !pl->twW) return nullptr;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_fused[{dev, key}].push_back(pl);
+  return pl;
+}
+
+bool fused_shape(int H, int Wp) { return H == CP_N && Wp == FUSED_P * FUSED_Q; }
+
+struct ReconGeom {
+  bool fused;
+  int n_act, n_tiles;
+  size_t per_slice;     // workspace bytes per slice in flight
+  size_t t_bytes;       // intermediate bytes per slice
+};
+
+int recon_geom(int A, int C, int H, int W, int pad_left, int Wp, int oh, int ow, const float* mask,
+               unsigned flags, ReconGeom& g) {
+  g.fused = fused_shape(H, Wp) && !(flags & MRIACL_FORCE_GENERIC);
+  g.n_tiles = (oh + RP_ROWS - 1) / RP_ROWS;
+  if (g.fused) {
+    int n_act = 0;
+    for (int w = 0; w < W; ++w) n_act += (!mask || mask[w] != 0.0f) ? 1 : 0;
+    g.n_act = n_act;
+    g.t_bytes = align_up((size_t)A * C * (size_t)(n_act > 0 ? n_act : 1) * oh * sizeof(cf), 256);
+    g.per_slice = g.t_bytes + align_up((size_t)g.n_tiles * 3 * sizeof(float), 256);
+  } else {
+    g.n_act = W;
+    g.t_bytes = align_up((size_t)A * C * H * Wp * sizeof(cf), 256);
+    g.per_slice = g.t_bytes;
+  }
+  return 0;
+}
+
+int validate_recon(int B, int A, int C, int H, int W, int pad_left, int Wp, int oh, int ow) {
+  if (B < 0 || A < 1 || C < 1 || H < 1 || W < 1) return fail(MRIACL_ERR_INVALID, "bad dims B=%d A=%d C=%d H=%d W=%d", B, A, C, H, W);
+  if (pad_left < 0 || Wp < W + pad_left) return fail(MRIACL_ERR_INVALID, "W_padded=%d < W=%d + pad_left=%d", Wp, W, pad_left);
+  if (oh < 1 || ow < 1 || oh > H || ow > Wp) return fail(MRIACL_ERR_INVALID, "Invalid shapes: crop %dx%d of %dx%d", oh, ow, H, Wp);
+  if (H > MRIACL_MAX_LINE || Wp > MRIACL_MAX_LINE) return fail(MRIACL_ERR_UNSUPPORTED, "line length above %d", MRIACL_MAX_LINE);
+  return 0;
+}
+
+// one generic centred 1-D pass over [n_frames] frames
+int launch_generic_pass(GenFftParams gp, int dev, rt_stream_t st) {
+  std::vector<int> rad = generic_radices(gp.N);
+  if ((int)rad.size() > MRIACL_GEN_MAX_STAGES) return fail(MRIACL_ERR_UNSUPPORTED, "too many FFT stages for N=%d", gp.N);
+  gp.n_stages = (int)rad.size();
+  for (int i = 0; i < gp.n_stages; ++i) gp.radix[i] = rad[i];
+  gp.tw = get_twiddles(dev, gp.N, -1);
+  if (!gp.tw) return fail(MRIACL_ERR_CUDA, "twiddle table allocation failed: %s", rt_last_error_string());
+  int L = MRIACL_GEN_SMEM_ELEMS / gp.N;
+  L = L < 1 ? 1 : (L > 8 ? 8 : L);
+  if (L > gp.lines_per_frame) L = gp.lines_per_frame;
+  gp.lines_per_block = L;
+  const int blocks = ((gp.lines_per_frame + L - 1) / L) * gp.n_frames;
+  if (blocks == 0) return 0;
+  const size_t smem = (size_t)2 * L * gp.N * sizeof(cf);
+  MRIACL_LAUNCH(generic_fft_kernel, blocks, MRIACL_GEN_THREADS, smem, st, gp);
+  return 0;
+}
+
+// centred 2-D transform of n_frames frames [H][W(+pad)] -> out [n_frames][H][Wp]
+int generic_fft2c(const cf* in, long long sb, long long sa, int A, int C, cf* out, int n_frames, int H, int W,
+                  int pad_left, int Wp, const float* mask_dev, int inverse, int dev, rt_stream_t st) {
+  GenFftParams r{};
+  r.in = in; r.out = out; r.mask = mask_dev;
+  r.N = Wp; r.in_len = W; r.in_pad = pad_left;
+  r.lines_per_frame = H; r.n_frames = n_frames; r.lines_contig = 0;
+  r.in_es = 1; r.in_ls = W; r.in_sb = sb; r.in_sa = sa; r.in_sc = (long long)H * W; r.A = A; r.C = C;
+  r.out_es = 1; r.out_ls = Wp; r.out_fs = (long long)H * Wp;
+  r.inverse = inverse; r.scale = (float)(1.0 / std::sqrt((double)Wp));
+  if (int rc = launch_generic_pass(r, dev, st)) return rc;
+  GenFftParams c{};
+  c.in = out; c.out = out; c.mask = nullptr;
+  c.N = H; c.in_len = H; c.in_pad = 0;
+  c.lines_per_frame = Wp; c.n_frames = n_frames; c.lines_contig = 1;
+  c.in_es = Wp; c.in_ls = 1; c.in_sb = (long long)H * Wp; c.in_sa = 0; c.in_sc = 0; c.A = 1; c.C = 1;
+  c.out_es = Wp; c.out_ls = 1; c.out_fs = (long long)H * Wp;
+  c.inverse = inverse; c.scale = (float)(1.0 / std::sqrt((double)H));
+  return launch_generic_pass(c, dev, st);
+}
+
+int grid_for(long long work_items, int per_block) {
+  long long g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  return (int)g;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int mriacl_abi_version(void) { return MRIACL_ABI_VERSION; }
+const char* mriacl_last_error(void) { return g_err.c_str(); }
+uint64_t mriacl_launch_count(void) { return launch_counter().load(); }
+
+int mriacl_supported(int H, int W_padded) {
+  if (H < 1 || W_padded < 1 || H > MRIACL_MAX_LINE || W_padded > MRIACL_MAX_LINE) return MRIACL_PATH_NONE;
+  return fused_shape(H, W_padded) ? MRIACL_PATH_FUSED : MRIACL_PATH_GENERIC;
+}
+
+size_t mriacl_recon_rss_workspace_bytes(int slices, int A, int C, int H, int W, int pad_left, int W_padded,
+                                        int out_h, int out_w, const float* mask_w_host, unsigned flags) {
+  if (slices < 1) slices = 1;
+  if (validate_recon(slices, A, C, H, W, pad_left, W_padded, out_h, out_w)) return 0;
+  ReconGeom g;
+  recon_geom(A, C, H, W, pad_left, W_padded, out_h, out_w, mask_w_host, flags, g);
+  return g.per_slice * (size_t)slices;
+}
+
+int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long long avg_stride,
+                         const float* mask_w_host, float* out, float* mean_std,
+                         int B, int A, int C, int H, int W, int pad_left, int W_padded,
+                         int out_h, int out_w, unsigned flags, float eps,
+                         void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  const int Wp = W_padded, oh = out_h, ow = out_w;
+  if (int rc = validate_recon(B, A, C, H, W, pad_left, Wp, oh, ow)) return rc;
+  if (B == 0) return MRIACL_OK;
+  if (!kspace_c64 || !out || !workspace) return fail(MRIACL_ERR_INVALID, "null kspace/out/workspace pointer");
+  const int dev = rt_device();
+  if (dev < 0) return fail(MRIACL_ERR_CUDA, "no CUDA device: %s", rt_last_error_string());
+  if (ensure_smem_attrs(dev)) return fail(MRIACL_ERR_CUDA, "cudaFuncSetAttribute failed: %s", rt_last_error_string());
+  rt_stream_t st = (rt_stream_t)cuda_stream;
+  const int sms = device_sms(dev);
+
+  ReconGeom g;
+  recon_geom(A, C, H, W, pad_left, Wp, oh, ow, mask_w_host, flags, g);
+  if (workspace_bytes < g.per_slice)
+    return fail(MRIACL_ERR_WORKSPACE, "workspace %zu B < %zu B needed for one slice", workspace_bytes, g.per_slice);
+  int chunk = (int)std::min<size_t>((size_t)B, workspace_bytes / g.per_slice);
+  const cf* ksp = (const cf*)kspace_c64;
+  const int row0 = crop_start(H, oh), col0 = crop_start(Wp, ow);
+  const bool want_norm = (flags & MRIACL_NORM_INSTANCE) != 0;
+  const int flip = (flags & MRIACL_FLIP_ROWS) ? 1 : 0;
+
+  if (g.fused) {
+    std::shared_ptr<FusedPlanDev> pl = get_fused_plan(dev, H, W, pad_left, Wp, oh, ow, mask_w_host, true);
+    if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
+    const int n_act = (int)pl->host.act_w.size();
+    const int n_groups = (n_act + CP_G - 1) / CP_G;
+    const int rp_smem = rowpass_smem_bytes<FUSED_P, FUSED_Q>(ow, A);
+    if (rp_smem > 200 * 1024) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (ow=%d)", ow);
+    for (int s0 = 0; s0 < B; s0 += chunk) {
+      const int ns = std::min(chunk, B - s0);
+      cf* T = (cf*)workspace;
+      float* partials = (float*)((char*)workspace + g.t_bytes * (size_t)ns);
+      if (n_groups > 0) {
+        ColPassParams cp{};
+        cp.ksp = ksp; cp.sb = slice_stride; cp.sa = avg_stride; cp.A = A; cp.C = C; cp.W = W;
+        cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.n_act = n_act; cp.n_groups = n_groups;
+        cp.tw = pl->twH; cp.T = T; cp.oh = oh; cp.row0 = row0; cp.flip = flip;
+        cp.frame0 = s0 * A * C; cp.n_frames = ns * A * C;
+        const long long items = (long long)cp.n_frames * n_groups;
+        const int grid = (int)std::min<long long>(items, (long long)sms * 4);
+        MRIACL_LAUNCH(colpass640_kernel, grid, CP_T, CP_SMEM_BYTES, st, cp);
+      }
+      RowPassParams rp{};
+      rp.T = T; rp.n_act = n_act; rp.oh = oh; rp.sched = pl->sched; rp.tw = pl->twW;
+      rp.out = out + (size_t)s0 * oh * ow; rp.partials = partials; rp.ow = ow; rp.col0 = col0;
+      rp.A = A; rp.C = C; rp.scale = (float)(1.0 / std::sqrt((double)H * (double)Wp));
+      rp.n_slices = ns; rp.n_tiles = g.n_tiles;
+      {
+        const int items = ns * g.n_tiles;
+        const int per_sm = rp_smem > 110 * 1024 ? 1 : 2;
+        const int grid = std::min(items, sms * per_sm);
+        auto kfn = rowpass_kernel<FUSED_P, FUSED_Q>;
+        MRIACL_LAUNCH(kfn, grid, RP_T, rp_smem, st, rp);
+      }
+      if (want_norm || mean_std) {
+        NormParams np{};
+        np.in = rp.out; np.out = rp.out; np.mean_std = mean_std ? mean_std + 2 * (size_t)s0 : nullptr;
+        np.partials = partials; np.n_part = g.n_tiles; np.n = (long long)oh * ow; np.eps = eps;
+        np.normalize = want_norm ? 1 : 0;
+        MRIACL_LAUNCH(normalize_instance_kernel, ns, 512, 0, st, np);
+      }
+    }
+  } else {
+    const float* mask_dev = nullptr;
+    if (get_device_mask(dev, mask_w_host, W, &mask_dev)) return fail(MRIACL_ERR_CUDA, "mask upload failed: %s", rt_last_error_string());
+    for (int s0 = 0; s0 < B; s0 += chunk) {
+      const int ns = std::min(chunk, B - s0);
+      cf* img = (cf*)workspace;
+      if (int rc = generic_fft2c(ksp + (long long)s0 * slice_stride, slice_stride, avg_stride, A, C, img, ns * A * C,
+                                 H, W, pad_left, Wp, mask_dev, 1, dev, st)) return rc;
+      RssCropParams rc{};
+      rc.img = img; rc.out = out + (size_t)s0 * oh * ow; rc.n_slices = ns; rc.A = A; rc.C = C; rc.H = H; rc.Wp = Wp;
+      rc.oh = oh; rc.ow = ow; rc.row0 = row0; rc.col0 = col0; rc.flip = flip;
+      MRIACL_LAUNCH(rss_crop_kernel, grid_for((long long)ns * oh * ow, 256), 256, 0, st, rc);
+      if (want_norm || mean_std) {
+        NormParams np{};
+        np.in = rc.out; np.out = rc.out; np.mean_std = mean_std ? mean_std + 2 * (size_t)s0 : nullptr;
+        np.partials = nullptr; np.n_part = 0; np.n = (long long)oh * ow; np.eps = eps; np.normalize = want_norm ? 1 : 0;
+        MRIACL_LAUNCH(normalize_instance_kernel, ns, 512, 0, st, np);
+      }
+    }
+  }
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+}
+
+size_t mriacl_ifft2c_abs_workspace_bytes(int B, int H, int W) {
+  if (B < 1) B = 1;
+  if (H < 1 || W < 1) return 0;
+  if (fused_shape(H, W)) return mriacl_recon_rss_workspace_bytes(B, 1, 1, H, W, 0, W, H, W, nullptr, 0);
+  return align_up((size_t)B * H * W * sizeof(cf), 256);
+}
+
+int mriacl_ifft2c_abs_f32(const void* kspace_c64, float* out, int B, int H, int W,
+                          void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (B < 0 || H < 1 || W < 1) return fail(MRIACL_ERR_INVALID, "bad dims B=%d H=%d W=%d", B, H, W);
+  if (B == 0) return MRIACL_OK;
+  // RSS over a single coil is the magnitude: reuse the fused stage without crop or normalisation
+  return mriacl_recon_rss_f32(kspace_c64, (long long)H * W, 0, nullptr, out, nullptr, B, 1, 1, H, W, 0, W, H, W,
+                              0u, 0.f, workspace, workspace_bytes, cuda_stream);
+}
+
+int mriacl_fft2c_c64(const void* in_c64, void* out_c64, int B, int H, int W, int inverse, void* cuda_stream) {
+  if (B < 0 || H < 1 || W < 1) return fail(MRIACL_ERR_INVALID, "bad dims B=%d H=%d W=%d", B, H, W);
+  if (H > MRIACL_MAX_LINE || W > MRIACL_MAX_LINE) return fail(MRIACL_ERR_UNSUPPORTED, "line length above %d", MRIACL_MAX_LINE);
+  if (B == 0) return MRIACL_OK;
+  if (!in_c64 || !out_c64) return fail(MRIACL_ERR_INVALID, "null pointer");
+  const int dev = rt_device();
+  if (dev < 0) return fail(MRIACL_ERR_CUDA, "no CUDA device: %s", rt_last_error_string());
+  if (ensure_smem_attrs(dev)) return fail(MRIACL_ERR_CUDA, "cudaFuncSetAttribute failed: %s", rt_last_error_string());
+  if (int rc = generic_fft2c((const cf*)in_c64, (long long)H * W, 0, 1, 1, (cf*)out_c64, B, H, W, 0, W, nullptr,
+                             inverse ? 1 : 0, dev, (rt_stream_t)cuda_stream)) return rc;
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+}
+
+int mriacl_complex_abs_f32(const void* in_c64, float* out, size_t n, int squared, void* cuda_stream) {
+  if (n == 0) return MRIACL_OK;
+  if (!in_c64 || !out) return fail(MRIACL_ERR_INVALID, "null pointer");
+  MRIACL_LAUNCH(complex_abs_kernel, grid_for((long long)n, 256), 256, 0, (rt_stream_t)cuda_stream,
+                (const cf*)in_c64, out, (long long)n, squared);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+}
+
+int mriacl_rss_f32(const void* in, float* out, size_t outer, int C, size_t inner, int is_complex, void* cuda_stream) {
+  if (C < 1) return fail(MRIACL_ERR_INVALID, "bad coil count %d", C);
+  if (outer * inner == 0) return MRIACL_OK;
+  if (!in || !out) return fail(MRIACL_ERR_INVALID, "null pointer");
+  MRIACL_LAUNCH(rss_kernel, grid_for((long long)(outer * inner), 256), 256, 0, (rt_stream_t)cuda_stream,
+                (const float*)in, out, (long long)outer, C, (long long)inner, is_complex);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+}
+
+int mriacl_center_crop_or_pad(const void* in, void* out, int B, int H, int W, int out_h, int out_w,
+                              int elem_bytes, void* cuda_stream) {
+  if (B < 0 || H < 1 || W < 1 || out_h < 1 || out_w < 1) return fail(MRIACL_ERR_INVALID, "bad dims");
+  if (elem_bytes != 4 && elem_bytes != 8) return fail(MRIACL_ERR_INVALID, "elem_bytes must be 4 or 8");
+  if (B == 0) return MRIACL_OK;
+  if (!in || !out) return fail(MRIACL_ERR_INVALID, "null pointer");
+  MRIACL_LAUNCH(crop_or_pad_kernel, grid_for((long long)B * out_h * out_w, 256), 256, 0, (rt_stream_t)cuda_stream,
+                (const float*)in, (float*)out, B, H, W, out_h, out_w, elem_bytes / 4);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+}
+
+int mriacl_normalize_instance_f32(const float* in, float* out, float* mean_std, int B, size_t n, float eps,
+                                  void* cuda_stream) {
+  if (B < 0 || n < 1) return fail(MRIACL_ERR_INVALID, "bad dims");
+  if (B == 0) return MRIACL_OK;
+  if (!in || !out) return fail(MRIACL_ERR_INVALID, "null pointer");
+  NormParams np{};
+  np.in = in; np.out = out; np.mean_std = mean_std; np.partials = nullptr; np.n_part = 0;
+  np.n = (long long)n; np.eps = eps; np.normalize = 1;
+  MRIACL_LAUNCH(normalize_instance_kernel, B, 512, 0, (rt_stream_t)cuda_stream, np);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+}
+
+}  // extern "C"

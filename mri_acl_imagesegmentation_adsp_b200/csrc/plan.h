@@ -1,0 +1,132 @@
+// plan.h -- host-side planners (plain C++, no CUDA calls): which columns are sampled, how the
+// row pass distributes its pruned first-stage DFTs over warps, twiddle tables, radix lists.
+// Shared by the product library (mriacl_recon.cu) and the CPU emulation tests.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <vector>
+
+namespace mriacl {
+
+struct HostCf { float x, y; };
+
+// w_N^k = exp(sign * 2 pi i k / N), computed in double, rounded once to float
+inline std::vector<HostCf> make_twiddles(int n, int sign) {
+  std::vector<HostCf> t(n);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k = 0; k < n; ++k) {
+    // exact values on the axes so that quarter turns carry no rounding noise
+    const double ang = two_pi * (double)k / (double)n;
+    double c = std::cos(ang), s = std::sin(ang);
+    if ((4 * k) % n == 0) {
+      const int q = (4 * k) / n;
+      c = (q == 0) ? 1.0 : (q == 2) ? -1.0 : 0.0;
+      s = (q == 1) ? 1.0 : (q == 3) ? -1.0 : 0.0;
+    }
+    t[k].x = (float)c;
+    t[k].y = (float)(sign * s);
+  }
+  return t;
+}
+
+// radix list for the generic Stockham kernel: 4s, then a 2, then odd primes ascending
+inline std::vector<int> generic_radices(int n) {
+  std::vector<int> r;
+  while (n % 4 == 0) { r.push_back(4); n /= 4; }
+  if (n % 2 == 0) { r.push_back(2); n /= 2; }
+  for (int p = 3; (long long)p * p <= n; p += 2)
+    while (n % p == 0) { r.push_back(p); n /= p; }
+  if (n > 1) r.push_back(n);
+  return r;
+}
+
+inline int crop_start(int n, int out) { return (n - out) / 2; }
+
+// ---------------------------------------------------------------------------------------
+// Fused plan: sampled-column list for the column pass and the warp schedule of the row pass.
+// ---------------------------------------------------------------------------------------
+struct FusedPlanHost {
+  int H = 0, W = 0, pad_left = 0, Wp = 0, oh = 0, ow = 0, row0 = 0, col0 = 0;
+  int P = 0, Q = 0;
+  std::vector<int> act_w;       // physical (unpadded) column index of active column j, ascending
+  std::vector<float> act_m;     // its mask value
+  std::vector<int> sched;       // row-pass schedule (layout below)
+  std::vector<double> warp_cost;
+};
+
+// Schedule layout (int32):
+//   sched[w], w < n_warps          offset of warp w's list
+//   list: n_units, then per unit   n2, type, nnz, payload
+//     type 1 (dense):  payload = P ints: active-column index j of n1 = 0..P-1, or -1
+//     type 0 (sparse): payload = nnz pairs (n, j): logical index n = Q n1 + n2 and column j
+inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow, const float* mask,
+                             int P, int Q, int n_warps, int max_sparse, FusedPlanHost& pl) {
+  pl.H = H; pl.W = W; pl.pad_left = pad_left; pl.Wp = Wp; pl.oh = oh; pl.ow = ow;
+  pl.row0 = crop_start(H, oh); pl.col0 = crop_start(Wp, ow);
+  pl.P = P; pl.Q = Q;
+  pl.act_w.clear(); pl.act_m.clear();
+  std::vector<int> j_of_w(W, -1);
+  for (int w = 0; w < W; ++w) {
+    const float m = mask ? mask[w] : 1.0f;
+    if (m != 0.0f) { j_of_w[w] = (int)pl.act_w.size(); pl.act_w.push_back(w); pl.act_m.push_back(m); }
+  }
+  struct Unit { int n2, type, nnz; std::vector<int> payload; double cost; };
+  std::vector<Unit> units;
+  for (int n2 = 0; n2 < Q; ++n2) {
+    Unit u; u.n2 = n2;
+    std::vector<int> jn1(P, -1);
+    std::vector<int> pairs;
+    int nnz = 0;
+    for (int n1 = 0; n1 < P; ++n1) {
+      const int n = Q * n1 + n2;
+      int ph = n + Wp / 2; if (ph >= Wp) ph -= Wp;        // logical -> physical (ifftshift)
+      const int w = ph - pad_left;
+      if (w >= 0 && w < W && j_of_w[w] >= 0) {
+        jn1[n1] = j_of_w[w]; pairs.push_back(n); pairs.push_back(j_of_w[w]); ++nnz;
+      }
+    }
+    u.nnz = nnz;
+    if (nnz > max_sparse) { u.type = 1; u.payload = jn1; u.cost = 900.0; }
+    else { u.type = 0; u.payload = pairs; u.cost = 60.0 + 8.0 * P * nnz; }
+    units.push_back(u);
+  }
+  // longest-processing-time-first assignment to warps
+  std::vector<int> order(units.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return units[a].cost > units[b].cost; });
+  std::vector<std::vector<int>> per_warp(n_warps);
+  pl.warp_cost.assign(n_warps, 0.0);
+  for (int ui : order) {
+    int best = 0;
+    for (int w = 1; w < n_warps; ++w) if (pl.warp_cost[w] < pl.warp_cost[best]) best = w;
+    per_warp[best].push_back(ui);
+    pl.warp_cost[best] += units[ui].cost;
+  }
+  pl.sched.assign(n_warps, 0);
+  for (int w = 0; w < n_warps; ++w) {
+    pl.sched[w] = (int)pl.sched.size();
+    pl.sched.push_back((int)per_warp[w].size());
+    for (int ui : per_warp[w]) {
+      const Unit& u = units[ui];
+      pl.sched.push_back(u.n2); pl.sched.push_back(u.type); pl.sched.push_back(u.nnz);
+      pl.sched.insert(pl.sched.end(), u.payload.begin(), u.payload.end());
+    }
+  }
+}
+
+// FNV-1a over the plan-defining inputs: cache key for device-resident plans
+inline uint64_t plan_key(const int* dims, int n_dims, const float* mask, int mask_len) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  };
+  mix(dims, sizeof(int) * n_dims);
+  if (mask) mix(mask, sizeof(float) * mask_len);
+  else { const int none = -1; mix(&none, sizeof(none)); }
+  return h;
+}
+
+}  // namespace mriacl

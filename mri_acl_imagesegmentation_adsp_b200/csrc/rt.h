@@ -1,0 +1,53 @@
+// rt.h -- the few runtime calls the host orchestration needs, behind one seam.
+//
+// Product build (nvcc): CUDA runtime.  Emulation build (g++ with tests/emu/cuda_emu.h, used only
+// by tests/emu to check the orchestration and kernels on a GPU-less machine): host memory and
+// the thread-per-CUDA-thread emulator.  The emulation library is never looked for, loaded or
+// linked by the product package.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+namespace mriacl {
+
+inline std::atomic<uint64_t>& launch_counter() { static std::atomic<uint64_t> c{0}; return c; }
+
+#ifdef MRIACL_EMU
+typedef void* rt_stream_t;
+inline int rt_malloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 1; }
+inline int rt_free(void* p) { std::free(p); return 0; }
+inline int rt_upload(void* dst, const void* src, size_t n) { std::memcpy(dst, src, n); return 0; }
+inline int rt_device() { return 0; }
+inline int rt_sm_count(int) { return 2; }
+inline const char* rt_last_error_string() { return "emulation"; }
+inline int rt_check() { return 0; }
+inline int rt_allow_smem(const void*, int) { return 0; }
+#define MRIACL_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
+  do { emu::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), (size_t)(smem),           \
+                   [&] { kern(__VA_ARGS__); });                                               \
+       ::mriacl::launch_counter()++; } while (0)
+#else
+typedef cudaStream_t rt_stream_t;
+inline int rt_malloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) == cudaSuccess ? 0 : 1; }
+inline int rt_free(void* p) { return cudaFree(p) == cudaSuccess ? 0 : 1; }
+inline int rt_upload(void* dst, const void* src, size_t n) {
+  return cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : 1;   // plan build only, once per plan
+}
+inline int rt_device() { int d = -1; return cudaGetDevice(&d) == cudaSuccess ? d : -1; }
+inline int rt_sm_count(int dev) {
+  int n = 0;
+  return cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess ? n : 0;
+}
+inline const char* rt_last_error_string() { return cudaGetErrorString(cudaGetLastError()); }
+inline int rt_check() { return cudaPeekAtLastError() == cudaSuccess ? 0 : 1; }
+inline int rt_allow_smem(const void* fn, int bytes) {
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : 1;
+}
+#define MRIACL_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
+  do { kern<<<(unsigned)(grid), (unsigned)(block), (size_t)(smem), (stream)>>>(__VA_ARGS__);  \
+       ::mriacl::launch_counter()++; } while (0)
+#endif
+
+}  // namespace mriacl

@@ -1,0 +1,106 @@
+"""Cartesian zero-filled reconstruction -- fills the reference's empty ``src/recon/cartesian.py``.
+
+``zero_filled_rss`` is the fused k-space -> image input stage of BASELINE.json's north star:
+undersampling-mask apply, (zero-pad of the phase-encode axis), centred 2-D inverse FFT per coil,
+root-sum-of-squares coil combine, (flipud, mean over averages), centre crop and instance
+normalisation, as ONE C-ABI call per batch (``mriacl_recon_rss_f32``).
+
+It replaces the chain the reference spells three ways (none of them batched or on the GPU):
+``src/utils/kspace.py:11-31`` (+ sqrt-sum-squares), the vendored fastMRI functions
+``ZIP!/DL_reconstruction/fftc.py:41-65`` / ``coil_combine.py:28-41`` / ``data/transforms.py:45-67,143-162``
+and the prostate T2 chain ``ZIP!/fastmri_prostate/reconstruction/t2/prostate_t2_recon.py:65-121``.
+The output layout is what ``src/preprocess/mri_preprocess.py:124-140`` and
+``src/dataio/datasets.py:90-95`` feed the U-Net: float32, ``(S, oh, ow)`` (``[:, None]`` gives NCHW).
+"""
+from __future__ import annotations
+
+from typing import Any, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _device as D
+from ..adapters import recon_cabi as cabi
+
+
+def _crop_start(n: int, out: int) -> int:
+    return (n - out) // 2
+
+
+def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int]] = (320, 320),
+                    normalize: Optional[str] = "instance", eps: float = 0.0, flip_rows: bool = False,
+                    average_axis: Optional[int] = None, pad: Optional[Tuple[int, int]] = None,
+                    *, chunk_slices: Optional[int] = None, force_generic: bool = False):
+    """k-space -> cropped (normalised) RSS magnitude images.
+
+    kspace   complex64 ``(C,H,W)``, ``(S,C,H,W)`` or, with ``average_axis`` 0 or 1,
+             ``(A,S,C,H,W)`` / ``(S,A,C,H,W)``; numpy, torch complex or torch real view ``(...,2)``;
+             CPU inputs are copied to the current CUDA device, CUDA inputs are used in place.
+    mask     sampling mask along W (0/1 or weights), length W, or None.  (The record dict's
+             ``'mask'`` key of the reference is a segmentation mask -- a different thing.)
+    crop     ``(oh, ow)`` centre crop, start ``(n-out)//2``; None keeps ``(H, W_padded)``.
+             A crop larger than the image raises ValueError like ``center_crop``.
+    normalize  ``"instance"`` -> ``(x-mean)/(std+eps)`` with the unbiased std; None -> raw RSS.
+    flip_rows  ``np.flipud`` of every combined image (prostate chain).
+    average_axis  mean of the per-average RSS images (after the coil combine).
+    pad      ``(left, right)`` zero-padding of the W axis before the transform.
+
+    Returns ``(image, mean, std)``: image float32 ``(S,oh,ow)`` (``(oh,ow)`` for a single slice),
+    mean/std float32 ``(S,)`` (0-d for a single slice) of the un-normalised crop.  Types follow
+    the input (numpy in -> numpy out, CPU torch in -> CPU torch out, CUDA in -> CUDA out).
+    """
+    if normalize not in (None, "instance"):
+        raise ValueError(f"normalize must be None or 'instance', got {normalize!r}")
+    mv = D.to_device_complex(kspace)
+    k = mv.tensor
+    single = False
+    if average_axis is None:
+        if k.ndim == 3:
+            k, single = k[None], True
+        if k.ndim != 4:
+            raise ValueError(f"kspace must be (C,H,W) or (S,C,H,W), got {tuple(k.shape)}")
+        S, C, H, W = k.shape
+        A = 1
+        slice_stride, avg_stride = C * H * W, 0
+    else:
+        if k.ndim != 5 or average_axis not in (0, 1):
+            raise ValueError("with average_axis the kspace must be (A,S,C,H,W) [axis 0] or (S,A,C,H,W) [axis 1]")
+        if average_axis == 0:
+            A, S, C, H, W = k.shape
+            slice_stride, avg_stride = C * H * W, S * C * H * W
+        else:
+            S, A, C, H, W = k.shape
+            slice_stride, avg_stride = A * C * H * W, C * H * W
+    pad_left, pad_right = (0, 0) if pad is None else (int(pad[0]), int(pad[1]))
+    if pad_left < 0 or pad_right < 0:
+        raise ValueError("pad must be non-negative")
+    Wp = W + pad_left + pad_right
+    oh, ow = (H, Wp) if crop is None else (int(crop[0]), int(crop[1]))
+    if not (0 < oh <= H and 0 < ow <= Wp):
+        raise ValueError("Invalid shapes.")
+    m = D.host_mask(mask, W)
+    flags = (cabi.NORM_INSTANCE if normalize == "instance" else 0) | (cabi.FLIP_ROWS if flip_rows else 0) \
+        | (cabi.FORCE_GENERIC if force_generic else 0)
+
+    lib = D.lib()
+    out = torch.empty((S, oh, ow), dtype=torch.float32, device=k.device)
+    mean_std = torch.empty((S, 2), dtype=torch.float32, device=k.device)
+    if S > 0:
+        chunk = max(1, min(S, chunk_slices or D.DEFAULT_CHUNK_SLICES))
+        nbytes = lib.recon_rss_workspace_bytes(chunk, A, C, H, W, pad_left, Wp, oh, ow, m, flags)
+        ws = D.workspace(nbytes)
+        lib.recon_rss(k.data_ptr(), slice_stride, avg_stride, m, out.data_ptr(), mean_std.data_ptr(),
+                      S, A, C, H, W, pad_left, Wp, oh, ow, flags, float(eps), ws.data_ptr(), ws.numel(), D.stream_ptr())
+    mean, std = mean_std[:, 0], mean_std[:, 1]
+    if single:
+        out, mean, std = out[0], mean[0], std[0]
+    return mv.back(out), mv.back(mean), mv.back(std)
+
+
+def recon_to_unet_input(kspace: Any, mask: Any = None, crop: Tuple[int, int] = (320, 320), eps: float = 0.0,
+                        **kw) -> Any:
+    """``(S,C,H,W)`` k-space -> ``(S,1,oh,ow)`` float32 contiguous NCHW, the tensor contract of
+    ``preprocess_records`` (``src/preprocess/mri_preprocess.py:135-140``) / ``KneeNPZ2DSlices``
+    (``src/dataio/datasets.py:90-95,133``)."""
+    img, _, _ = zero_filled_rss(kspace, mask, crop, "instance", eps, **kw)
+    return img[:, None] if isinstance(img, torch.Tensor) else img[:, None, :, :]

@@ -1,0 +1,175 @@
+"""The kernel sources and host orchestration of libmriacl_recon, compiled for the CPU with the
+thread-per-CUDA-thread emulator in tests/emu/ and checked against the oracle.
+
+This is how index maps, plans, barriers and the C-ABI argument handling are validated in the
+GPU-less build container.  It is test infrastructure: the emulation library is built into
+tests/emu/_build/ and is never loaded by the product package.  The `-m gpu` tests run the same
+checks (and more) on the real sm_100a build.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from mri_acl_imagesegmentation_adsp_b200 import synth
+from mri_acl_imagesegmentation_adsp_b200.adapters import recon_cabi as cabi
+from oracle import recon_oracle as O
+
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+TOL = 1e-5   # BASELINE.json: rel-L2 <= 1e-5 in fp32
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    return cabi.ReconLibrary(os.path.join(EMU_DIR, "_build", "libmriacl_emu.so"))
+
+
+def P(a):
+    return a.ctypes.data
+
+
+def fft2c(lib, x, inverse):
+    x = np.ascontiguousarray(x)
+    out = np.empty_like(x)
+    b = int(np.prod(x.shape[:-2])) if x.ndim > 2 else 1
+    lib.fft2c(P(x), P(out), b, x.shape[-2], x.shape[-1], inverse)
+    return out
+
+
+def recon(lib, k, mask, crop, flags=0, pad=(0, 0), eps=0.0, chunk=None):
+    """k: (S, A, C, H, W) complex64"""
+    S, A, C, H, W = k.shape
+    Wp = W + pad[0] + pad[1]
+    out = np.zeros((S,) + tuple(crop), np.float32)
+    ms = np.zeros((S, 2), np.float32)
+    nbytes = lib.recon_rss_workspace_bytes(chunk or S, A, C, H, W, pad[0], Wp, crop[0], crop[1], mask, flags)
+    ws = np.zeros(nbytes, np.uint8)
+    lib.recon_rss(P(k), A * C * H * W, C * H * W, mask, P(out), P(ms), S, A, C, H, W, pad[0], Wp, crop[0], crop[1],
+                  flags, eps, P(ws), nbytes)
+    return out, ms
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 12), (3, 15, 11), (1, 30, 23), (1, 37, 5), (1, 64, 40)])
+def test_generic_fft2c(emu, shape):
+    x = synth.gaussian_kspace(shape, 3)
+    assert O.rel_l2(fft2c(emu, x, True), O.ifft2c(x)) <= TOL
+    assert O.rel_l2(fft2c(emu, x, False), O.fft2c(x)) <= TOL
+
+
+def test_generic_chain_small(emu, golden):
+    k, m = golden["small_even/kspace"], golden["small_even/mask"]
+    out, ms = recon(emu, k[None, None], m, (16, 16), cabi.NORM_INSTANCE)
+    assert O.rel_l2(out[0], golden["small_even/fastmri_chain_16x16"]) <= TOL
+    np.testing.assert_allclose(ms[0], golden["small_even/fastmri_mean_std"], rtol=1e-5)
+    raw, _ = recon(emu, k[None, None], m, (16, 16), 0)
+    assert O.rel_l2(raw[0], golden["small_even/numpy_chain_16x16"]) <= TOL
+
+
+def test_generic_prostate_small(emu, golden):
+    k = golden["prostate_small/kspace"]                      # (A, S, C, RO, PE)
+    kk = np.ascontiguousarray(k.transpose(1, 0, 2, 3, 4))     # (S, A, C, RO, PE)
+    out, _ = recon(emu, kk, None, (16, 16), cabi.FLIP_ROWS, pad=(5, 6))
+    assert O.rel_l2(out, golden["prostate_small/final_16x16"]) <= TOL
+
+
+def test_fused_knee_slice(emu, golden):
+    """configs[0]: the fused column pass + row pass + normalise on the 15-coil 640x368 slice."""
+    assert emu.supported(640, 368) == cabi.PATH_FUSED and emu.supported(640, 372) == cabi.PATH_GENERIC
+    k = synth.gaussian_kspace((1, 1) + synth.KNEE_SHAPE, 0)
+    m = synth.knee_mask()
+    out, ms = recon(emu, k, m, synth.CROP, cabi.NORM_INSTANCE)
+    assert O.rel_l2(out[0], golden["knee_gauss/fastmri_chain"]) <= TOL
+    np.testing.assert_allclose(ms[0], golden["knee_gauss/fastmri_mean_std"], rtol=1e-5)
+    raw, _ = recon(emu, k, m, synth.CROP, 0)
+    assert O.rel_l2(raw[0], golden["knee_gauss/numpy_chain"]) <= TOL
+    # crop indexing is exact: the cropped launch equals the window of the uncropped one, bit for bit
+    full, _ = recon(emu, k, m, (640, 368), 0)
+    np.testing.assert_array_equal(raw[0], full[0, 160:480, 24:344])
+    # masked-out columns are never read: garbage there changes nothing, bit for bit
+    k2 = k.copy()
+    k2[..., m == 0] = np.complex64(1e30 + 1e30j)
+    raw2, _ = recon(emu, k2, m, synth.CROP, 0)
+    np.testing.assert_array_equal(raw, raw2)
+
+
+def test_fused_variants(emu):
+    """ragged column groups, flip, averages, odd crop, weighted mask, two slices in two chunks."""
+    rng = np.random.default_rng(5)
+    k = synth.gaussian_kspace((2, 2, 2, 640, 368), 7)
+    m = np.zeros(368, np.float32)
+    idx = np.sort(rng.choice(368, size=21, replace=False))
+    m[idx] = rng.uniform(0.5, 1.5, size=21).astype(np.float32)
+    out, ms = recon(emu, k, m, (77, 200), cabi.FLIP_ROWS | cabi.NORM_INSTANCE, chunk=1)
+    for s in range(2):
+        ims = []
+        for a in range(2):
+            img = O.complex_abs(O.ifft2c(O.apply_mask(k[s, a], m)))
+            ims.append(np.flipud(np.sqrt((img ** 2).sum(0))))
+        ref = O.center_crop(np.mean(ims, axis=0), (77, 200)).astype(np.float32)
+        nref, mean, std = O.normalize_instance(np.ascontiguousarray(ref))
+        assert O.rel_l2(out[s], nref) <= TOL
+        np.testing.assert_allclose(ms[s], [mean, std], rtol=1e-5)
+    gen, _ = recon(emu, k, m, (77, 200), cabi.FLIP_ROWS | cabi.NORM_INSTANCE | cabi.FORCE_GENERIC)
+    assert O.rel_l2(out, gen) <= TOL
+
+
+def test_fused_single_coil_full(emu, golden):
+    k = synth.gaussian_kspace((640, 368), 1)
+    out = np.zeros((1, 640, 368), np.float32)
+    nbytes = emu.ifft2c_abs_workspace_bytes(1, 640, 368)
+    ws = np.zeros(nbytes, np.uint8)
+    emu.ifft2c_abs(P(k), P(out), 1, 640, 368, P(ws), nbytes)
+    assert O.rel_l2(out[0, ::2], golden["single_coil/ifft2c_single_rows_even"]) <= TOL
+
+
+def test_elementwise_ops(emu, golden):
+    k = golden["small_odd/kspace"]
+    out = np.zeros(k.shape, np.float32)
+    emu.complex_abs(P(k), P(out), k.size, False)
+    assert O.rel_l2(out, O.complex_abs(k)) <= 1e-6
+    img = np.ascontiguousarray(O.ifft2c(k))
+    r = np.zeros((2, 30, 23), np.float32)
+    emu.rss(P(img), P(r), 2, 3, 30 * 23, True)
+    assert O.rel_l2(r, golden["small_odd/rss_complex"]) <= TOL
+    a = np.ascontiguousarray(np.abs(k))
+    emu.rss(P(a), P(r), 2, 3, 30 * 23, False)
+    assert O.rel_l2(r, golden["small_odd/rss_real"]) <= 1e-6
+    x = golden["small_even/ifft2c_single_coil0"]
+    for oh, ow in [(40, 12), (8, 8), (32, 24), (5, 50)]:
+        o = np.zeros((oh, ow), np.float32)
+        emu.center_crop_or_pad(P(x), P(o), 1, 32, 24, oh, ow, 4)
+        np.testing.assert_array_equal(o, O.center_crop_or_pad(x, oh, ow))
+    kc = np.ascontiguousarray(k[0])
+    o = np.zeros((3, 12, 40), np.complex64)
+    emu.center_crop_or_pad(P(kc), P(o), 3, 30, 23, 12, 40, 8)
+    np.testing.assert_array_equal(o, O.center_crop_or_pad(kc, 12, 40))
+    y = (np.abs(synth.gaussian_kspace((2, 320, 320), 3)) + 2).astype(np.float32)
+    o = np.zeros_like(y)
+    ms = np.zeros((2, 2), np.float32)
+    emu.normalize_instance(P(y), P(o), P(ms), 2, 320 * 320, 1e-11)
+    for i in range(2):
+        ref, mean, std = O.normalize_instance(y[i], 1e-11)
+        assert O.rel_l2(o[i], ref) <= 2e-6
+        np.testing.assert_allclose(ms[i], [mean, std], rtol=2e-6)
+
+
+def test_error_convention(emu):
+    k = synth.gaussian_kspace((1, 1, 2, 16, 12), 1)
+    with pytest.raises(ValueError):          # crop larger than the image -> "Invalid shapes."
+        recon(emu, k, None, (17, 12))
+    with pytest.raises(ValueError):
+        emu.fft2c(P(k), P(k), 1, 0, 12, True)
+    with pytest.raises(ValueError):
+        emu.fft2c(P(k), P(k), 1, 5000, 12, True)
+    out = np.zeros((1, 8, 8), np.float32)
+    ws = np.zeros(64, np.uint8)
+    with pytest.raises(RuntimeError):        # workspace too small
+        emu.recon_rss(P(k), 2 * 16 * 12, 0, None, P(out), 0, 1, 1, 2, 16, 12, 0, 12, 8, 8, 0, 0.0, P(ws), 64)
+    # empty batch is a no-op
+    emu.recon_rss(P(k), 2 * 16 * 12, 0, None, P(out), 0, 0, 1, 2, 16, 12, 0, 12, 8, 8, 0, 0.0, P(ws), 64)
+    # all-zero mask: zeros before normalisation (NaN after, as in the reference's 0/0)
+    km = synth.gaussian_kspace((1, 1, 2, 640, 368), 2)
+    z, _ = recon(emu, km, np.zeros(368, np.float32), (64, 64), 0)
+    assert not z.any()
