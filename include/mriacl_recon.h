@@ -45,6 +45,11 @@ extern "C" {
 #define MRIACL_FLIP_ROWS      0x1u  /* np.flipud of each combined image (ZIP!/fastmri_prostate/reconstruction/t2/prostate_t2_recon.py:101) */
 #define MRIACL_NORM_INSTANCE  0x2u  /* (x-mean)/(std+eps), unbiased std (ZIP!/DL_reconstruction/data/transforms.py:143-162) */
 #define MRIACL_FORCE_GENERIC  0x4u  /* testing: use the generic (any-size) kernels even where a fused plan exists */
+/* profiling only (bench.py's per-kernel timing): run just the named phase(s) of the fused plan;
+ * none set = the whole stage.  The workspace must still hold the previous phase's output. */
+#define MRIACL_ONLY_COLPASS   0x100u
+#define MRIACL_ONLY_ROWPASS   0x200u
+#define MRIACL_ONLY_NORM      0x400u
 
 /* path selector reported by mriacl_supported */
 #define MRIACL_PATH_NONE    0

@@ -285,6 +285,10 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
   const int row0 = crop_start(H, oh), col0 = crop_start(Wp, ow);
   const bool want_norm = (flags & MRIACL_NORM_INSTANCE) != 0;
   const int flip = (flags & MRIACL_FLIP_ROWS) ? 1 : 0;
+  const unsigned only = flags & (MRIACL_ONLY_COLPASS | MRIACL_ONLY_ROWPASS | MRIACL_ONLY_NORM);
+  const bool do_col = !only || (only & MRIACL_ONLY_COLPASS);
+  const bool do_row = !only || (only & MRIACL_ONLY_ROWPASS);
+  const bool do_norm = !only || (only & MRIACL_ONLY_NORM);
 
   if (g.fused) {
     std::shared_ptr<FusedPlanDev> pl = get_fused_plan(dev, H, W, pad_left, Wp, oh, ow, mask_w_host, true);
@@ -297,7 +301,7 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
       const int ns = std::min(chunk, B - s0);
       cf* T = (cf*)workspace;
       float* partials = (float*)((char*)workspace + g.t_bytes * (size_t)ns);
-      if (n_groups > 0) {
+      if (n_groups > 0 && do_col) {
         ColPassParams cp{};
         cp.ksp = ksp; cp.sb = slice_stride; cp.sa = avg_stride; cp.A = A; cp.C = C; cp.W = W;
         cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.n_act = n_act; cp.n_groups = n_groups;
@@ -312,14 +316,14 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
       rp.out = out + (size_t)s0 * oh * ow; rp.partials = partials; rp.ow = ow; rp.col0 = col0;
       rp.A = A; rp.C = C; rp.scale = (float)(1.0 / std::sqrt((double)H * (double)Wp));
       rp.n_slices = ns; rp.n_tiles = g.n_tiles;
-      {
+      if (do_row) {
         const int items = ns * g.n_tiles;
         const int per_sm = rp_smem > 110 * 1024 ? 1 : 2;
         const int grid = std::min(items, sms * per_sm);
         auto kfn = rowpass_kernel<FUSED_P, FUSED_Q>;
         MRIACL_LAUNCH(kfn, grid, RP_T, rp_smem, st, rp);
       }
-      if (want_norm || mean_std) {
+      if ((want_norm || mean_std) && do_norm) {
         NormParams np{};
         np.in = rp.out; np.out = rp.out; np.mean_std = mean_std ? mean_std + 2 * (size_t)s0 : nullptr;
         np.partials = partials; np.n_part = g.n_tiles; np.n = (long long)oh * ow; np.eps = eps;

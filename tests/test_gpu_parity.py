@@ -1,0 +1,249 @@
+"""Parity of the sm_100a library against the oracle and the frozen reference outputs, through
+the public Python API (which calls the C ABI).  Run on the B200 box: pytest -m gpu.
+
+Bar (BASELINE.json): rel-L2 <= 1e-5 for floating point; mask and crop indexing bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from mri_acl_imagesegmentation_adsp_b200 import synth
+from mri_acl_imagesegmentation_adsp_b200.adapters import recon_cabi as cabi
+from mri_acl_imagesegmentation_adsp_b200.fastmri import coil_combine, fftc, math_fn, transforms
+from mri_acl_imagesegmentation_adsp_b200.preprocess.mri_preprocess import MRIKneePreprocessor
+from mri_acl_imagesegmentation_adsp_b200.prostate import t2
+from mri_acl_imagesegmentation_adsp_b200.recon.cartesian import recon_to_unet_input, zero_filled_rss
+from mri_acl_imagesegmentation_adsp_b200.utils import kspace as K
+from oracle import recon_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_library_loaded():
+    lib = cabi.library()          # raises if csrc/libmriacl_recon.so is missing: no silent fallback
+    before = lib.launch_count()
+    yield
+    assert lib.launch_count() > before, "no kernel of libmriacl_recon.so was launched"
+
+
+# ---------------------------------------------------------------------------------------------
+# complex-output API (generic kernels)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(4, 32, 24), (2, 3, 30, 23), (1, 37, 5), (2, 640, 368), (1, 640, 372), (3, 451)])
+def test_fft2c_ifft2c(shape):
+    x = synth.gaussian_kspace(shape, 31)
+    a, b = K.ifft2c(x), K.fft2c(x)
+    assert isinstance(a, np.ndarray) and a.dtype == np.complex64 and a.shape == x.shape
+    assert O.rel_l2(a, O.ifft2c(x)) <= TOL
+    assert O.rel_l2(b, O.fft2c(x)) <= TOL
+    assert O.rel_l2(K.fft2c(K.ifft2c(x)), x) <= TOL
+
+
+def test_golden_small(golden):
+    k = golden["small_even/kspace"]
+    assert O.rel_l2(K.ifft2c(k), golden["small_even/ifft2c"]) <= TOL
+    assert O.rel_l2(K.fft2c(k), golden["small_even/fft2c"]) <= TOL
+    assert O.rel_l2(K.complex_abs(k), golden["small_even/complex_abs"]) <= 1e-6
+    ko = golden["small_odd/kspace"]
+    assert O.rel_l2(K.ifft2c(ko), golden["small_odd/ifft2c"]) <= TOL
+    t = transforms.to_tensor(ko)
+    assert O.rel_l2(fftc.ifft2c_new(t).numpy(), golden["small_odd/ifft2c_new"]) <= TOL
+    assert O.rel_l2(fftc.fft2c_new(t).numpy(), golden["small_odd/fft2c_new"]) <= TOL
+    img = fftc.ifft2c_new(t.cuda())
+    assert img.is_cuda and img.shape == t.shape
+    assert O.rel_l2(coil_combine.rss_complex(img, dim=1).cpu().numpy(), golden["small_odd/rss_complex"]) <= TOL
+    assert O.rel_l2(coil_combine.rss(torch.from_numpy(np.abs(ko)), dim=1).numpy(), golden["small_odd/rss_real"]) <= 1e-6
+    assert O.rel_l2(math_fn.complex_abs(t).numpy(), np.abs(ko)) <= 1e-6
+    assert O.rel_l2(math_fn.complex_abs_sq(t).numpy(), np.abs(ko) ** 2) <= 1e-6
+    assert O.rel_l2(t2.ifftnd(ko[0], [1, 2]), golden["small_odd/ifftnd"]) <= TOL
+    assert O.rel_l2(MRIKneePreprocessor.ifft2c_single(ko[1, 2]), golden["small_odd/ifft2c_single"]) <= TOL
+    with pytest.raises(ValueError):
+        fftc.ifft2c_new(torch.zeros(4, 4, 3))
+    with pytest.raises(ValueError):
+        MRIKneePreprocessor.ifft2c_single(ko)
+
+
+def test_crop_pad_bit_exact(golden):
+    x = golden["small_even/ifft2c_single_coil0"]
+    np.testing.assert_array_equal(K.center_crop_or_pad(x, 40, 12), golden["small_even/crop_or_pad_40x12"])
+    probe = np.arange(640 * 368, dtype=np.float32).reshape(640, 368)
+    c = K.center_crop_or_pad(probe, 320, 320)
+    np.testing.assert_array_equal(c, probe[160:480, 24:344])
+    np.testing.assert_array_equal(c[[0, 0, -1, -1], [0, -1, 0, -1]], golden["index/crop_probe_corners"])
+    z = synth.gaussian_kspace((2, 3, 30, 23), 4)
+    for oh, ow in [(12, 40), (30, 23), (31, 22), (7, 7)]:
+        np.testing.assert_array_equal(K.center_crop_or_pad(z, oh, ow), O.center_crop_or_pad(z, oh, ow))
+    np.testing.assert_array_equal(transforms.center_crop(torch.from_numpy(probe), (320, 320)).numpy(), c)
+    with pytest.raises(ValueError):
+        transforms.center_crop(torch.from_numpy(probe), (641, 320))
+
+
+def test_normalize_instance(golden):
+    x = np.abs(synth.gaussian_kspace((320, 320), 3)).astype(np.float32) + 2.0
+    out, mean, std = transforms.normalize_instance(torch.from_numpy(x), eps=1e-11)
+    np.testing.assert_allclose([mean.item(), std.item()], golden["norm/mean_std"], rtol=2e-6)
+    assert O.rel_l2(out.numpy()[::8, ::8], golden["norm/out_sub"]) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# the fused stage, configs[0]
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,gen", [("knee_gauss", synth.gaussian_kspace), ("knee_phantom", synth.phantom_kspace)])
+def test_knee_config0_against_reference_outputs(golden, name, gen):
+    k = gen(synth.KNEE_SHAPE, 0)
+    m = synth.knee_mask()
+    img, mean, std = zero_filled_rss(k, m, synth.CROP, "instance")
+    assert img.dtype == np.float32 and img.shape == (320, 320)
+    assert O.rel_l2(img, golden[f"{name}/fastmri_chain"]) <= TOL
+    np.testing.assert_allclose([mean, std], golden[f"{name}/fastmri_mean_std"], rtol=1e-5)
+    raw, _, _ = zero_filled_rss(k, m, synth.CROP, None)
+    assert O.rel_l2(raw, golden[f"{name}/numpy_chain"]) <= TOL
+    gen_raw, _, _ = zero_filled_rss(k, m, synth.CROP, None, force_generic=True)
+    assert O.rel_l2(gen_raw, golden[f"{name}/numpy_chain"]) <= TOL
+    dense, _, _ = zero_filled_rss(k, None, synth.CROP, None)
+    if name == "knee_gauss":
+        assert O.rel_l2(dense[::4, ::4], golden["knee_gauss/numpy_chain_nomask_sub4"]) <= TOL
+
+
+def test_mask_and_crop_indexing_bit_exact():
+    k = torch.from_numpy(synth.gaussian_kspace((2,) + synth.KNEE_SHAPE, 40)).cuda()
+    m = synth.knee_mask()
+    raw, _, _ = zero_filled_rss(k, m, synth.CROP, None)
+    full, _, _ = zero_filled_rss(k, m, None, None)
+    assert full.shape == (2, 640, 368)
+    assert torch.equal(raw, full[:, 160:480, 24:344])
+    k2 = k.clone()
+    k2[..., torch.from_numpy(m == 0).cuda()] = complex(1e30, -1e30)
+    raw2, _, _ = zero_filled_rss(k2, m, synth.CROP, None)
+    assert torch.equal(raw, raw2)
+    # batching / chunking never changes a slice
+    one, _, _ = zero_filled_rss(k[1], m, synth.CROP, None)
+    assert torch.equal(one, raw[1])
+    c1, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=1)
+    assert torch.equal(c1, raw)
+
+
+def test_fused_variants_against_oracle():
+    rng = np.random.default_rng(5)
+    k = synth.gaussian_kspace((2, 2, 3, 640, 368), 7)       # (S, A, C, H, W)
+    m = np.zeros(368, np.float32)
+    idx = np.sort(rng.choice(368, size=21, replace=False))
+    m[idx] = rng.uniform(0.5, 1.5, size=21).astype(np.float32)
+    out, mean, std = zero_filled_rss(k, m, (77, 200), "instance", flip_rows=True, average_axis=1, chunk_slices=1)
+    gen, gmean, gstd = zero_filled_rss(k, m, (77, 200), "instance", flip_rows=True, average_axis=1, force_generic=True)
+    for s in range(2):
+        ims = []
+        for a in range(2):
+            mag = O.complex_abs(O.ifft2c(O.apply_mask(k[s, a], m)))
+            ims.append(np.flipud(np.sqrt((mag ** 2).sum(0))))
+        ref = np.ascontiguousarray(O.center_crop(np.mean(ims, axis=0), (77, 200)).astype(np.float32))
+        nref, rmean, rstd = O.normalize_instance(ref)
+        assert O.rel_l2(out[s], nref) <= TOL
+        assert O.rel_l2(gen[s], nref) <= TOL
+        np.testing.assert_allclose([mean[s], std[s]], [rmean, rstd], rtol=1e-5)
+        np.testing.assert_allclose([gmean[s], gstd[s]], [rmean, rstd], rtol=1e-5)
+
+
+def test_single_coil_live_path(golden):
+    k = synth.gaussian_kspace((640, 368), 1)
+    a = MRIKneePreprocessor.ifft2c_single(k)
+    assert a.dtype == np.float32 and a.shape == (640, 368)
+    assert O.rel_l2(a[::2], golden["single_coil/ifft2c_single_rows_even"]) <= TOL
+    b = MRIKneePreprocessor.ifft2c_single(synth.gaussian_kspace((640, 372), 2))     # 372-wide file: generic kernels
+    assert O.rel_l2(b[::5, ::3], golden["single_coil/ifft2c_single_372_sub"]) <= TOL
+    recs = [{"kspace": synth.gaussian_kspace((640, 368), 50 + i), "meta": {"slice": i}} for i in range(3)]
+    pack = MRIKneePreprocessor().recon_records(recs)
+    assert pack["tensor"].shape == (3, 1, 640, 368) and pack["tensor"].dtype == torch.float32
+    for i, r in enumerate(recs):
+        assert O.rel_l2(pack["tensor"][i, 0].cpu().numpy(), O.ifft2c_single(r["kspace"])) <= TOL
+    with pytest.raises(ValueError):
+        MRIKneePreprocessor().recon_records([{"kspace": np.zeros((2, 8, 8), np.float32)}])
+
+
+def test_analytic_and_parseval():
+    k = np.zeros((1, 640, 368), np.complex64)
+    k[0, 320, 184] = 1.0
+    img, _, _ = zero_filled_rss(k, None, None, None)
+    np.testing.assert_allclose(img, 1.0 / np.sqrt(640 * 368), rtol=2e-6)
+    # batch 64 at full size, device-generated: Parseval per slice (sum RSS^2 == sum |k|^2)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    kb = torch.view_as_complex(torch.randn((64, 15, 640, 368, 2), device="cuda", generator=g))
+    full, _, _ = zero_filled_rss(kb, None, None, None)
+    e_img = (full.double() ** 2).sum(dim=(1, 2))
+    e_k = (torch.view_as_real(kb).double() ** 2).sum(dim=(1, 2, 3, 4))
+    assert float(((e_img - e_k).abs() / e_k).max()) <= 1e-5
+    # linearity in magnitude: scaling k-space by c scales the un-normalised image by |c|,
+    # and leaves the instance-normalised image unchanged
+    m = synth.knee_mask()
+    a, _, _ = zero_filled_rss(kb[:4], m, synth.CROP, None)
+    b, _, _ = zero_filled_rss(kb[:4] * 3.0, m, synth.CROP, None)
+    assert float((b - 3.0 * a).norm() / (3.0 * a).norm()) <= 2e-6
+    na, mean, std = zero_filled_rss(kb[:4], m, synth.CROP, "instance")
+    nb, _, _ = zero_filled_rss(kb[:4] * 3.0, m, synth.CROP, "instance")
+    assert float((na - nb).norm() / na.norm()) <= TOL
+    # the normalised output has zero mean and unit (unbiased) std
+    assert float(na.mean(dim=(1, 2)).abs().max()) <= 1e-5
+    assert float((na.std(dim=(1, 2)) - 1).abs().max()) <= 1e-5
+    torch.testing.assert_close(mean, a.mean(dim=(1, 2)), rtol=1e-5, atol=0)
+    torch.testing.assert_close(std, a.std(dim=(1, 2)), rtol=1e-5, atol=0)
+
+
+def test_layouts_and_types():
+    k = synth.gaussian_kspace((2, 4, 640, 368), 60)
+    m = synth.knee_mask()
+    ref, _, _ = zero_filled_rss(k, m)
+    t_cpu = torch.from_numpy(k)
+    o_cpu, _, _ = zero_filled_rss(t_cpu, torch.from_numpy(m))
+    assert isinstance(o_cpu, torch.Tensor) and o_cpu.device.type == "cpu"
+    np.testing.assert_array_equal(o_cpu.numpy(), ref)
+    o_ri, _, _ = zero_filled_rss(torch.view_as_real(t_cpu).cuda(), m)        # fastMRI real view (...,2)
+    assert o_ri.is_cuda
+    np.testing.assert_array_equal(o_ri.cpu().numpy(), ref)
+    nc = torch.from_numpy(k).cuda().permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)   # non-contiguous view
+    o_nc, _, _ = zero_filled_rss(nc, m)
+    np.testing.assert_array_equal(o_nc.cpu().numpy(), ref)
+    x = recon_to_unet_input(torch.from_numpy(k).cuda(), m)
+    assert x.shape == (2, 1, 320, 320) and x.dtype == torch.float32 and x.is_contiguous()
+    empty, _, _ = zero_filled_rss(torch.zeros((0, 4, 640, 368), dtype=torch.complex64, device="cuda"), m)
+    assert empty.shape == (0, 320, 320)
+
+
+def test_errors():
+    k = synth.gaussian_kspace((2, 16, 12), 1)
+    with pytest.raises(ValueError):
+        zero_filled_rss(k, None, (17, 12))
+    with pytest.raises(ValueError):
+        zero_filled_rss(k, np.ones(11, np.float32), (8, 8))
+    with pytest.raises(ValueError):
+        zero_filled_rss(k[0], None, (8, 8))
+    with pytest.raises(ValueError):
+        zero_filled_rss(np.zeros((2, 16, 12), np.float32), None, (8, 8))
+    with pytest.raises(ValueError):
+        zero_filled_rss(k, None, (8, 8), normalize="zscore")
+    with pytest.raises(ValueError):
+        K.ifft2c(np.zeros((1, 5000, 4), np.complex64))
+
+
+# ---------------------------------------------------------------------------------------------
+# prostate T2 chain, configs[2]
+# ---------------------------------------------------------------------------------------------
+def test_prostate_small(golden):
+    k = golden["prostate_small/kspace"]
+    assert t2.padding_lr(32, 20) == (5, 6) and t2.padding_lr(640, 450) == (94, 95)
+    for av in range(2):
+        cc = t2.create_coil_combined_im(O.zero_pad_pe(k[av], 5, 6))
+        assert cc.dtype == np.float64
+        assert O.rel_l2(cc, golden["prostate_small/coil_combined"][av]) <= TOL
+    fin = t2.t2_average_combine(k, (5, 6), (16, 16))
+    assert fin.dtype == np.float64 and fin.shape == (2, 16, 16)
+    assert O.rel_l2(fin, golden["prostate_small/final_16x16"]) <= TOL
+
+
+def test_prostate_config2_one_slice(golden, manifest):
+    case = manifest["cases"]["prostate_one_slice"]
+    k = synth.gaussian_kspace(tuple(case["shape"]), case["seed"])
+    fin = t2.t2_average_combine(k, synth.PROSTATE_PAD, synth.CROP, mask=synth.prostate_mask())
+    assert fin.shape == (1, 320, 320)
+    assert O.rel_l2(fin, golden["prostate/one_slice_final"]) <= TOL
