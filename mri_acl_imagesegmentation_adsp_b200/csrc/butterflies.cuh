@@ -125,9 +125,12 @@ template <bool INV> __device__ __forceinline__ void fft16(cf* v) {
 //   X[k], X[P-k] = x0 + sum a_n cos(2 pi n k/P)  +-  i sum b_n sin(2 pi n k/P)
 // ~ (P-1)^2 real FMAs with immediate constants.  Results are handed to emit(k, X[k]) as they
 // are produced so the caller can twiddle and store without keeping all P outputs live.
-template <int P, bool INV, class Emit>
-__device__ __forceinline__ void dft_odd_sym(const cf* x, Emit&& emit) {
+// The _part form computes only the output pairs k in [KLO, KHI) (and X[0] when WITH0), so one
+// transform can be shared between two warps.
+template <int P, bool INV, int KLO, int KHI, bool WITH0, class Emit>
+__device__ __forceinline__ void dft_odd_sym_part(const cf* x, Emit&& emit) {
   constexpr int Hh = (P - 1) / 2;
+  static_assert(KLO >= 1 && KHI <= Hh + 1 && KLO <= KHI, "pair range");
   cf a[Hh], b[Hh];
   const cf x0 = x[0];
   static_for<Hh>([&](auto nn) {
@@ -135,13 +138,13 @@ __device__ __forceinline__ void dft_odd_sym(const cf* x, Emit&& emit) {
     a[n - 1] = cadd(x[n], x[P - n]);
     b[n - 1] = csub(x[n], x[P - n]);
   });
-  {
+  if constexpr (WITH0) {
     cf s = x0;
     static_for<Hh>([&](auto nn) { s = cadd(s, a[nn.value]); });
     emit(std::integral_constant<int, 0>{}, s);
   }
-  static_for<Hh>([&](auto kk) {
-    constexpr int k = kk.value + 1;
+  static_for<KHI - KLO>([&](auto kk) {
+    constexpr int k = kk.value + KLO;
     float ar = x0.x, ai = x0.y, br = 0.f, bi = 0.f;
     static_for<Hh>([&](auto nn) {
       constexpr int n = nn.value + 1;
@@ -157,6 +160,11 @@ __device__ __forceinline__ void dft_odd_sym(const cf* x, Emit&& emit) {
     emit(std::integral_constant<int, k>{}, INV ? plus : minus);
     emit(std::integral_constant<int, P - k>{}, INV ? minus : plus);
   });
+}
+
+template <int P, bool INV, class Emit>
+__device__ __forceinline__ void dft_odd_sym(const cf* x, Emit&& emit) {
+  dft_odd_sym_part<P, INV, 1, (P - 1) / 2 + 1, true>(x, emit);
 }
 
 }  // namespace mriacl

@@ -14,7 +14,8 @@
 // The input ifftshift is the load index map (physical row h -> logical n = (h - 320) mod 640),
 // the output fftshift + centre crop + optional flipud is the store index map, so neither shift
 // moves data.  Only the out_h kept rows are written, to the intermediate T[frame][j][row]
-// (row-contiguous, so the row pass reads it coalesced with lane = row).
+// (row-contiguous with a pitch that is a multiple of 32, so the row pass can bulk-copy 32-row
+// blocks with 16-byte cp.async).
 //
 // Shared-memory layout per column: slot(m1, m2, n3) = 90 m1 + 10 m2 + n3 (each block of 80 is
 // padded to 90) and column pitch 722 complex.  With it pass 1 (lanes over 10 n2 + n3), pass 2
@@ -41,8 +42,8 @@ struct ColPassParams {
   int n_act;
   int n_groups;                  // ceil(n_act / 8)
   const cf* tw;                  // w640^k = exp(+2 pi i k / 640)
-  cf* T;                         // [n_frames][n_act][oh]
-  int oh, row0, flip;
+  cf* T;                         // [n_frames][n_act][ohp]
+  int oh, ohp, row0, flip;       // ohp = row pitch of T (multiple of 32)
   int frame0;                    // first global frame of this launch (f = (b*A + a)*C + c)
   int n_frames;
 };
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(CP_T, 4) colpass640_kernel(ColPassParams p) {
           v[2 * q + 1] = cf_make(t.z, t.w);
         }
         radix10<true>(v);
-        cf* dst = p.T + ((long long)fl * p.n_act + j0 + k) * p.oh;
+        cf* dst = p.T + ((long long)fl * p.n_act + j0 + k) * p.ohp;
 #pragma unroll
         for (int m3 = 0; m3 < 10; ++m3) {
           const int m = r3 + 64 * m3;

@@ -160,14 +160,17 @@ struct NormParams {
   float* mean_std;     // [B][2] or nullptr
   const float* partials;  // [B][n_part][3] or nullptr
   int n_part;
+  int n_split;         // blocks per image (1 unless partials are given)
   long long n;         // elements per image
   float eps;
   int normalize;
 };
 
+// grid = B * n_split: block (b, part) normalises its 1/n_split share of image b (every block
+// re-derives the statistics: from the partials that is a handful of FMAs).
 __global__ void __launch_bounds__(512) normalize_instance_kernel(NormParams p) {
   __shared__ double red[33];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / p.n_split, part = blockIdx.x - b * p.n_split;
   const float* x = p.in + (long long)b * p.n;
   double mean, m2;
   if (p.partials) {
@@ -193,11 +196,13 @@ __global__ void __launch_bounds__(512) normalize_instance_kernel(NormParams p) {
   }
   const float fmean = (float)mean;
   const float fstd = (float)sqrt(m2 / (double)(p.n - 1));
-  if (threadIdx.x == 0 && p.mean_std) { p.mean_std[2 * b] = fmean; p.mean_std[2 * b + 1] = fstd; }
+  if (threadIdx.x == 0 && part == 0 && p.mean_std) { p.mean_std[2 * b] = fmean; p.mean_std[2 * b + 1] = fstd; }
   if (p.normalize && p.out) {
     float* y = p.out + (long long)b * p.n;
     const float den = fstd + p.eps;
-    for (long long i = threadIdx.x; i < p.n; i += blockDim.x) y[i] = (x[i] - fmean) / den;
+    const long long per = (p.n + p.n_split - 1) / p.n_split;
+    const long long lo = part * per, hi = lo + per < p.n ? lo + per : p.n;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) y[i] = (x[i] - fmean) / den;
   }
 }
 

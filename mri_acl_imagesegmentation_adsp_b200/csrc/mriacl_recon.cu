@@ -2,6 +2,7 @@
 // orchestration of the kernels.  Built for sm_100a only; no cuFFT, no CPU fallback.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -49,6 +50,14 @@ int device_sms(int dev) {
 }
 
 constexpr int FUSED_P = 23, FUSED_Q = 16;
+constexpr int SMEM_MAX = 227 * 1024;           // dynamic shared memory a B200 CTA may opt in to
+// warps of the row-pass CTA (one CTA per SM): 24 gives every k1 of stage 2 its own warp, 16 leaves
+// more registers per thread.  MRIACL_RP_WARPS=16|24 selects at run time (tuning knob).
+int rp_warps() {
+  static int nw = [] { const char* e = getenv("MRIACL_RP_WARPS"); return (e && atoi(e) == 16) ? 16 : 24; }();
+  return nw;
+}
+
 constexpr int GEN_SMEM_BYTES = 2 * MRIACL_GEN_SMEM_ELEMS * 8;
 
 int ensure_smem_attrs(int dev) {
@@ -58,7 +67,8 @@ int ensure_smem_attrs(int dev) {
   int bad = 0;
   bad |= rt_allow_smem((const void*)generic_fft_kernel, GEN_SMEM_BYTES);
   bad |= rt_allow_smem((const void*)colpass640_kernel, CP_SMEM_BYTES);
-  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q>, 200 * 1024);
+  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, 24>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, 16>, SMEM_MAX);
   if (!bad) d.smem_set = true;
   return bad;
 }
@@ -134,7 +144,7 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     }
   }
   auto pl = std::make_shared<FusedPlanDev>();
-  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, FUSED_P, FUSED_Q, RP_NW, RP_MAX_SPARSE, pl->host);
+  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, FUSED_P, FUSED_Q, rp_warps(), RP_MAX_SPARSE, /*split_dense=*/true, pl->host);
   pl->has_mask = mask != nullptr;
   if (mask) pl->mask_copy.assign(mask, mask + W);
   if (device_side) {
@@ -173,7 +183,8 @@ int recon_geom(int A, int C, int H, int W, int pad_left, int Wp, int oh, int ow,
     int n_act = 0;
     for (int w = 0; w < W; ++w) n_act += (!mask || mask[w] != 0.0f) ? 1 : 0;
     g.n_act = n_act;
-    g.t_bytes = align_up((size_t)A * C * (size_t)(n_act > 0 ? n_act : 1) * oh * sizeof(cf), 256);
+    const size_t ohp = (size_t)g.n_tiles * RP_ROWS;
+    g.t_bytes = align_up((size_t)A * C * (size_t)(n_act > 0 ? n_act : 1) * ohp * sizeof(cf), 256);
     g.per_slice = g.t_bytes + align_up((size_t)g.n_tiles * 3 * sizeof(float), 256);
   } else {
     g.n_act = W;
@@ -241,6 +252,9 @@ int grid_for(long long work_items, int per_block) {
 }  // namespace
 
 // =========================================================================================
+// Only the C ABI is exported: the library is built with -fvisibility=hidden so that none of its
+// inline helpers can be interposed by (or onto) another shared object in the same process.
+#pragma GCC visibility push(default)
 extern "C" {
 
 int mriacl_abi_version(void) { return MRIACL_ABI_VERSION; }
@@ -295,8 +309,13 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
     if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
     const int n_act = (int)pl->host.act_w.size();
     const int n_groups = (n_act + CP_G - 1) / CP_G;
-    const int rp_smem = rowpass_smem_bytes<FUSED_P, FUSED_Q>(ow, A);
-    if (rp_smem > 200 * 1024) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (ow=%d)", ow);
+    const int ohp = g.n_tiles * RP_ROWS;
+    const int rp_fixed = rowpass_fixed_smem<FUSED_P, FUSED_Q>() + 64;
+    int n_buf = 2;
+    if (rowpass_smem_bytes(rp_fixed, n_act, 2, ow, A) > SMEM_MAX) n_buf = 1;
+    const int rp_smem = rowpass_smem_bytes(rp_fixed, n_act, n_buf, ow, A);
+    if (rp_smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, ow, A);
+    if ((int)pl->host.sched.size() > RP_SCHED_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass schedule too long");
     for (int s0 = 0; s0 < B; s0 += chunk) {
       const int ns = std::min(chunk, B - s0);
       cf* T = (cf*)workspace;
@@ -305,30 +324,36 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
         ColPassParams cp{};
         cp.ksp = ksp; cp.sb = slice_stride; cp.sa = avg_stride; cp.A = A; cp.C = C; cp.W = W;
         cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.n_act = n_act; cp.n_groups = n_groups;
-        cp.tw = pl->twH; cp.T = T; cp.oh = oh; cp.row0 = row0; cp.flip = flip;
+        cp.tw = pl->twH; cp.T = T; cp.oh = oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
         cp.frame0 = s0 * A * C; cp.n_frames = ns * A * C;
         const long long items = (long long)cp.n_frames * n_groups;
         const int grid = (int)std::min<long long>(items, (long long)sms * 4);
         MRIACL_LAUNCH(colpass640_kernel, grid, CP_T, CP_SMEM_BYTES, st, cp);
       }
       RowPassParams rp{};
-      rp.T = T; rp.n_act = n_act; rp.oh = oh; rp.sched = pl->sched; rp.tw = pl->twW;
+      rp.T = T; rp.n_act = n_act; rp.oh = oh; rp.ohp = ohp; rp.sched = pl->sched; rp.sched_len = (int)pl->host.sched.size();
+      rp.n_buf = n_buf; rp.tw = pl->twW;
       rp.out = out + (size_t)s0 * oh * ow; rp.partials = partials; rp.ow = ow; rp.col0 = col0;
       rp.A = A; rp.C = C; rp.scale = (float)(1.0 / std::sqrt((double)H * (double)Wp));
       rp.n_slices = ns; rp.n_tiles = g.n_tiles;
       if (do_row) {
         const int items = ns * g.n_tiles;
-        const int per_sm = rp_smem > 110 * 1024 ? 1 : 2;
-        const int grid = std::min(items, sms * per_sm);
-        auto kfn = rowpass_kernel<FUSED_P, FUSED_Q>;
-        MRIACL_LAUNCH(kfn, grid, RP_T, rp_smem, st, rp);
+        const int grid = std::min(items, sms);
+        if (rp_warps() == 24) {
+          auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, 24>;
+          MRIACL_LAUNCH(kfn, grid, 24 * 32, rp_smem, st, rp);
+        } else {
+          auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, 16>;
+          MRIACL_LAUNCH(kfn, grid, 16 * 32, rp_smem, st, rp);
+        }
       }
       if ((want_norm || mean_std) && do_norm) {
         NormParams np{};
         np.in = rp.out; np.out = rp.out; np.mean_std = mean_std ? mean_std + 2 * (size_t)s0 : nullptr;
         np.partials = partials; np.n_part = g.n_tiles; np.n = (long long)oh * ow; np.eps = eps;
         np.normalize = want_norm ? 1 : 0;
-        MRIACL_LAUNCH(normalize_instance_kernel, ns, 512, 0, st, np);
+        np.n_split = want_norm ? std::max(1, std::min(16, (int)(np.n / 8192))) : 1;
+        MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, st, np);
       }
     }
   } else {
@@ -346,7 +371,7 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
       if (want_norm || mean_std) {
         NormParams np{};
         np.in = rc.out; np.out = rc.out; np.mean_std = mean_std ? mean_std + 2 * (size_t)s0 : nullptr;
-        np.partials = nullptr; np.n_part = 0; np.n = (long long)oh * ow; np.eps = eps; np.normalize = want_norm ? 1 : 0;
+        np.partials = nullptr; np.n_part = 0; np.n_split = 1; np.n = (long long)oh * ow; np.eps = eps; np.normalize = want_norm ? 1 : 0;
         MRIACL_LAUNCH(normalize_instance_kernel, ns, 512, 0, st, np);
       }
     }
@@ -422,7 +447,7 @@ int mriacl_normalize_instance_f32(const float* in, float* out, float* mean_std, 
   if (B == 0) return MRIACL_OK;
   if (!in || !out) return fail(MRIACL_ERR_INVALID, "null pointer");
   NormParams np{};
-  np.in = in; np.out = out; np.mean_std = mean_std; np.partials = nullptr; np.n_part = 0;
+  np.in = in; np.out = out; np.mean_std = mean_std; np.partials = nullptr; np.n_part = 0; np.n_split = 1;
   np.n = (long long)n; np.eps = eps; np.normalize = 1;
   MRIACL_LAUNCH(normalize_instance_kernel, B, 512, 0, (rt_stream_t)cuda_stream, np);
   if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
@@ -430,3 +455,4 @@ int mriacl_normalize_instance_f32(const float* in, float* out, float* mean_std, 
 }
 
 }  // extern "C"
+#pragma GCC visibility pop

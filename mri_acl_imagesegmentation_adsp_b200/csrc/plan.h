@@ -60,9 +60,11 @@ struct FusedPlanHost {
 //   sched[w], w < n_warps          offset of warp w's list
 //   list: n_units, then per unit   n2, type, nnz, payload
 //     type 1 (dense):  payload = P ints: active-column index j of n1 = 0..P-1, or -1
+//     type 2 / 3 (dense, first / second half of the outputs): same payload; used when
+//                      split_dense so that one dense residue is shared by two warps
 //     type 0 (sparse): payload = nnz pairs (n, j): logical index n = Q n1 + n2 and column j
 inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow, const float* mask,
-                             int P, int Q, int n_warps, int max_sparse, FusedPlanHost& pl) {
+                             int P, int Q, int n_warps, int max_sparse, bool split_dense, FusedPlanHost& pl) {
   pl.H = H; pl.W = W; pl.pad_left = pad_left; pl.Wp = Wp; pl.oh = oh; pl.ow = ow;
   pl.row0 = crop_start(H, oh); pl.col0 = crop_start(Wp, ow);
   pl.P = P; pl.Q = Q;
@@ -88,9 +90,23 @@ inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow,
       }
     }
     u.nnz = nnz;
-    if (nnz > max_sparse) { u.type = 1; u.payload = jn1; u.cost = 900.0; }
-    else { u.type = 0; u.payload = pairs; u.cost = 60.0 + 8.0 * P * nnz; }
-    units.push_back(u);
+    if (nnz > max_sparse) {
+      u.payload = jn1;
+      const double hp = (P - 1) / 2;
+      const double full = 2.0 * P + 2.2 * (P - 1) + hp * (4.0 * hp + 26.0);
+      if (split_dense) {
+        u.type = 2; u.cost = 0.5 * full + 30.0;
+        units.push_back(u);
+        u.type = 3;
+        units.push_back(u);
+      } else {
+        u.type = 1; u.cost = full;
+        units.push_back(u);
+      }
+    } else {
+      u.type = 0; u.payload = pairs; u.cost = 20.0 + P * (8.0 * nnz + 4.0);
+      units.push_back(u);
+    }
   }
   // longest-processing-time-first assignment to warps
   std::vector<int> order(units.size());

@@ -2,14 +2,17 @@
 // |.|^2 accumulation over coils, sqrt, mean over averages, fftshift + centre crop as the store
 // index map, and per-tile statistics for the instance normalisation.
 //
-// One work item = (slice, tile of 32 output rows); lane = row, so every lane of a warp runs the
-// same plan-driven control flow and every shared-memory access is stride-1 across lanes.
-// For each coil frame:
-//   stage 1  (decimation in time, n = Q n1 + n2):  for each residue n2 the P-point DFT over n1 of
-//            the SAMPLED columns only.  The host plan classifies each residue as dense (symmetric
-//            direct DFT with immediate constants) or sparse (<= 6 sampled columns: direct
-//            accumulation with w_N^{n k1}), and balances the units over the 8 warps.  Inputs come
-//            straight from the intermediate T[frame][j][row] (coalesced, lane = row).
+// One work item = (slice, tile of 32 output rows); one persistent CTA per SM; lane = row, so every
+// lane of a warp runs the same plan-driven control flow and every shared-memory access is stride-1
+// across lanes (no bank conflicts anywhere in this kernel).  For each coil frame:
+//   prefetch the frame's [n_act][32 rows] block of the intermediate T into shared memory with
+//            cp.async, one frame ahead (double buffered when it fits), so HBM/L2 latency never
+//            sits in front of the arithmetic;
+//   stage 1  (decimation in time, n = Q n1 + n2): for each residue n2 the P-point DFT over n1 of the
+//            SAMPLED columns only.  The host plan classifies each residue as dense (symmetric direct
+//            DFT with immediate constants, optionally split in two halves of its outputs) or sparse
+//            (<= 6 sampled columns: direct accumulation with w_N^{n k1}) and balances the pieces over
+//            the warps;
 //   stage 2  for each k1 the Q-point FFT over n2 in registers -> X[k1 + P k2]; |X|^2 is added to
 //            per-thread accumulators that stay in registers across all coils.
 // Width 368 = 23 x 16 is the knee case; the template is general in (P odd, Q = 16).
@@ -18,15 +21,15 @@
 
 namespace mriacl {
 
-constexpr int RP_T = 256;          // threads per CTA
-constexpr int RP_NW = 8;           // warps
 constexpr int RP_ROWS = 32;        // rows per tile (= lanes)
 constexpr int RP_MAX_SPARSE = 6;   // a residue with more sampled columns than this is "dense"
+constexpr int RP_SCHED_MAX = 2048; // ints of schedule kept in shared memory
 
 struct RowPassParams {
-  const cf* T;           // [n_slices*A*C][n_act][oh]
-  int n_act, oh;
+  const cf* T;           // [n_slices*A*C][n_act][ohp]
+  int n_act, oh, ohp;    // ohp = row pitch of T (multiple of 32)
   const int* sched;      // warp schedule, see plan.h
+  int sched_len;
   const cf* tw;          // w_N^k = exp(+2 pi i k / N)
   float* out;            // [n_slices][oh][ow]  (already offset to the first slice of the launch)
   float* partials;       // [n_slices][n_tiles][3] (count, mean, M2) or nullptr
@@ -34,13 +37,37 @@ struct RowPassParams {
   int A, C;
   float scale;           // 1 / sqrt(H * N)
   int n_slices, n_tiles;
+  int n_buf;             // 1 or 2 prefetch buffers
 };
 
-template <int P, int Q> constexpr int rowpass_smem_bytes(int ow, int A) {
-  return P * Q * RP_ROWS * 8 + P * Q * 8 + (A > 1 ? RP_ROWS * (ow + 1) * 4 : 0);
+// shared memory: Y [P][Q][32] | twiddles [N] | schedule | T buffers | (A > 1) average tile
+template <int P, int Q> __host__ __device__ constexpr int rowpass_fixed_smem() {
+  return P * Q * RP_ROWS * 8 + P * Q * 8 + RP_SCHED_MAX * 4;
+}
+inline int rowpass_smem_bytes(int fixed, int n_act, int n_buf, int ow, int A) {
+  return fixed + n_buf * n_act * RP_ROWS * 8 + (A > 1 ? RP_ROWS * (ow + 1) * 4 : 0);
 }
 
-__device__ __forceinline__ float rp_block_sum(float v, float* red /* 9 floats */) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+#if defined(MRIACL_EMU)
+  reinterpret_cast<float4*>(smem_dst)[0] = reinterpret_cast<const float4*>(gsrc)[0];
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#if !defined(MRIACL_EMU)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N_PENDING> __device__ __forceinline__ void cp_async_wait() {
+#if !defined(MRIACL_EMU)
+  asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
+#endif
+}
+
+template <int NW> __device__ __forceinline__ float rp_block_sum(float v, float* red /* NW floats */) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
@@ -48,132 +75,187 @@ __device__ __forceinline__ float rp_block_sum(float v, float* red /* 9 floats */
   __syncthreads();
   float t = 0.f;
 #pragma unroll
-  for (int w = 0; w < RP_NW; ++w) t += red[w];
+  for (int w = 0; w < NW; ++w) t += red[w];
   return t;
 }
 
-template <int P, int Q>
-__global__ void __launch_bounds__(RP_T, 2) rowpass_kernel(RowPassParams p) {
+// sparse residue with exactly NNZ sampled columns: Y'[k1] = sum_e x_e w_N^{n_e k1}
+template <int P, int Q, int NNZ>
+__device__ __forceinline__ void rp_sparse_unit(const int* sch, const cf* tb, const cf* twsm, cf* ycol) {
+  constexpr int N = P * Q;
+  cf xe[NNZ > 0 ? NNZ : 1];
+  int ne[NNZ > 0 ? NNZ : 1], idx[NNZ > 0 ? NNZ : 1];
+#pragma unroll
+  for (int e = 0; e < NNZ; ++e) {
+    ne[e] = sch[2 * e];
+    xe[e] = tb[sch[2 * e + 1] * RP_ROWS];
+    idx[e] = 0;
+  }
+#pragma unroll 1
+  for (int k1 = 0; k1 < P; ++k1) {
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int e = 0; e < NNZ; ++e) {
+      const cf w = twsm[idx[e]];
+      re = fmaf(xe[e].x, w.x, fmaf(-xe[e].y, w.y, re));
+      im = fmaf(xe[e].x, w.y, fmaf(xe[e].y, w.x, im));
+      idx[e] += ne[e];
+      if (idx[e] >= N) idx[e] -= N;
+    }
+    ycol[k1 * Q * RP_ROWS] = cf_make(re, im);
+  }
+}
+
+template <int P, int Q, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) rowpass_kernel(RowPassParams p) {
   static_assert(Q == 16, "stage 2 is the register-level 16-point FFT");
   constexpr int N = P * Q;
-  constexpr int KPW = (P + RP_NW - 1) / RP_NW;
+  constexpr int NT = NW * 32;
+  constexpr int KPW = (P + NW - 1) / NW;
+  constexpr int HP = (P - 1) / 2;          // pairs of the symmetric DFT
+  constexpr int HSPLIT = (HP + 2) / 2;     // half A: X0 and pairs 1..HSPLIT-1, half B: pairs HSPLIT..HP
   MRIACL_DYN_SMEM(cf, Y);                       // [P][Q][32]
   cf* twsm = Y + N * RP_ROWS;                   // [N]
+  int* schsm = reinterpret_cast<int*>(twsm + N);
+  cf* tbuf = reinterpret_cast<cf*>(schsm + RP_SCHED_MAX);          // [n_buf][n_act][32]
+  float* avsm = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * p.n_act * RP_ROWS);   // (A > 1)
   float* osm = reinterpret_cast<float*>(Y);     // output tile [32][ow+1], aliases Y
-  float* avsm = reinterpret_cast<float*>(twsm + N);  // running sum over averages (A > 1 only)
-  __shared__ float red[RP_NW + 1];
+  __shared__ float red[NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int opitch = p.ow + 1;
-  for (int i = tid; i < N; i += RP_T) twsm[i] = p.tw[i];
+  for (int i = tid; i < N; i += NT) twsm[i] = p.tw[i];
+  for (int i = tid; i < p.sched_len; i += NT) schsm[i] = p.sched[i];
+  __syncthreads();
 
-  const int my_off = p.sched[warp];
+  const int my_off = schsm[warp];
   const int n_items = p.n_slices * p.n_tiles;
-  const long long frame_elems = (long long)p.n_act * p.oh;
+  const int n_frames = p.A * p.C;
+  const long long frame_elems = (long long)p.n_act * p.ohp;
+  const int tile_elems = p.n_act * RP_ROWS;           // complex elements of one prefetched block
+  const int n_copies = p.n_act * (RP_ROWS / 2);       // 16-byte copies per block
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int s = item / p.n_tiles, tile = item - s * p.n_tiles;
-    const int row = tile * RP_ROWS + lane;
-    const bool rvalid = row < p.oh;
-    if (p.A > 1) for (int i = tid; i < RP_ROWS * opitch; i += RP_T) avsm[i] = 0.f;
-    __syncthreads();   // twsm / avsm ready; previous item's tile fully consumed
+    const cf* Tit = p.T + (long long)s * n_frames * frame_elems + tile * RP_ROWS;
 
-    for (int a = 0; a < p.A; ++a) {
-      float acc[KPW][Q];
+    auto prefetch = [&](int f, int buf) {
+      const cf* src = Tit + (long long)f * frame_elems;
+      cf* dst = tbuf + (size_t)buf * tile_elems;
+      for (int i = tid; i < n_copies; i += NT) {
+        const int j = i >> 4, part = i & 15;
+        cp_async16(dst + j * RP_ROWS + 2 * part, src + (long long)j * p.ohp + 2 * part);
+      }
+      cp_async_commit();
+    };
+
+    if (p.A > 1) for (int i = tid; i < RP_ROWS * opitch; i += NT) avsm[i] = 0.f;
+    prefetch(0, 0);
+
+    float acc[KPW][Q];
+    for (int f = 0; f < n_frames; ++f) {
+      const int buf = p.n_buf == 2 ? (f & 1) : 0;
+      if (f % p.C == 0) {
 #pragma unroll
-      for (int kk = 0; kk < KPW; ++kk)
+        for (int kk = 0; kk < KPW; ++kk)
 #pragma unroll
-        for (int k2 = 0; k2 < Q; ++k2) acc[kk][k2] = 0.f;
+          for (int k2 = 0; k2 < Q; ++k2) acc[kk][k2] = 0.f;
+      }
+      if (p.n_buf == 2) {
+        if (f + 1 < n_frames) { prefetch(f + 1, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();   // block f visible; stage 2 of frame f-1 (and the previous item's tile reads) done
 
-      for (int c = 0; c < p.C; ++c) {
-        const cf* Tf = p.T + ((long long)(s * p.A + a) * p.C + c) * frame_elems + (rvalid ? row : 0);
-
-        // ---------------- stage 1: pruned P-point DFTs of my residues ----------------
-        const int n_units = p.sched[my_off];
+      // ---------------- stage 1: pruned P-point DFTs of my pieces ----------------
+      {
+        const cf* tb = tbuf + (size_t)buf * tile_elems + lane;
+        const int n_units = schsm[my_off];
         int off = my_off + 1;
         for (int u = 0; u < n_units; ++u) {
-          const int n2 = p.sched[off], type = p.sched[off + 1], nnz = p.sched[off + 2];
+          const int n2 = schsm[off], type = schsm[off + 1], nnz = schsm[off + 2];
           off += 3;
           cf* ycol = Y + n2 * RP_ROWS + lane;          // + k1 * Q * 32
-          if (type == 1) {
+          if (type != 0) {
             cf x[P];
 #pragma unroll
             for (int n1 = 0; n1 < P; ++n1) {
-              const int j = p.sched[off + n1];
-              x[n1] = (j >= 0 && rvalid) ? Tf[(long long)j * p.oh] : cf_make(0.f, 0.f);
+              const int j = schsm[off + n1];
+              x[n1] = j >= 0 ? tb[j * RP_ROWS] : cf_make(0.f, 0.f);
             }
             off += P;
-            dft_odd_sym<P, true>(x, [&](auto kc, cf val) {
+            auto emit = [&](auto kc, cf val) {
               constexpr int k1 = decltype(kc)::value;
               if (k1 != 0) val = cmul(val, twsm[(n2 * k1) % N]);
               ycol[k1 * Q * RP_ROWS] = val;
-            });
+            };
+            if (type == 1) dft_odd_sym_part<P, true, 1, HP + 1, true>(x, emit);
+            else if (type == 2) dft_odd_sym_part<P, true, 1, HSPLIT, true>(x, emit);
+            else dft_odd_sym_part<P, true, HSPLIT, HP + 1, false>(x, emit);
           } else {
-            cf xe[RP_MAX_SPARSE];
-            int ne[RP_MAX_SPARSE], idx[RP_MAX_SPARSE];
-#pragma unroll
-            for (int e = 0; e < RP_MAX_SPARSE; ++e) {
-              xe[e] = cf_make(0.f, 0.f); ne[e] = 0; idx[e] = 0;
-              if (e < nnz) {
-                ne[e] = p.sched[off + 2 * e];
-                const int j = p.sched[off + 2 * e + 1];
-                if (rvalid) xe[e] = Tf[(long long)j * p.oh];
-              }
+            const int* sch = schsm + off;
+            switch (nnz) {
+              case 0: rp_sparse_unit<P, Q, 0>(sch, tb, twsm, ycol); break;
+              case 1: rp_sparse_unit<P, Q, 1>(sch, tb, twsm, ycol); break;
+              case 2: rp_sparse_unit<P, Q, 2>(sch, tb, twsm, ycol); break;
+              case 3: rp_sparse_unit<P, Q, 3>(sch, tb, twsm, ycol); break;
+              case 4: rp_sparse_unit<P, Q, 4>(sch, tb, twsm, ycol); break;
+              case 5: rp_sparse_unit<P, Q, 5>(sch, tb, twsm, ycol); break;
+              default: rp_sparse_unit<P, Q, 6>(sch, tb, twsm, ycol); break;
             }
             off += 2 * nnz;
-            for (int k1 = 0; k1 < P; ++k1) {
-              float re = 0.f, im = 0.f;
+          }
+        }
+      }
+      __syncthreads();
+      if (p.n_buf == 1 && f + 1 < n_frames) prefetch(f + 1, 0);   // single buffer: overlap with stage 2 only
+
+      // ---------------- stage 2: Q-point FFT over n2, accumulate |X|^2 ----------------
 #pragma unroll
-              for (int e = 0; e < RP_MAX_SPARSE; ++e) {
-                if (e < nnz) {
-                  const cf w = twsm[idx[e]];
-                  re = fmaf(xe[e].x, w.x, fmaf(-xe[e].y, w.y, re));
-                  im = fmaf(xe[e].x, w.y, fmaf(xe[e].y, w.x, im));
-                  idx[e] += ne[e];
-                  if (idx[e] >= N) idx[e] -= N;
-                }
-              }
-              ycol[k1 * Q * RP_ROWS] = cf_make(re, im);
+      for (int kk = 0; kk < KPW; ++kk) {
+        const int k1 = warp + NW * kk;
+        if (k1 < P) {
+          cf v[Q];
+          const cf* yrow = Y + k1 * Q * RP_ROWS + lane;
+#pragma unroll
+          for (int n2 = 0; n2 < Q; ++n2) v[n2] = yrow[n2 * RP_ROWS];
+          fft16<true>(v);
+#pragma unroll
+          for (int k2 = 0; k2 < Q; ++k2) acc[kk][k2] = cnorm2_acc(v[k2], acc[kk][k2]);
+        }
+      }
+
+      // ---------------- end of an average: sqrt, shift + crop into the running tile ----------------
+      if (p.A > 1 && (f + 1) % p.C == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KPW; ++kk) {
+          const int k1 = warp + NW * kk;
+          if (k1 < P) {
+#pragma unroll
+            for (int k2 = 0; k2 < Q; ++k2) {
+              const int cc = phys_of_logical(k1 + P * k2, N) - p.col0;
+              if (cc >= 0 && cc < p.ow) avsm[lane * opitch + cc] += sqrtf(acc[kk][k2]) * p.scale;   // private owner
             }
           }
         }
-        __syncthreads();
-
-        // ---------------- stage 2: Q-point FFT over n2, accumulate |X|^2 ----------------
-#pragma unroll
-        for (int kk = 0; kk < KPW; ++kk) {
-          const int k1 = warp + RP_NW * kk;
-          if (k1 < P) {
-            cf v[Q];
-            const cf* yrow = Y + k1 * Q * RP_ROWS + lane;
-#pragma unroll
-            for (int n2 = 0; n2 < Q; ++n2) v[n2] = yrow[n2 * RP_ROWS];
-            fft16<true>(v);
-#pragma unroll
-            for (int k2 = 0; k2 < Q; ++k2) acc[kk][k2] = cnorm2_acc(v[k2], acc[kk][k2]);
-          }
-        }
-        __syncthreads();
       }
-
-      // ---------------- per-average epilogue: sqrt, shift + crop into the tile ----------------
+    }
+    __syncthreads();     // all stage-2 reads of Y done: the output tile may alias it
+    if (p.A == 1) {
 #pragma unroll
       for (int kk = 0; kk < KPW; ++kk) {
-        const int k1 = warp + RP_NW * kk;
+        const int k1 = warp + NW * kk;
         if (k1 < P) {
 #pragma unroll
           for (int k2 = 0; k2 < Q; ++k2) {
             const int cc = phys_of_logical(k1 + P * k2, N) - p.col0;
-            if (cc >= 0 && cc < p.ow) {
-              const float v = sqrtf(acc[kk][k2]) * p.scale;
-              if (p.A > 1) avsm[lane * opitch + cc] += v; else osm[lane * opitch + cc] = v;
-            }
+            if (cc >= 0 && cc < p.ow) osm[lane * opitch + cc] = sqrtf(acc[kk][k2]) * p.scale;
           }
         }
       }
-      // (A > 1: avsm is private per (lane, cc) owner, no barrier needed between averages)
+      __syncthreads();
     }
-    __syncthreads();
 
     // ---------------- write the tile (coalesced) and its statistics ----------------
     const float* tile_sm = p.A > 1 ? avsm : osm;
@@ -182,7 +264,7 @@ __global__ void __launch_bounds__(RP_T, 2) rowpass_kernel(RowPassParams p) {
     const int n_here = rows_here * p.ow;
     float* dst = p.out + ((long long)s * p.oh + tile * RP_ROWS) * p.ow;
     float lsum = 0.f;
-    for (int e = tid; e < n_here; e += RP_T) {
+    for (int e = tid; e < n_here; e += NT) {
       const int r = e / p.ow, cc = e - r * p.ow;
       float v = tile_sm[r * opitch + cc];
       if (p.A > 1) v *= inv_a;
@@ -190,22 +272,22 @@ __global__ void __launch_bounds__(RP_T, 2) rowpass_kernel(RowPassParams p) {
       lsum += v;
     }
     if (p.partials) {
-      const float mean = rp_block_sum(lsum, red) / (float)n_here;
+      const float mean = rp_block_sum<NW>(lsum, red) / (float)n_here;
       float lq = 0.f;
-      for (int e = tid; e < n_here; e += RP_T) {
+      for (int e = tid; e < n_here; e += NT) {
         const int r = e / p.ow, cc = e - r * p.ow;
         float v = tile_sm[r * opitch + cc];
         if (p.A > 1) v *= inv_a;
         const float d = v - mean;
         lq = fmaf(d, d, lq);
       }
-      const float m2 = rp_block_sum(lq, red);
+      const float m2 = rp_block_sum<NW>(lq, red);
       if (tid == 0) {
         float* q = p.partials + ((long long)s * p.n_tiles + tile) * 3;
         q[0] = (float)n_here; q[1] = mean; q[2] = m2;
       }
     }
-    // the loop-top barrier orders these tile reads before the next item's writes
+    __syncthreads();   // tile fully consumed before the next item's prefetch / stage 1 reuse the buffers
   }
 }
 
