@@ -50,7 +50,7 @@ int device_sms(int dev) {
 }
 
 constexpr int FUSED_P = 23, FUSED_Q = 16;
-constexpr int SMEM_MAX = 227 * 1024;           // dynamic shared memory a B200 CTA may opt in to
+constexpr int SMEM_MAX = 227 * 1024 - 512;     // dynamic shared memory a B200 CTA may opt in to (227 KB minus the kernels' static part)
 // warps of the row-pass CTA (one CTA per SM): 24 gives every k1 of stage 2 its own warp, 16 leaves
 // more registers per thread.  MRIACL_RP_WARPS=16|24 selects at run time (tuning knob).
 int rp_warps() {
