@@ -2,8 +2,9 @@
 //
 // One work item = (frame, group of <= 8 sampled phase-encode columns).  The CTA gathers the
 // group's columns from all 640 readout rows of complex64 k-space (the only HBM read of the
-// path; every 32-byte sector of a row that holds a sampled column is touched exactly once),
-// multiplies by the mask value, and runs the 640-point inverse DFT of each column in shared
+// path; every 32-byte sector of a row that holds a sampled column is touched exactly once)
+// with 8-byte cp.async straight into shared memory, one item ahead of the arithmetic (double
+// buffered), multiplies by the mask value, and runs the 640-point inverse DFT of each column in shared
 // memory as three in-place decimation-in-frequency passes 8 x 8 x 10:
 //
 //   n = 80 n1 + 10 n2 + n3   ->   m = m1 + 8 m2 + 64 m3
@@ -31,7 +32,8 @@ constexpr int CP_T = 160;        // threads per CTA: 2 column subsets x 80 butte
 constexpr int CP_G = 8;          // columns per work item
 constexpr int CP_BLK = 90;       // padded size of one n1/m1 block of 80
 constexpr int CP_PITCH = 722;    // complex elements between columns in shared memory (== 2 mod 16)
-constexpr int CP_SMEM_BYTES = CP_G * CP_PITCH * 8;
+constexpr int CP_BUF = CP_G * CP_PITCH;          // complex elements of one item buffer
+constexpr int CP_SMEM_BYTES = 2 * CP_BUF * 8;    // double buffered
 
 struct ColPassParams {
   const cf* ksp;                 // k-space, element (b,a,c,h,w) at b*sb + a*sa + (c*H + h)*W + w
@@ -39,6 +41,7 @@ struct ColPassParams {
   int A, C, W;
   const int* act_w;              // [n_act] physical (unpadded) column of active column j
   const float* act_m;            // [n_act] mask value of active column j
+  int unit_mask;                 // 1: every mask value is exactly 1 (skip the multiply)
   int n_act;
   int n_groups;                  // ceil(n_act / 8)
   const cf* tw;                  // w640^k = exp(+2 pi i k / 640)
@@ -48,12 +51,28 @@ struct ColPassParams {
   int n_frames;
 };
 
-__device__ __forceinline__ int cp_slot(int i) {   // logical index 0..639 -> padded slot
-  const int blk = i / 80;
-  return i + blk * (CP_BLK - 80);
+// 8-byte asynchronous global -> shared copy (LDGSTS): the gather needs one complex64 out of
+// every 32-byte sector, so 16-byte copies cannot be used.
+__device__ __forceinline__ void cp_async8(cf* smem_dst, const cf* gsrc) {
+#if defined(MRIACL_EMU)
+  *smem_dst = *gsrc;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit_group() {
+#if !defined(MRIACL_EMU)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N_PENDING> __device__ __forceinline__ void cp_async_wait_group() {
+#if !defined(MRIACL_EMU)
+  asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
+#endif
 }
 
-__global__ void __launch_bounds__(CP_T, 4) colpass640_kernel(ColPassParams p) {
+__global__ void __launch_bounds__(CP_T, 2) colpass640_kernel(ColPassParams p) {
   MRIACL_DYN_SMEM(cf, sm);
   const int tid = threadIdx.x;
   const int sub = tid / 80, pos = tid - sub * 80;
@@ -69,47 +88,70 @@ __global__ void __launch_bounds__(CP_T, 4) colpass640_kernel(ColPassParams p) {
       tw2[m] = p.tw[(8 * n3 * m) % CP_N];
     }
   }
-  // pass 3: thread r < 64 owns (m1, m2) = (r % 8, r / 8)
+  // pass 3: thread r < 64 owns (m1, m2) = (r % 8, r / 8); its ten outputs m = r + 64 m3 land on
+  // fixed rows of T (fftshift + crop + flip), computed once
   const int sub3 = tid / 64, r3 = tid - sub3 * 64;
   const int base3 = (r3 % 8) * CP_BLK + (r3 / 8) * 10;
+  int rr3[10];
+#pragma unroll
+  for (int m3 = 0; m3 < 10; ++m3) {
+    const int rfull = phys_of_logical(r3 + 64 * m3, CP_N);
+    const int rr = (p.flip ? CP_N - 1 - rfull : rfull) - p.row0;
+    rr3[m3] = (rr >= 0 && rr < p.oh) ? rr : -1;
+  }
 
-  const int k_ld = tid & 7, h_ld = tid >> 3;               // gather: 8 columns x 20 rows per sweep
+  // gather: thread (k, hs) copies rows h = 80 blk + 20 q + hs of column k; the logical index is
+  // (h + 320) mod 640 = 80 ((blk + 4) & 7) + 20 q + hs, i.e. slot 90 ((blk + 4) & 7) + 20 q + hs
+  const int k_ld = tid & 7, hs_ld = tid >> 3;
   const int n_items = p.n_frames * p.n_groups;
+  const long long row_step = 20LL * p.W;
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  auto issue_gather = [&](int item, int buf) {
     const int fl = item / p.n_groups, g = item - fl * p.n_groups;
     const int f = p.frame0 + fl;
     const int b = f / (p.A * p.C), a = (f / p.C) % p.A, c = f % p.C;
-    const cf* frame = p.ksp + b * p.sb + a * p.sa + (long long)c * CP_N * p.W;
     const int j0 = g * CP_G;
-    const int ncols = min(CP_G, p.n_act - j0);
-
-    // ---- gather + mask ---------------------------------------------------------------
-    if (k_ld < ncols) {
-      const int w = p.act_w[j0 + k_ld];
-      const float mv = p.act_m[j0 + k_ld];
-      const cf* src = frame + w;
-      cf* dst = sm + k_ld * CP_PITCH;
+    if (j0 + k_ld < p.n_act) {
+      const cf* src = p.ksp + b * p.sb + a * p.sa + ((long long)c * CP_N + hs_ld) * p.W + p.act_w[j0 + k_ld];
+      cf* dst = sm + buf * CP_BUF + k_ld * CP_PITCH + hs_ld;
 #pragma unroll
-      for (int it = 0; it < 32; it += 8) {
-        cf v[8];
+      for (int blk = 0; blk < 8; ++blk) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ld_stream(src + (long long)((it + u) * 20 + h_ld) * p.W);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int h = (it + u) * 20 + h_ld;
-          dst[cp_slot(logical_of_phys(h, CP_N))] = cscale(v[u], mv);
+        for (int q = 0; q < 4; ++q) {
+          cp_async8(dst + CP_BLK * ((blk + 4) & 7) + 20 * q, src);
+          src += row_step;
         }
       }
     }
+    cp_async_commit_group();
+  };
+
+  int buf = 0;
+  if (blockIdx.x < n_items) issue_gather(blockIdx.x, 0);
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
+    const int fl = item / p.n_groups, g = item - fl * p.n_groups;
+    const int j0 = g * CP_G;
+    const int ncols = min(CP_G, p.n_act - j0);
+    cf* cur = sm + buf * CP_BUF;
+
+    // prefetch the next item into the other buffer (its last readers finished before the barrier
+    // that ended the previous iteration), then wait for this item's gather
+    const int next = item + gridDim.x;
+    if (next < n_items) { issue_gather(next, buf ^ 1); cp_async_wait_group<1>(); } else cp_async_wait_group<0>();
     __syncthreads();
 
-    // ---- pass 1: radix-8 over n1 (stride 90), twiddle w640^{pos * m1} ---------------------
+    // ---- pass 1: radix-8 over n1 (stride 90), mask multiply, twiddle w640^{pos * m1} -------
     for (int k = sub; k < ncols; k += 2) {
-      cf* col = sm + k * CP_PITCH + pos;
+      cf* col = cur + k * CP_PITCH + pos;
       cf v[8];
 #pragma unroll
       for (int n1 = 0; n1 < 8; ++n1) v[n1] = col[n1 * CP_BLK];
+      if (!p.unit_mask) {
+        const float mv = p.act_m[j0 + k];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) v[n1] = cscale(v[n1], mv);
+      }
       radix8<true>(v);
       col[0] = v[0];
 #pragma unroll
@@ -119,7 +161,7 @@ __global__ void __launch_bounds__(CP_T, 4) colpass640_kernel(ColPassParams p) {
 
     // ---- pass 2: radix-8 over n2 (stride 10), twiddle w80^{n3 * m2} -----------------------
     for (int k = sub; k < ncols; k += 2) {
-      cf* col = sm + k * CP_PITCH + base2;
+      cf* col = cur + k * CP_PITCH + base2;
       cf v[8];
 #pragma unroll
       for (int n2 = 0; n2 < 8; ++n2) v[n2] = col[n2 * 10];
@@ -133,7 +175,7 @@ __global__ void __launch_bounds__(CP_T, 4) colpass640_kernel(ColPassParams p) {
     // ---- pass 3: radix-10 over n3 (contiguous), crop/shift/flip on the way out ------------
     if (tid < 128) {
       for (int k = sub3; k < ncols; k += 2) {
-        const float4* col4 = reinterpret_cast<const float4*>(sm + k * CP_PITCH + base3);
+        const float4* col4 = reinterpret_cast<const float4*>(cur + k * CP_PITCH + base3);
         cf v[10];
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
@@ -144,15 +186,11 @@ __global__ void __launch_bounds__(CP_T, 4) colpass640_kernel(ColPassParams p) {
         radix10<true>(v);
         cf* dst = p.T + ((long long)fl * p.n_act + j0 + k) * p.ohp;
 #pragma unroll
-        for (int m3 = 0; m3 < 10; ++m3) {
-          const int m = r3 + 64 * m3;
-          const int rfull = phys_of_logical(m, CP_N);
-          const int rr = (p.flip ? CP_N - 1 - rfull : rfull) - p.row0;
-          if (rr >= 0 && rr < p.oh) dst[rr] = v[m3];
-        }
+        for (int m3 = 0; m3 < 10; ++m3)
+          if (rr3[m3] >= 0) dst[rr3[m3]] = v[m3];
       }
     }
-    __syncthreads();
+    __syncthreads();   // this buffer is free for the gather issued in the next iteration
   }
 }
 

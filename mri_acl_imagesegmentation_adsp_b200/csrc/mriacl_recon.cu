@@ -124,6 +124,8 @@ struct FusedPlanDev {
   int* act_w = nullptr;
   float* act_m = nullptr;
   int* sched = nullptr;
+  cf* sptw = nullptr;
+  bool unit_mask = true;
   cf* twH = nullptr;
   cf* twW = nullptr;
 };
@@ -156,7 +158,11 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     if (na && (rt_upload(a, h.act_w.data(), sizeof(int) * na) || rt_upload(m, h.act_m.data(), sizeof(float) * na)))
       return nullptr;
     if (rt_upload(s, h.sched.data(), sizeof(int) * h.sched.size())) return nullptr;
-    pl->act_w = (int*)a; pl->act_m = (float*)m; pl->sched = (int*)s;
+    void* t = nullptr;
+    if (rt_malloc(&t, sizeof(HostCf) * h.sptw.size())) return nullptr;
+    if (!h.sptw.empty() && rt_upload(t, h.sptw.data(), sizeof(HostCf) * h.sptw.size())) return nullptr;
+    pl->act_w = (int*)a; pl->act_m = (float*)m; pl->sched = (int*)s; pl->sptw = (cf*)t;
+    for (float v : h.act_m) if (v != 1.0f) pl->unit_mask = false;
     pl->twH = get_twiddles(dev, H, +1);
     pl->twW = get_twiddles(dev, Wp, +1);
     if (!pl->twH || !pl->twW) return nullptr;
@@ -315,7 +321,8 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
     if (rowpass_smem_bytes(rp_fixed, n_act, 2, ow, A) > SMEM_MAX) n_buf = 1;
     const int rp_smem = rowpass_smem_bytes(rp_fixed, n_act, n_buf, ow, A);
     if (rp_smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, ow, A);
-    if ((int)pl->host.sched.size() > RP_SCHED_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass schedule too long");
+    if ((int)pl->host.sched.size() > RP_SCHED_MAX || (int)pl->host.sptw.size() > RP_SPTW_MAX)
+      return fail(MRIACL_ERR_UNSUPPORTED, "row-pass schedule too long");
     for (int s0 = 0; s0 < B; s0 += chunk) {
       const int ns = std::min(chunk, B - s0);
       cf* T = (cf*)workspace;
@@ -323,16 +330,16 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
       if (n_groups > 0 && do_col) {
         ColPassParams cp{};
         cp.ksp = ksp; cp.sb = slice_stride; cp.sa = avg_stride; cp.A = A; cp.C = C; cp.W = W;
-        cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.n_act = n_act; cp.n_groups = n_groups;
+        cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
         cp.tw = pl->twH; cp.T = T; cp.oh = oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
         cp.frame0 = s0 * A * C; cp.n_frames = ns * A * C;
         const long long items = (long long)cp.n_frames * n_groups;
-        const int grid = (int)std::min<long long>(items, (long long)sms * 4);
+        const int grid = (int)std::min<long long>(items, (long long)sms * 2);
         MRIACL_LAUNCH(colpass640_kernel, grid, CP_T, CP_SMEM_BYTES, st, cp);
       }
       RowPassParams rp{};
       rp.T = T; rp.n_act = n_act; rp.oh = oh; rp.ohp = ohp; rp.sched = pl->sched; rp.sched_len = (int)pl->host.sched.size();
-      rp.n_buf = n_buf; rp.tw = pl->twW;
+      rp.n_buf = n_buf; rp.tw = pl->twW; rp.sptw = pl->sptw; rp.sptw_len = (int)pl->host.sptw.size();
       rp.out = out + (size_t)s0 * oh * ow; rp.partials = partials; rp.ow = ow; rp.col0 = col0;
       rp.A = A; rp.C = C; rp.scale = (float)(1.0 / std::sqrt((double)H * (double)Wp));
       rp.n_slices = ns; rp.n_tiles = g.n_tiles;

@@ -53,6 +53,7 @@ struct FusedPlanHost {
   std::vector<int> act_w;       // physical (unpadded) column index of active column j, ascending
   std::vector<float> act_m;     // its mask value
   std::vector<int> sched;       // row-pass schedule (layout below)
+  std::vector<HostCf> sptw;     // twiddles of the sparse residues: [entry][SPTW_PITCH], w_N^{n_e k1}
   std::vector<double> warp_cost;
 };
 
@@ -62,7 +63,9 @@ struct FusedPlanHost {
 //     type 1 (dense):  payload = P ints: active-column index j of n1 = 0..P-1, or -1
 //     type 2 / 3 (dense, first / second half of the outputs): same payload; used when
 //                      split_dense so that one dense residue is shared by two warps
-//     type 0 (sparse): payload = nnz pairs (n, j): logical index n = Q n1 + n2 and column j
+//     type 0 (sparse): payload = offset of the unit's first row in sptw, then nnz column indices j;
+//                      sptw row e holds w_N^{n_e k1}, k1 = 0..P-1 (n_e = Q n1 + n2 logical index)
+constexpr int SPTW_PITCH = 24;   // complex elements per sptw row (P = 23 padded to a 16-byte multiple)
 inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow, const float* mask,
                              int P, int Q, int n_warps, int max_sparse, bool split_dense, FusedPlanHost& pl) {
   pl.H = H; pl.W = W; pl.pad_left = pad_left; pl.Wp = Wp; pl.oh = oh; pl.ow = ow;
@@ -76,10 +79,12 @@ inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow,
   }
   struct Unit { int n2, type, nnz; std::vector<int> payload; double cost; };
   std::vector<Unit> units;
+  const std::vector<HostCf> twN = make_twiddles(Wp, +1);
+  pl.sptw.clear();
   for (int n2 = 0; n2 < Q; ++n2) {
     Unit u; u.n2 = n2;
     std::vector<int> jn1(P, -1);
-    std::vector<int> pairs;
+    std::vector<int> pairs;   // (n, j)
     int nnz = 0;
     for (int n1 = 0; n1 < P; ++n1) {
       const int n = Q * n1 + n2;
@@ -104,7 +109,15 @@ inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow,
         units.push_back(u);
       }
     } else {
-      u.type = 0; u.payload = pairs; u.cost = 20.0 + P * (8.0 * nnz + 4.0);
+      u.type = 0; u.cost = 20.0 + P * (5.0 * nnz + 2.0);
+      u.payload.clear();
+      u.payload.push_back((int)pl.sptw.size());
+      for (int e = 0; e < nnz; ++e) {
+        const int n = pairs[2 * e];
+        u.payload.push_back(pairs[2 * e + 1]);
+        for (int k1 = 0; k1 < SPTW_PITCH; ++k1)
+          pl.sptw.push_back(k1 < P ? twN[(size_t)(((long long)n * k1) % Wp)] : HostCf{0.f, 0.f});
+      }
       units.push_back(u);
     }
   }

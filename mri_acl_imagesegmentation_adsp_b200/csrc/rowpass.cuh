@@ -23,13 +23,16 @@ namespace mriacl {
 
 constexpr int RP_ROWS = 32;        // rows per tile (= lanes)
 constexpr int RP_MAX_SPARSE = 6;   // a residue with more sampled columns than this is "dense"
-constexpr int RP_SCHED_MAX = 2048; // ints of schedule kept in shared memory
+constexpr int RP_SCHED_MAX = 1024; // ints of schedule kept in shared memory
+constexpr int RP_SPTW_MAX = 16 * RP_MAX_SPARSE * 24;   // complex twiddles of the sparse residues (worst case)
 
 struct RowPassParams {
   const cf* T;           // [n_slices*A*C][n_act][ohp]
   int n_act, oh, ohp;    // ohp = row pitch of T (multiple of 32)
   const int* sched;      // warp schedule, see plan.h
   int sched_len;
+  const cf* sptw;        // [sptw_len] twiddle rows of the sparse residues, pitch 24
+  int sptw_len;
   const cf* tw;          // w_N^k = exp(+2 pi i k / N)
   float* out;            // [n_slices][oh][ow]  (already offset to the first slice of the launch)
   float* partials;       // [n_slices][n_tiles][3] (count, mean, M2) or nullptr
@@ -40,9 +43,9 @@ struct RowPassParams {
   int n_buf;             // 1 or 2 prefetch buffers
 };
 
-// shared memory: Y [P][Q][32] | twiddles [N] | schedule | T buffers | (A > 1) average tile
+// shared memory: Y [P][Q][32] | twiddles [N] | sparse twiddle rows | schedule | T buffers | (A > 1) average tile
 template <int P, int Q> __host__ __device__ constexpr int rowpass_fixed_smem() {
-  return P * Q * RP_ROWS * 8 + P * Q * 8 + RP_SCHED_MAX * 4;
+  return P * Q * RP_ROWS * 8 + P * Q * 8 + RP_SPTW_MAX * 8 + RP_SCHED_MAX * 4;
 }
 inline int rowpass_smem_bytes(int fixed, int n_act, int n_buf, int ow, int A) {
   return fixed + n_buf * n_act * RP_ROWS * 8 + (A > 1 ? RP_ROWS * (ow + 1) * 4 : 0);
@@ -79,30 +82,29 @@ template <int NW> __device__ __forceinline__ float rp_block_sum(float v, float* 
   return t;
 }
 
-// sparse residue with exactly NNZ sampled columns: Y'[k1] = sum_e x_e w_N^{n_e k1}
+// sparse residue with exactly NNZ sampled columns: Y'[k1] = sum_e x_e w_N^{n_e k1}; the twiddle
+// rows were tabulated by the host plan, so every operand is a shared-memory load at an immediate offset
 template <int P, int Q, int NNZ>
-__device__ __forceinline__ void rp_sparse_unit(const int* sch, const cf* tb, const cf* twsm, cf* ycol) {
-  constexpr int N = P * Q;
+__device__ __forceinline__ void rp_sparse_unit(const int* sch, const cf* tb, const cf* sptw, cf* ycol) {
+  constexpr int PITCH = 24;
+  static_assert(P <= PITCH && PITCH % 2 == 0, "sptw row pitch");
   cf xe[NNZ > 0 ? NNZ : 1];
-  int ne[NNZ > 0 ? NNZ : 1], idx[NNZ > 0 ? NNZ : 1];
+  const float4* tw4 = reinterpret_cast<const float4*>(sptw + sch[0]);
 #pragma unroll
-  for (int e = 0; e < NNZ; ++e) {
-    ne[e] = sch[2 * e];
-    xe[e] = tb[sch[2 * e + 1] * RP_ROWS];
-    idx[e] = 0;
-  }
-#pragma unroll 1
-  for (int k1 = 0; k1 < P; ++k1) {
-    float re = 0.f, im = 0.f;
+  for (int e = 0; e < NNZ; ++e) xe[e] = tb[sch[1 + e] * RP_ROWS];
+#pragma unroll
+  for (int kp = 0; kp < PITCH / 2; ++kp) {
+    float re0 = 0.f, im0 = 0.f, re1 = 0.f, im1 = 0.f;
 #pragma unroll
     for (int e = 0; e < NNZ; ++e) {
-      const cf w = twsm[idx[e]];
-      re = fmaf(xe[e].x, w.x, fmaf(-xe[e].y, w.y, re));
-      im = fmaf(xe[e].x, w.y, fmaf(xe[e].y, w.x, im));
-      idx[e] += ne[e];
-      if (idx[e] >= N) idx[e] -= N;
+      const float4 w = tw4[e * (PITCH / 2) + kp];       // twiddles of k1 = 2 kp and 2 kp + 1
+      re0 = fmaf(xe[e].x, w.x, fmaf(-xe[e].y, w.y, re0));
+      im0 = fmaf(xe[e].x, w.y, fmaf(xe[e].y, w.x, im0));
+      re1 = fmaf(xe[e].x, w.z, fmaf(-xe[e].y, w.w, re1));
+      im1 = fmaf(xe[e].x, w.w, fmaf(xe[e].y, w.z, im1));
     }
-    ycol[k1 * Q * RP_ROWS] = cf_make(re, im);
+    ycol[(2 * kp) * Q * RP_ROWS] = cf_make(re0, im0);
+    if (2 * kp + 1 < P) ycol[(2 * kp + 1) * Q * RP_ROWS] = cf_make(re1, im1);
   }
 }
 
@@ -116,7 +118,8 @@ __global__ void __launch_bounds__(NW * 32, 1) rowpass_kernel(RowPassParams p) {
   constexpr int HSPLIT = (HP + 2) / 2;     // half A: X0 and pairs 1..HSPLIT-1, half B: pairs HSPLIT..HP
   MRIACL_DYN_SMEM(cf, Y);                       // [P][Q][32]
   cf* twsm = Y + N * RP_ROWS;                   // [N]
-  int* schsm = reinterpret_cast<int*>(twsm + N);
+  cf* sptwsm = twsm + N;                        // [RP_SPTW_MAX]
+  int* schsm = reinterpret_cast<int*>(sptwsm + RP_SPTW_MAX);
   cf* tbuf = reinterpret_cast<cf*>(schsm + RP_SCHED_MAX);          // [n_buf][n_act][32]
   float* avsm = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * p.n_act * RP_ROWS);   // (A > 1)
   float* osm = reinterpret_cast<float*>(Y);     // output tile [32][ow+1], aliases Y
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(NW * 32, 1) rowpass_kernel(RowPassParams p) {
   const int opitch = p.ow + 1;
   for (int i = tid; i < N; i += NT) twsm[i] = p.tw[i];
   for (int i = tid; i < p.sched_len; i += NT) schsm[i] = p.sched[i];
+  for (int i = tid; i < p.sptw_len; i += NT) sptwsm[i] = p.sptw[i];
   __syncthreads();
 
   const int my_off = schsm[warp];
@@ -139,12 +143,14 @@ __global__ void __launch_bounds__(NW * 32, 1) rowpass_kernel(RowPassParams p) {
     const int s = item / p.n_tiles, tile = item - s * p.n_tiles;
     const cf* Tit = p.T + (long long)s * n_frames * frame_elems + tile * RP_ROWS;
 
+    // thread i copies the 16-byte piece (j, part) = (i / 16, i % 16) of the block, then j += NT / 16
     auto prefetch = [&](int f, int buf) {
-      const cf* src = Tit + (long long)f * frame_elems;
-      cf* dst = tbuf + (size_t)buf * tile_elems;
+      const cf* src = Tit + (long long)f * frame_elems + (long long)(tid >> 4) * p.ohp + 2 * (tid & 15);
+      cf* dst = tbuf + (size_t)buf * tile_elems + (tid >> 4) * RP_ROWS + 2 * (tid & 15);
       for (int i = tid; i < n_copies; i += NT) {
-        const int j = i >> 4, part = i & 15;
-        cp_async16(dst + j * RP_ROWS + 2 * part, src + (long long)j * p.ohp + 2 * part);
+        cp_async16(dst, src);
+        src += (long long)(NT / 16) * p.ohp;
+        dst += (NT / 16) * RP_ROWS;
       }
       cp_async_commit();
     };
@@ -196,15 +202,15 @@ __global__ void __launch_bounds__(NW * 32, 1) rowpass_kernel(RowPassParams p) {
           } else {
             const int* sch = schsm + off;
             switch (nnz) {
-              case 0: rp_sparse_unit<P, Q, 0>(sch, tb, twsm, ycol); break;
-              case 1: rp_sparse_unit<P, Q, 1>(sch, tb, twsm, ycol); break;
-              case 2: rp_sparse_unit<P, Q, 2>(sch, tb, twsm, ycol); break;
-              case 3: rp_sparse_unit<P, Q, 3>(sch, tb, twsm, ycol); break;
-              case 4: rp_sparse_unit<P, Q, 4>(sch, tb, twsm, ycol); break;
-              case 5: rp_sparse_unit<P, Q, 5>(sch, tb, twsm, ycol); break;
-              default: rp_sparse_unit<P, Q, 6>(sch, tb, twsm, ycol); break;
+              case 0: rp_sparse_unit<P, Q, 0>(sch, tb, sptwsm, ycol); break;
+              case 1: rp_sparse_unit<P, Q, 1>(sch, tb, sptwsm, ycol); break;
+              case 2: rp_sparse_unit<P, Q, 2>(sch, tb, sptwsm, ycol); break;
+              case 3: rp_sparse_unit<P, Q, 3>(sch, tb, sptwsm, ycol); break;
+              case 4: rp_sparse_unit<P, Q, 4>(sch, tb, sptwsm, ycol); break;
+              case 5: rp_sparse_unit<P, Q, 5>(sch, tb, sptwsm, ycol); break;
+              default: rp_sparse_unit<P, Q, 6>(sch, tb, sptwsm, ycol); break;
             }
-            off += 2 * nnz;
+            off += 1 + nnz;
           }
         }
       }
