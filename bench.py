@@ -274,8 +274,25 @@ def ours(args) -> None:
 
         reps = max(5, min(args.steps, 20))
         sampler.active = True
-        for name, flag in (("colpass640", cabi.ONLY_COLPASS), ("rowpass_23x16", cabi.ONLY_ROWPASS),
-                           ("normalize_instance", cabi.ONLY_NORM)):
+        names = (("colpass640", cabi.ONLY_COLPASS), ("rowpass_23x16", cabi.ONLY_ROWPASS),
+                 ("normalize_instance", cabi.ONLY_NORM))
+        # (a) in pipeline order: the three phases of the same plan back to back, events in between
+        for _ in range(3):
+            for _, flag in names:
+                phase(flag)
+        torch.cuda.synchronize()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(reps)]
+        for r in range(reps):
+            for i, (_, flag) in enumerate(names):
+                evs[r][i].record()
+                phase(flag)
+            evs[r][3].record()
+        torch.cuda.synchronize()
+        for i, (name, _) in enumerate(names):
+            kern[name] = float(np.mean([evs[r][i].elapsed_time(evs[r][i + 1]) for r in range(reps)]))
+        kern["sum_in_pipeline"] = float(np.mean([evs[r][0].elapsed_time(evs[r][3]) for r in range(reps)]))
+        # (b) each phase alone, repeated (warm caches for its own working set)
+        for name, flag in names:
             for _ in range(3):
                 phase(flag)
             torch.cuda.synchronize()
@@ -285,7 +302,7 @@ def ours(args) -> None:
                 phase(flag)
             b.record()
             torch.cuda.synchronize()
-            kern[name] = a.elapsed_time(b) / reps
+            kern[name + "_alone"] = a.elapsed_time(b) / reps
         sampler.active = False
     if world > 1:
         dist.barrier()

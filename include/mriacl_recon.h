@@ -45,6 +45,8 @@ extern "C" {
 #define MRIACL_FLIP_ROWS      0x1u  /* np.flipud of each combined image (ZIP!/fastmri_prostate/reconstruction/t2/prostate_t2_recon.py:101) */
 #define MRIACL_NORM_INSTANCE  0x2u  /* (x-mean)/(std+eps), unbiased std (ZIP!/DL_reconstruction/data/transforms.py:143-162) */
 #define MRIACL_FORCE_GENERIC  0x4u  /* testing: use the generic (any-size) kernels even where a fused plan exists */
+#define MRIACL_SEQUENTIAL     0x8u  /* fused plan: run column pass, row pass, normalise back to back on the caller's
+                                       stream instead of the overlapped two-stream schedule */
 /* profiling only (bench.py's per-kernel timing): run just the named phase(s) of the fused plan;
  * none set = the whole stage.  The workspace must still hold the previous phase's output. */
 #define MRIACL_ONLY_COLPASS   0x100u
@@ -60,7 +62,7 @@ int         mriacl_abi_version(void);
 const char* mriacl_last_error(void);
 
 /* Which kernels serve a (H, W_padded) transform: MRIACL_PATH_FUSED for the shapes with a
- * hand-scheduled fused plan (640x368 knee, 640x640 padded prostate), MRIACL_PATH_GENERIC
+ * hand-scheduled fused plan (640x368 knee), MRIACL_PATH_GENERIC
  * for any other size up to MRIACL_MAX_LINE per axis, MRIACL_PATH_NONE beyond that. */
 #define MRIACL_MAX_LINE 4096
 int mriacl_supported(int H, int W_padded);

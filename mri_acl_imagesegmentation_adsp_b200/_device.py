@@ -13,9 +13,9 @@ import torch
 
 from .adapters import recon_cabi
 
-#: slices processed per launch group of the fused stage (bounds the intermediate that has to stay
-#: L2-resident between the column and the row pass); override with MRIACL_CHUNK_SLICES
-DEFAULT_CHUNK_SLICES = int(os.environ.get("MRIACL_CHUNK_SLICES", "16"))
+#: slices per launch group of the fused stage = slices the workspace can hold (4.4 MB of intermediate
+#: per 15-coil knee slice at 4x); larger batches are cut into groups.  Override with MRIACL_CHUNK_SLICES
+DEFAULT_CHUNK_SLICES = int(os.environ.get("MRIACL_CHUNK_SLICES", "64"))
 
 _workspaces: dict = {}
 

@@ -16,7 +16,7 @@ from typing import Optional
 ABI_VERSION = 1
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
-FLIP_ROWS, NORM_INSTANCE, FORCE_GENERIC = 0x1, 0x2, 0x4
+FLIP_ROWS, NORM_INSTANCE, FORCE_GENERIC, SEQUENTIAL = 0x1, 0x2, 0x4, 0x8
 ONLY_COLPASS, ONLY_ROWPASS, ONLY_NORM = 0x100, 0x200, 0x400   # profiling: single phases of the fused plan
 PATH_NONE, PATH_GENERIC, PATH_FUSED = 0, 1, 2
 

@@ -33,7 +33,8 @@ constexpr int CP_G = 8;          // columns per work item
 constexpr int CP_BLK = 90;       // padded size of one n1/m1 block of 80
 constexpr int CP_PITCH = 722;    // complex elements between columns in shared memory (== 2 mod 16)
 constexpr int CP_BUF = CP_G * CP_PITCH;          // complex elements of one item buffer
-constexpr int CP_SMEM_BYTES = 2 * CP_BUF * 8;    // double buffered
+constexpr int CP_SMEM_BYTES_DB = 2 * CP_BUF * 8; // persistent, double buffered
+constexpr int CP_SMEM_BYTES_SB = CP_BUF * 8;     // one item per CTA, single buffer
 
 struct ColPassParams {
   const cf* ksp;                 // k-space, element (b,a,c,h,w) at b*sb + a*sa + (c*H + h)*W + w
@@ -49,6 +50,7 @@ struct ColPassParams {
   int oh, ohp, row0, flip;       // ohp = row pitch of T (multiple of 32)
   int frame0;                    // first global frame of this launch (f = (b*A + a)*C + c)
   int n_frames;
+  int* done;                     // optional [n_slices]: += 1 per finished item of the slice (row pass waits on it)
 };
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): the gather needs one complex64 out of
@@ -72,7 +74,10 @@ template <int N_PENDING> __device__ __forceinline__ void cp_async_wait_group() {
 #endif
 }
 
-__global__ void __launch_bounds__(CP_T, 2) colpass640_kernel(ColPassParams p) {
+// DB = true: persistent grid, next item's gather in flight during the arithmetic (2 CTAs/SM);
+// DB = false: one item per CTA, single buffer (4 CTAs/SM; leaves room for a row-pass CTA on the SM).
+template <bool DB>
+__global__ void __launch_bounds__(CP_T, DB ? 2 : 4) colpass640_kernel(ColPassParams p) {
   MRIACL_DYN_SMEM(cf, sm);
   const int tid = threadIdx.x;
   const int sub = tid / 80, pos = tid - sub * 80;
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(CP_T, 2) colpass640_kernel(ColPassParams p) {
   int buf = 0;
   if (blockIdx.x < n_items) issue_gather(blockIdx.x, 0);
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= (DB ? 1 : 0)) {
     const int fl = item / p.n_groups, g = item - fl * p.n_groups;
     const int j0 = g * CP_G;
     const int ncols = min(CP_G, p.n_act - j0);
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(CP_T, 2) colpass640_kernel(ColPassParams p) {
     // prefetch the next item into the other buffer (its last readers finished before the barrier
     // that ended the previous iteration), then wait for this item's gather
     const int next = item + gridDim.x;
-    if (next < n_items) { issue_gather(next, buf ^ 1); cp_async_wait_group<1>(); } else cp_async_wait_group<0>();
+    if (DB && next < n_items) { issue_gather(next, buf ^ 1); cp_async_wait_group<1>(); } else cp_async_wait_group<0>();
     __syncthreads();
 
     // ---- pass 1: radix-8 over n1 (stride 90), mask multiply, twiddle w640^{pos * m1} -------
@@ -190,7 +195,14 @@ __global__ void __launch_bounds__(CP_T, 2) colpass640_kernel(ColPassParams p) {
           if (rr3[m3] >= 0) dst[rr3[m3]] = v[m3];
       }
     }
-    __syncthreads();   // this buffer is free for the gather issued in the next iteration
+    if (p.done) {        // publish: T rows of this item are visible device-wide before the count moves
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(p.done + fl / (p.A * p.C), 1);
+    } else {
+      __syncthreads();   // this buffer is free for the gather issued in the next iteration
+    }
+    if (!DB) break;
   }
 }
 

@@ -51,12 +51,11 @@ int device_sms(int dev) {
 
 constexpr int FUSED_P = 23, FUSED_Q = 16;
 constexpr int SMEM_MAX = 227 * 1024 - 512;     // dynamic shared memory a B200 CTA may opt in to (227 KB minus the kernels' static part)
-// warps of the row-pass CTA (one CTA per SM): 24 gives every k1 of stage 2 its own warp, 16 leaves
-// more registers per thread.  MRIACL_RP_WARPS=16|24 selects at run time (tuning knob).
-int rp_warps() {
-  static int nw = [] { const char* e = getenv("MRIACL_RP_WARPS"); return (e && atoi(e) == 16) ? 16 : 24; }();
-  return nw;
-}
+// Row-pass CTA shapes: 16 warps (one CTA owns the SM) for the sequential schedule, 8 warps for the
+// overlapped schedule, where one row-pass CTA shares each SM with column-pass CTAs.
+constexpr int RP_NW_SEQ = 16, RP_NW_OVL = 8;
+
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
 constexpr int GEN_SMEM_BYTES = 2 * MRIACL_GEN_SMEM_ELEMS * 8;
 
@@ -66,9 +65,10 @@ int ensure_smem_attrs(int dev) {
   if (d.smem_set) return 0;
   int bad = 0;
   bad |= rt_allow_smem((const void*)generic_fft_kernel, GEN_SMEM_BYTES);
-  bad |= rt_allow_smem((const void*)colpass640_kernel, CP_SMEM_BYTES);
-  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, 24>, SMEM_MAX);
-  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, 16>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)colpass640_kernel<true>, CP_SMEM_BYTES_DB);
+  bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB);
+  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX);
   if (!bad) d.smem_set = true;
   return bad;
 }
@@ -118,7 +118,9 @@ int get_device_mask(int dev, const float* mask, int w, const float** out) {
 }
 
 struct FusedPlanDev {
-  FusedPlanHost host;
+  FusedPlanHost host;            // schedule for RP_NW_SEQ warps
+  FusedPlanHost host_ovl;        // schedule for RP_NW_OVL warps (same columns, same sptw)
+  int* sched_ovl = nullptr;
   std::vector<float> mask_copy;
   bool has_mask = false;
   int* act_w = nullptr;
@@ -146,7 +148,8 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     }
   }
   auto pl = std::make_shared<FusedPlanDev>();
-  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, FUSED_P, FUSED_Q, rp_warps(), RP_MAX_SPARSE, /*split_dense=*/true, pl->host);
+  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, FUSED_P, FUSED_Q, RP_NW_SEQ, RP_MAX_SPARSE, /*split_dense=*/true, pl->host);
+  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, FUSED_P, FUSED_Q, RP_NW_OVL, RP_MAX_SPARSE, /*split_dense=*/true, pl->host_ovl);
   pl->has_mask = mask != nullptr;
   if (mask) pl->mask_copy.assign(mask, mask + W);
   if (device_side) {
@@ -161,6 +164,10 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     void* t = nullptr;
     if (rt_malloc(&t, sizeof(HostCf) * h.sptw.size())) return nullptr;
     if (!h.sptw.empty() && rt_upload(t, h.sptw.data(), sizeof(HostCf) * h.sptw.size())) return nullptr;
+    void* s2 = nullptr;
+    if (rt_malloc(&s2, sizeof(int) * pl->host_ovl.sched.size()) ||
+        rt_upload(s2, pl->host_ovl.sched.data(), sizeof(int) * pl->host_ovl.sched.size())) return nullptr;
+    pl->sched_ovl = (int*)s2;
     pl->act_w = (int*)a; pl->act_m = (float*)m; pl->sched = (int*)s; pl->sptw = (cf*)t;
     for (float v : h.act_m) if (v != 1.0f) pl->unit_mask = false;
     pl->twH = get_twiddles(dev, H, +1);
@@ -191,7 +198,7 @@ int recon_geom(int A, int C, int H, int W, int pad_left, int Wp, int oh, int ow,
     g.n_act = n_act;
     const size_t ohp = (size_t)g.n_tiles * RP_ROWS;
     g.t_bytes = align_up((size_t)A * C * (size_t)(n_act > 0 ? n_act : 1) * ohp * sizeof(cf), 256);
-    g.per_slice = g.t_bytes + align_up((size_t)g.n_tiles * 3 * sizeof(float), 256);
+    g.per_slice = g.t_bytes + align_up((size_t)g.n_tiles * 3 * sizeof(float), 256) + 256;   // + completion counter
   } else {
     g.n_act = W;
     g.t_bytes = align_up((size_t)A * C * H * Wp * sizeof(cf), 256);
@@ -246,6 +253,154 @@ int generic_fft2c(const cf* in, long long sb, long long sa, int A, int C, cf* ou
   c.out_es = Wp; c.out_ls = 1; c.out_fs = (long long)H * Wp;
   c.inverse = inverse; c.scale = (float)(1.0 / std::sqrt((double)H));
   return launch_generic_pass(c, dev, st);
+}
+
+// ---- side stream + events of the overlapped schedule, one set per (device, caller stream) ----
+struct OverlapRes { rt_stream_t side = nullptr; rt_event_t ev_start[2], ev_row[2]; bool ok = false; };
+std::map<std::pair<int, void*>, OverlapRes> g_ovl;
+
+OverlapRes* get_overlap_res(int dev, rt_stream_t st) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  OverlapRes& r = g_ovl[{dev, (void*)st}];
+  if (!r.ok) {
+    int bad = rt_stream_create_high_priority(&r.side);
+    for (int i = 0; i < 2; ++i) { bad |= rt_event_create(&r.ev_start[i]); bad |= rt_event_create(&r.ev_row[i]); }
+    if (bad) return nullptr;
+    r.ok = true;
+  }
+  return &r;
+}
+
+struct FusedArgs {
+  const cf* ksp; long long slice_stride, avg_stride; const float* mask; float* out; float* mean_std;
+  int B, A, C, H, W, pad_left, Wp, oh, ow; unsigned flags; float eps;
+  void* workspace; size_t workspace_bytes; rt_stream_t st; int dev, sms;
+};
+
+// The fused 640x368 plan.  Two schedules:
+//  sequential  column pass (persistent, double-buffered gather) -> row pass (16 warps, one CTA per SM)
+//              -> normalise, back to back on the caller's stream, `chunk` slices per group;
+//  overlapped  (default on the device) the row pass is ONE persistent launch per group on a side stream
+//              with 8-warp CTAs that leave room for column-pass CTAs on every SM; it consumes slices as the
+//              concurrently running column pass (caller's stream) publishes them through per-slice counters,
+//              so the HBM-bound gather and the issue-bound row transform share the SMs and the intermediate
+//              is read back while still in L2.  The side stream is joined to the caller's stream at the end.
+int run_fused(const FusedArgs& a, const ReconGeom& g) {
+  std::shared_ptr<FusedPlanDev> pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
+  if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
+  const int n_act = (int)pl->host.act_w.size();
+  const int n_groups = (n_act + CP_G - 1) / CP_G;
+  const int ohp = g.n_tiles * RP_ROWS;
+  const int row0 = crop_start(a.H, a.oh), col0 = crop_start(a.Wp, a.ow);
+  const bool want_norm = (a.flags & MRIACL_NORM_INSTANCE) != 0;
+  const int flip = (a.flags & MRIACL_FLIP_ROWS) ? 1 : 0;
+  const unsigned only = a.flags & (MRIACL_ONLY_COLPASS | MRIACL_ONLY_ROWPASS | MRIACL_ONLY_NORM);
+  const bool do_col = !only || (only & MRIACL_ONLY_COLPASS);
+  const bool do_row = !only || (only & MRIACL_ONLY_ROWPASS);
+  const bool do_norm = !only || (only & MRIACL_ONLY_NORM);
+#ifdef MRIACL_EMU
+  const bool overlap_default = false;
+#else
+  const bool overlap_default = true;
+#endif
+  static const bool overlap_env = env_int("MRIACL_OVERLAP", overlap_default ? 1 : 0) != 0;
+  const bool overlap = overlap_env && !only && !(a.flags & MRIACL_SEQUENTIAL) && n_groups > 0;
+
+  const FusedPlanHost& hp = overlap ? pl->host_ovl : pl->host;
+  const int sched_len = (int)hp.sched.size(), sptw_len = (int)hp.sptw.size();
+  // overlapped: single prefetch buffer unless told otherwise, so that two column-pass CTAs fit beside the row pass
+  int n_buf = overlap ? env_int("MRIACL_OVL_ROWBUF", 1) : 2;
+  if (n_buf < 1 || n_buf > 2) n_buf = 1;
+  if (rowpass_smem_bytes(FUSED_P, FUSED_Q, sptw_len, sched_len, n_act, n_buf, a.ow, a.A) > SMEM_MAX) n_buf = 1;
+  const int rp_smem = rowpass_smem_bytes(FUSED_P, FUSED_Q, sptw_len, sched_len, n_act, n_buf, a.ow, a.A);
+  if (rp_smem > SMEM_MAX)
+    return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
+
+  const size_t cap_slices = a.workspace_bytes / g.per_slice;
+  OverlapRes* ov = nullptr;
+  int chunk, n_bufs_ws;
+  if (overlap) {
+    ov = get_overlap_res(a.dev, a.st);
+    if (!ov) return fail(MRIACL_ERR_CUDA, "side stream / event creation failed: %s", rt_last_error_string());
+    if (cap_slices >= (size_t)a.B) { chunk = a.B; n_bufs_ws = 1; }
+    else if (cap_slices >= 2) { chunk = (int)(cap_slices / 2); n_bufs_ws = 2; }
+    else { chunk = 1; n_bufs_ws = 1; }
+  } else {
+    chunk = (int)std::min<size_t>((size_t)a.B, cap_slices);
+    n_bufs_ws = 1;
+  }
+  const size_t buf_bytes = g.per_slice * (size_t)chunk;
+  const size_t part_bytes = align_up((size_t)g.n_tiles * 3 * sizeof(float), 256);
+
+  int group = 0;
+  for (int s0 = 0; s0 < a.B; s0 += chunk, ++group) {
+    const int ns = std::min(chunk, a.B - s0);
+    const int wb = group % n_bufs_ws;
+    char* base = (char*)a.workspace + buf_bytes * wb;
+    cf* T = (cf*)base;
+    float* partials = (float*)(base + g.t_bytes * (size_t)chunk);
+    int* counters = (int*)(base + (g.t_bytes + part_bytes) * (size_t)chunk);
+
+    ColPassParams cp{};
+    cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = a.W;
+    cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
+    cp.tw = pl->twH; cp.T = T; cp.oh = a.oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
+    cp.frame0 = s0 * a.A * a.C; cp.n_frames = ns * a.A * a.C; cp.done = nullptr;
+    const long long col_items = (long long)cp.n_frames * n_groups;
+
+    RowPassParams rp{};
+    rp.T = T; rp.n_act = n_act; rp.oh = a.oh; rp.ohp = ohp;
+    rp.sched = overlap ? pl->sched_ovl : pl->sched; rp.sched_len = sched_len;
+    rp.n_buf = n_buf; rp.tw = pl->twW; rp.sptw = pl->sptw; rp.sptw_len = sptw_len;
+    rp.out = a.out + (size_t)s0 * a.oh * a.ow; rp.partials = partials; rp.ow = a.ow; rp.col0 = col0;
+    rp.A = a.A; rp.C = a.C; rp.scale = (float)(1.0 / std::sqrt((double)a.H * (double)a.Wp));
+    rp.n_slices = ns; rp.n_tiles = g.n_tiles; rp.done = nullptr; rp.done_target = 0; rp.error_flag = nullptr;
+    const int row_items = ns * g.n_tiles;
+
+    NormParams np{};
+    np.in = rp.out; np.out = rp.out; np.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
+    np.partials = partials; np.n_part = g.n_tiles; np.n = (long long)a.oh * a.ow; np.eps = a.eps;
+    np.normalize = want_norm ? 1 : 0;
+    np.n_split = want_norm ? std::max(1, std::min(16, (int)(np.n / 8192))) : 1;
+    const bool run_norm = (want_norm || a.mean_std) && do_norm;
+
+    if (!overlap) {
+      if (n_groups > 0 && do_col) {
+        const int grid = (int)std::min<long long>(col_items, (long long)a.sms * 2);
+        MRIACL_LAUNCH(colpass640_kernel<true>, grid, CP_T, CP_SMEM_BYTES_DB, a.st, cp);
+      }
+      if (do_row) {
+        auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>;
+        MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_SEQ * 32, rp_smem, a.st, rp);
+      }
+      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, a.st, np);
+    } else {
+      // T buffer wb: its previous reader (row pass of group - n_bufs_ws) must be done
+      if (group >= n_bufs_ws && rt_stream_wait_event(a.st, ov->ev_row[wb])) return fail(MRIACL_ERR_CUDA, "stream wait failed");
+      if (rt_memset_async(counters, 0, sizeof(int) * (size_t)ns, a.st) || rt_event_record(ov->ev_start[wb], a.st) ||
+          rt_stream_wait_event(ov->side, ov->ev_start[wb]))
+        return fail(MRIACL_ERR_CUDA, "overlap setup failed: %s", rt_last_error_string());
+      cp.done = counters;
+      rp.done = counters; rp.done_target = a.A * a.C * n_groups;
+      // the row pass goes first so that it is resident (one CTA per SM) when the column-pass CTAs arrive
+      auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>;
+#ifdef MRIACL_EMU   // the emulator runs launches one after another: producer first
+      MRIACL_LAUNCH(colpass640_kernel<false>, (int)col_items, CP_T, CP_SMEM_BYTES_SB, a.st, cp);
+      MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_OVL * 32, rp_smem, ov->side, rp);
+#else
+      MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_OVL * 32, rp_smem, ov->side, rp);
+      MRIACL_LAUNCH(colpass640_kernel<false>, (int)col_items, CP_T, CP_SMEM_BYTES_SB, a.st, cp);
+#endif
+      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, ov->side, np);
+      if (rt_event_record(ov->ev_row[wb], ov->side)) return fail(MRIACL_ERR_CUDA, "event record failed");
+    }
+  }
+  if (overlap) {   // join: everything on the side stream happens-before whatever the caller enqueues next
+    const int used = std::min(group, n_bufs_ws);
+    for (int i = 0; i < used; ++i)
+      if (rt_stream_wait_event(a.st, ov->ev_row[i])) return fail(MRIACL_ERR_CUDA, "stream join failed");
+  }
+  return 0;
 }
 
 int grid_for(long long work_items, int per_block) {
@@ -305,64 +460,11 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
   const int row0 = crop_start(H, oh), col0 = crop_start(Wp, ow);
   const bool want_norm = (flags & MRIACL_NORM_INSTANCE) != 0;
   const int flip = (flags & MRIACL_FLIP_ROWS) ? 1 : 0;
-  const unsigned only = flags & (MRIACL_ONLY_COLPASS | MRIACL_ONLY_ROWPASS | MRIACL_ONLY_NORM);
-  const bool do_col = !only || (only & MRIACL_ONLY_COLPASS);
-  const bool do_row = !only || (only & MRIACL_ONLY_ROWPASS);
-  const bool do_norm = !only || (only & MRIACL_ONLY_NORM);
 
   if (g.fused) {
-    std::shared_ptr<FusedPlanDev> pl = get_fused_plan(dev, H, W, pad_left, Wp, oh, ow, mask_w_host, true);
-    if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
-    const int n_act = (int)pl->host.act_w.size();
-    const int n_groups = (n_act + CP_G - 1) / CP_G;
-    const int ohp = g.n_tiles * RP_ROWS;
-    const int rp_fixed = rowpass_fixed_smem<FUSED_P, FUSED_Q>() + 64;
-    int n_buf = 2;
-    if (rowpass_smem_bytes(rp_fixed, n_act, 2, ow, A) > SMEM_MAX) n_buf = 1;
-    const int rp_smem = rowpass_smem_bytes(rp_fixed, n_act, n_buf, ow, A);
-    if (rp_smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, ow, A);
-    if ((int)pl->host.sched.size() > RP_SCHED_MAX || (int)pl->host.sptw.size() > RP_SPTW_MAX)
-      return fail(MRIACL_ERR_UNSUPPORTED, "row-pass schedule too long");
-    for (int s0 = 0; s0 < B; s0 += chunk) {
-      const int ns = std::min(chunk, B - s0);
-      cf* T = (cf*)workspace;
-      float* partials = (float*)((char*)workspace + g.t_bytes * (size_t)ns);
-      if (n_groups > 0 && do_col) {
-        ColPassParams cp{};
-        cp.ksp = ksp; cp.sb = slice_stride; cp.sa = avg_stride; cp.A = A; cp.C = C; cp.W = W;
-        cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
-        cp.tw = pl->twH; cp.T = T; cp.oh = oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
-        cp.frame0 = s0 * A * C; cp.n_frames = ns * A * C;
-        const long long items = (long long)cp.n_frames * n_groups;
-        const int grid = (int)std::min<long long>(items, (long long)sms * 2);
-        MRIACL_LAUNCH(colpass640_kernel, grid, CP_T, CP_SMEM_BYTES, st, cp);
-      }
-      RowPassParams rp{};
-      rp.T = T; rp.n_act = n_act; rp.oh = oh; rp.ohp = ohp; rp.sched = pl->sched; rp.sched_len = (int)pl->host.sched.size();
-      rp.n_buf = n_buf; rp.tw = pl->twW; rp.sptw = pl->sptw; rp.sptw_len = (int)pl->host.sptw.size();
-      rp.out = out + (size_t)s0 * oh * ow; rp.partials = partials; rp.ow = ow; rp.col0 = col0;
-      rp.A = A; rp.C = C; rp.scale = (float)(1.0 / std::sqrt((double)H * (double)Wp));
-      rp.n_slices = ns; rp.n_tiles = g.n_tiles;
-      if (do_row) {
-        const int items = ns * g.n_tiles;
-        const int grid = std::min(items, sms);
-        if (rp_warps() == 24) {
-          auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, 24>;
-          MRIACL_LAUNCH(kfn, grid, 24 * 32, rp_smem, st, rp);
-        } else {
-          auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, 16>;
-          MRIACL_LAUNCH(kfn, grid, 16 * 32, rp_smem, st, rp);
-        }
-      }
-      if ((want_norm || mean_std) && do_norm) {
-        NormParams np{};
-        np.in = rp.out; np.out = rp.out; np.mean_std = mean_std ? mean_std + 2 * (size_t)s0 : nullptr;
-        np.partials = partials; np.n_part = g.n_tiles; np.n = (long long)oh * ow; np.eps = eps;
-        np.normalize = want_norm ? 1 : 0;
-        np.n_split = want_norm ? std::max(1, std::min(16, (int)(np.n / 8192))) : 1;
-        MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, st, np);
-      }
-    }
+    FusedArgs fa{ksp, slice_stride, avg_stride, mask_w_host, out, mean_std, B, A, C, H, W, pad_left, Wp, oh, ow,
+                 flags, eps, workspace, workspace_bytes, st, dev, sms};
+    if (int rc = run_fused(fa, g)) return rc;
   } else {
     const float* mask_dev = nullptr;
     if (get_device_mask(dev, mask_w_host, W, &mask_dev)) return fail(MRIACL_ERR_CUDA, "mask upload failed: %s", rt_last_error_string());

@@ -41,14 +41,31 @@ struct RowPassParams {
   float scale;           // 1 / sqrt(H * N)
   int n_slices, n_tiles;
   int n_buf;             // 1 or 2 prefetch buffers
+  const int* done;       // optional [n_slices]: items of the slice finished by a concurrently running column pass
+  int done_target;       // ... the slice is ready when done[s] == done_target
+  int* error_flag;       // set to 1 if the wait for a slice timed out
 };
 
 // shared memory: Y [P][Q][32] | twiddles [N] | sparse twiddle rows | schedule | T buffers | (A > 1) average tile
-template <int P, int Q> __host__ __device__ constexpr int rowpass_fixed_smem() {
-  return P * Q * RP_ROWS * 8 + P * Q * 8 + RP_SPTW_MAX * 8 + RP_SCHED_MAX * 4;
+__host__ __device__ inline int rp_round16(int v) { return (v + 15) / 16 * 16; }
+inline int rowpass_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_act, int n_buf, int ow, int A) {
+  return P * Q * RP_ROWS * 8 + P * Q * 8 + rp_round16(sptw_len * 8) + rp_round16(sched_len * 4) +
+         n_buf * n_act * RP_ROWS * 8 + (A > 1 ? RP_ROWS * (ow + 1) * 4 : 0);
 }
-inline int rowpass_smem_bytes(int fixed, int n_act, int n_buf, int ow, int A) {
-  return fixed + n_buf * n_act * RP_ROWS * 8 + (A > 1 ? RP_ROWS * (ow + 1) * 4 : 0);
+
+// spin (one thread) until a concurrently running producer has published `target`; bounded so that a
+// scheduling surprise ends in an error flag instead of a hung device
+__device__ __forceinline__ bool rp_wait_count(const int* counter, int target) {
+#if defined(MRIACL_EMU)
+  return *counter >= target;
+#else
+  const volatile int* c = counter;
+  for (long long spin = 0; spin < (1LL << 24); ++spin) {
+    if (*c >= target) { __threadfence(); return true; }
+    __nanosleep(256);
+  }
+  return false;
+#endif
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -109,7 +126,7 @@ __device__ __forceinline__ void rp_sparse_unit(const int* sch, const cf* tb, con
 }
 
 template <int P, int Q, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) rowpass_kernel(RowPassParams p) {
+__global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) rowpass_kernel(RowPassParams p) {
   static_assert(Q == 16, "stage 2 is the register-level 16-point FFT");
   constexpr int N = P * Q;
   constexpr int NT = NW * 32;
@@ -118,9 +135,9 @@ __global__ void __launch_bounds__(NW * 32, 1) rowpass_kernel(RowPassParams p) {
   constexpr int HSPLIT = (HP + 2) / 2;     // half A: X0 and pairs 1..HSPLIT-1, half B: pairs HSPLIT..HP
   MRIACL_DYN_SMEM(cf, Y);                       // [P][Q][32]
   cf* twsm = Y + N * RP_ROWS;                   // [N]
-  cf* sptwsm = twsm + N;                        // [RP_SPTW_MAX]
-  int* schsm = reinterpret_cast<int*>(sptwsm + RP_SPTW_MAX);
-  cf* tbuf = reinterpret_cast<cf*>(schsm + RP_SCHED_MAX);          // [n_buf][n_act][32]
+  cf* sptwsm = twsm + N;                        // [sptw_len]
+  int* schsm = reinterpret_cast<int*>(reinterpret_cast<char*>(sptwsm) + rp_round16(p.sptw_len * 8));
+  cf* tbuf = reinterpret_cast<cf*>(reinterpret_cast<char*>(schsm) + rp_round16(p.sched_len * 4));   // [n_buf][n_act][32]
   float* avsm = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * p.n_act * RP_ROWS);   // (A > 1)
   float* osm = reinterpret_cast<float*>(Y);     // output tile [32][ow+1], aliases Y
   __shared__ float red[NW];
@@ -155,6 +172,15 @@ __global__ void __launch_bounds__(NW * 32, 1) rowpass_kernel(RowPassParams p) {
       cp_async_commit();
     };
 
+    if (p.done) {     // overlapped with the column pass: wait until every column group of slice s has landed
+      __shared__ int ready;
+      if (tid == 0) {
+        ready = rp_wait_count(p.done + s, p.done_target) ? 1 : 0;
+        if (!ready && p.error_flag) *p.error_flag = 1;
+      }
+      __syncthreads();
+      if (!ready) return;
+    }
     if (p.A > 1) for (int i = tid; i < RP_ROWS * opitch; i += NT) avsm[i] = 0.f;
     prefetch(0, 0);
 

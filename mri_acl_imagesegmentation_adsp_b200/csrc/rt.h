@@ -24,6 +24,12 @@ inline int rt_sm_count(int) { return 2; }
 inline const char* rt_last_error_string() { return "emulation"; }
 inline int rt_check() { return 0; }
 inline int rt_allow_smem(const void*, int) { return 0; }
+typedef int rt_event_t;
+inline int rt_stream_create_high_priority(rt_stream_t* s) { *s = nullptr; return 0; }
+inline int rt_event_create(rt_event_t* e) { *e = 0; return 0; }
+inline int rt_event_record(rt_event_t, rt_stream_t) { return 0; }
+inline int rt_stream_wait_event(rt_stream_t, rt_event_t) { return 0; }
+inline int rt_memset_async(void* p, int v, size_t n, rt_stream_t) { std::memset(p, v, n); return 0; }
 #define MRIACL_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
   do { emu::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), (size_t)(smem),           \
                    [&] { kern(__VA_ARGS__); });                                               \
@@ -45,6 +51,16 @@ inline int rt_check() { return cudaPeekAtLastError() == cudaSuccess ? 0 : 1; }
 inline int rt_allow_smem(const void* fn, int bytes) {
   return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : 1;
 }
+typedef cudaEvent_t rt_event_t;
+inline int rt_stream_create_high_priority(rt_stream_t* s) {
+  int lo = 0, hi = 0;
+  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return 1;
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi) == cudaSuccess ? 0 : 1;
+}
+inline int rt_event_create(rt_event_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess ? 0 : 1; }
+inline int rt_event_record(rt_event_t e, rt_stream_t s) { return cudaEventRecord(e, s) == cudaSuccess ? 0 : 1; }
+inline int rt_stream_wait_event(rt_stream_t s, rt_event_t e) { return cudaStreamWaitEvent(s, e, 0) == cudaSuccess ? 0 : 1; }
+inline int rt_memset_async(void* p, int v, size_t n, rt_stream_t s) { return cudaMemsetAsync(p, v, n, s) == cudaSuccess ? 0 : 1; }
 #define MRIACL_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
   do { kern<<<(unsigned)(grid), (unsigned)(block), (size_t)(smem), (stream)>>>(__VA_ARGS__);  \
        ::mriacl::launch_counter()++; } while (0)

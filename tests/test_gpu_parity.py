@@ -123,6 +123,25 @@ def test_mask_and_crop_indexing_bit_exact():
     assert torch.equal(one, raw[1])
     c1, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=1)
     assert torch.equal(c1, raw)
+    # the overlapped (two-stream) and the back-to-back kernel schedules do the same arithmetic
+    seq, _, _ = zero_filled_rss(k, m, synth.CROP, None, sequential=True)
+    assert torch.equal(seq, raw)
+
+
+def test_overlapped_schedule_many_groups():
+    """batch larger than the workspace: groups alternate between two intermediate buffers."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    k = torch.view_as_complex(torch.randn((13, 15, 640, 368, 2), device="cuda", generator=g))
+    m = synth.knee_mask()
+    ref, rmean, rstd = zero_filled_rss(k, m, synth.CROP, "instance", sequential=True, chunk_slices=13)
+    for chunk in (13, 6, 4, 2, 1):
+        out, mean, std = zero_filled_rss(k, m, synth.CROP, "instance", chunk_slices=chunk)
+        assert torch.equal(out, ref), chunk
+        assert torch.equal(mean, rmean) and torch.equal(std, rstd)
+    # repeated calls reuse counters, events and the side stream
+    for _ in range(5):
+        out, _, _ = zero_filled_rss(k, m, synth.CROP, "instance", chunk_slices=5)
+    assert torch.equal(out, ref)
 
 
 def test_fused_variants_against_oracle():
