@@ -256,7 +256,7 @@ int generic_fft2c(const cf* in, long long sb, long long sa, int A, int C, cf* ou
 }
 
 // ---- side stream + events of the overlapped schedule, one set per (device, caller stream) ----
-struct OverlapRes { rt_stream_t side = nullptr; rt_event_t ev_start[2], ev_row[2]; bool ok = false; };
+struct OverlapRes { rt_stream_t side = nullptr; rt_event_t ev_start[2], ev_row[2]; int* error_flag = nullptr; bool ok = false; };
 std::map<std::pair<int, void*>, OverlapRes> g_ovl;
 
 OverlapRes* get_overlap_res(int dev, rt_stream_t st) {
@@ -265,7 +265,12 @@ OverlapRes* get_overlap_res(int dev, rt_stream_t st) {
   if (!r.ok) {
     int bad = rt_stream_create_high_priority(&r.side);
     for (int i = 0; i < 2; ++i) { bad |= rt_event_create(&r.ev_start[i]); bad |= rt_event_create(&r.ev_row[i]); }
+    void* ef = nullptr;
+    const int zero = 0;
+    bad |= rt_malloc(&ef, sizeof(int));
+    if (!bad) bad |= rt_upload(ef, &zero, sizeof(int));
     if (bad) return nullptr;
+    r.error_flag = (int*)ef;
     r.ok = true;
   }
   return &r;
@@ -381,14 +386,17 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
           rt_stream_wait_event(ov->side, ov->ev_start[wb]))
         return fail(MRIACL_ERR_CUDA, "overlap setup failed: %s", rt_last_error_string());
       cp.done = counters;
-      rp.done = counters; rp.done_target = a.A * a.C * n_groups;
+      rp.done = counters; rp.done_target = a.A * a.C * n_groups; rp.error_flag = ov->error_flag;
       // the row pass goes first so that it is resident (one CTA per SM) when the column-pass CTAs arrive
       auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>;
 #ifdef MRIACL_EMU   // the emulator runs launches one after another: producer first
       MRIACL_LAUNCH(colpass640_kernel<false>, (int)col_items, CP_T, CP_SMEM_BYTES_SB, a.st, cp);
       MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_OVL * 32, rp_smem, ov->side, rp);
 #else
-      MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_OVL * 32, rp_smem, ov->side, rp);
+      // a few SMs are left without a row-pass CTA: the column pass can always make progress there, whatever
+      // the block scheduler decides about co-residency on the others
+      static const int reserve = std::max(0, env_int("MRIACL_OVL_RESERVE_SMS", 8));
+      MRIACL_LAUNCH(kfn, std::min(row_items, std::max(1, a.sms - reserve)), RP_NW_OVL * 32, rp_smem, ov->side, rp);
       MRIACL_LAUNCH(colpass640_kernel<false>, (int)col_items, CP_T, CP_SMEM_BYTES_SB, a.st, cp);
 #endif
       if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, ov->side, np);

@@ -53,37 +53,20 @@ inline int rowpass_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_a
          n_buf * n_act * RP_ROWS * 8 + (A > 1 ? RP_ROWS * (ow + 1) * 4 : 0);
 }
 
-// spin (one thread) until a concurrently running producer has published `target`; bounded so that a
-// scheduling surprise ends in an error flag instead of a hung device
-__device__ __forceinline__ bool rp_wait_count(const int* counter, int target) {
+// spin (one thread) until a concurrently running producer has published `target`.  Bounded (~50 ms) and
+// abortable through a device-wide flag, so that a scheduling surprise ends in an error flag, not a hung device.
+__device__ __forceinline__ bool rp_wait_count(const int* counter, int target, int* error_flag) {
 #if defined(MRIACL_EMU)
   return *counter >= target;
 #else
   const volatile int* c = counter;
-  for (long long spin = 0; spin < (1LL << 24); ++spin) {
+  const volatile int* err = error_flag;
+  for (int spin = 0; spin < (1 << 18); ++spin) {
     if (*c >= target) { __threadfence(); return true; }
-    __nanosleep(256);
+    if (err && (spin & 63) == 63 && *err) return false;
+    __nanosleep(200);
   }
   return false;
-#endif
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-#if defined(MRIACL_EMU)
-  reinterpret_cast<float4*>(smem_dst)[0] = reinterpret_cast<const float4*>(gsrc)[0];
-#else
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_commit() {
-#if !defined(MRIACL_EMU)
-  asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-template <int N_PENDING> __device__ __forceinline__ void cp_async_wait() {
-#if !defined(MRIACL_EMU)
-  asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
 #endif
 }
 
@@ -175,8 +158,8 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) rowpass_kernel(RowPa
     if (p.done) {     // overlapped with the column pass: wait until every column group of slice s has landed
       __shared__ int ready;
       if (tid == 0) {
-        ready = rp_wait_count(p.done + s, p.done_target) ? 1 : 0;
-        if (!ready && p.error_flag) *p.error_flag = 1;
+        ready = rp_wait_count(p.done + s, p.done_target, p.error_flag) ? 1 : 0;
+        if (!ready && p.error_flag) atomicAdd(p.error_flag, 1);
       }
       __syncthreads();
       if (!ready) return;

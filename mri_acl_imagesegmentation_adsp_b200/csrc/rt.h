@@ -49,7 +49,10 @@ inline int rt_sm_count(int dev) {
 inline const char* rt_last_error_string() { return cudaGetErrorString(cudaGetLastError()); }
 inline int rt_check() { return cudaPeekAtLastError() == cudaSuccess ? 0 : 1; }
 inline int rt_allow_smem(const void* fn, int bytes) {
-  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : 1;
+  // opt in to large dynamic shared memory and ask for the largest shared-memory carveout, so that the SM is
+  // already configured for co-resident CTAs of our other kernels (a carveout change needs an idle SM)
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 1;
+  return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess ? 0 : 1;
 }
 typedef cudaEvent_t rt_event_t;
 inline int rt_stream_create_high_priority(rt_stream_t* s) {

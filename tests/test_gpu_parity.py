@@ -133,14 +133,19 @@ def test_overlapped_schedule_many_groups():
     g = torch.Generator(device="cuda").manual_seed(3)
     k = torch.view_as_complex(torch.randn((13, 15, 640, 368, 2), device="cuda", generator=g))
     m = synth.knee_mask()
-    ref, rmean, rstd = zero_filled_rss(k, m, synth.CROP, "instance", sequential=True, chunk_slices=13)
+    ref, _, _ = zero_filled_rss(k, m, synth.CROP, None, sequential=True, chunk_slices=13)
+    nref, rmean, rstd = zero_filled_rss(k, m, synth.CROP, "instance", sequential=True, chunk_slices=13)
     for chunk in (13, 6, 4, 2, 1):
-        out, mean, std = zero_filled_rss(k, m, synth.CROP, "instance", chunk_slices=chunk)
-        assert torch.equal(out, ref), chunk
-        assert torch.equal(mean, rmean) and torch.equal(std, rstd)
+        out, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=chunk)
+        assert torch.equal(out, ref), chunk            # same arithmetic, bit for bit
+        nout, mean, std = zero_filled_rss(k, m, synth.CROP, "instance", chunk_slices=chunk)
+        # (the tile statistics are reduced over 8 instead of 16 warps: last-bit differences only)
+        torch.testing.assert_close(nout, nref, rtol=0, atol=2e-6)
+        torch.testing.assert_close(mean, rmean, rtol=1e-6, atol=0)
+        torch.testing.assert_close(std, rstd, rtol=1e-6, atol=0)
     # repeated calls reuse counters, events and the side stream
     for _ in range(5):
-        out, _, _ = zero_filled_rss(k, m, synth.CROP, "instance", chunk_slices=5)
+        out, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=5)
     assert torch.equal(out, ref)
 
 
