@@ -70,6 +70,25 @@ __device__ __forceinline__ bool rp_wait_count(const int* counter, int target, in
 #endif
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+#if defined(MRIACL_EMU)
+  reinterpret_cast<float4*>(smem_dst)[0] = reinterpret_cast<const float4*>(gsrc)[0];
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#if !defined(MRIACL_EMU)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N_PENDING> __device__ __forceinline__ void cp_async_wait() {
+#if !defined(MRIACL_EMU)
+  asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
+#endif
+}
+
 template <int NW> __device__ __forceinline__ float rp_block_sum(float v, float* red /* NW floats */) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
