@@ -51,6 +51,7 @@ struct ColPassParams {
   int frame0;                    // first global frame of this launch (f = (b*A + a)*C + c)
   int n_frames;
   int* done;                     // optional [n_slices]: += 1 per finished item of the slice (row pass waits on it)
+  int persist;                   // single-buffer variant: 1 = grid-stride over items, 0 = one item per CTA
 };
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): the gather needs one complex64 out of
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(CP_T, DB ? 2 : 4) colpass640_kernel(ColPassPar
     } else {
       __syncthreads();   // this buffer is free for the gather issued in the next iteration
     }
-    if (!DB) break;
+    if (!DB && !p.persist) break;
   }
 }
 

@@ -49,13 +49,15 @@ int device_sms(int dev) {
   return d.sms;
 }
 
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
 constexpr int FUSED_P = 23, FUSED_Q = 16;
 constexpr int SMEM_MAX = 227 * 1024 - 512;     // dynamic shared memory a B200 CTA may opt in to (227 KB minus the kernels' static part)
 // Row-pass CTA shapes: 16 warps (one CTA owns the SM) for the sequential schedule, 8 warps for the
 // overlapped schedule, where one row-pass CTA shares each SM with column-pass CTAs.
 constexpr int RP_NW_SEQ = 16, RP_NW_OVL = 8;
 
-int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
 
 constexpr int GEN_SMEM_BYTES = 2 * MRIACL_GEN_SMEM_ELEMS * 8;
 
@@ -65,10 +67,12 @@ int ensure_smem_attrs(int dev) {
   if (d.smem_set) return 0;
   int bad = 0;
   bad |= rt_allow_smem((const void*)generic_fft_kernel, GEN_SMEM_BYTES);
-  bad |= rt_allow_smem((const void*)colpass640_kernel<true>, CP_SMEM_BYTES_DB);
-  bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB);
+  const int cp_carve = env_int("MRIACL_CP_CARVEOUT", -1);
+  const int ovl = env_int("MRIACL_OVERLAP", 0);
+  bad |= rt_allow_smem((const void*)colpass640_kernel<true>, CP_SMEM_BYTES_DB, cp_carve);
+  bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, ovl ? 100 : cp_carve);
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
-  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX, 100);
   if (!bad) d.smem_set = true;
   return bad;
 }
@@ -303,12 +307,8 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
   const bool do_col = !only || (only & MRIACL_ONLY_COLPASS);
   const bool do_row = !only || (only & MRIACL_ONLY_ROWPASS);
   const bool do_norm = !only || (only & MRIACL_ONLY_NORM);
-#ifdef MRIACL_EMU
-  const bool overlap_default = false;
-#else
-  const bool overlap_default = true;
-#endif
-  static const bool overlap_env = env_int("MRIACL_OVERLAP", overlap_default ? 1 : 0) != 0;
+  // (the overlapped schedule is opt-in: see DESIGN.md for what it needs from the column-pass gather)
+  static const bool overlap_env = env_int("MRIACL_OVERLAP", 0) != 0;
   const bool overlap = overlap_env && !only && !(a.flags & MRIACL_SEQUENTIAL) && n_groups > 0;
 
   const FusedPlanHost& hp = overlap ? pl->host_ovl : pl->host;
@@ -371,8 +371,16 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
 
     if (!overlap) {
       if (n_groups > 0 && do_col) {
-        const int grid = (int)std::min<long long>(col_items, (long long)a.sms * 2);
-        MRIACL_LAUNCH(colpass640_kernel<true>, grid, CP_T, CP_SMEM_BYTES_DB, a.st, cp);
+        // tuning knobs: MRIACL_CP_DB=0 single-buffer CTAs, MRIACL_CP_PER_SM=k persistent CTAs per SM (0 = one item per CTA)
+        static const int cp_db = env_int("MRIACL_CP_DB", 1), cp_per_sm = env_int("MRIACL_CP_PER_SM", 2);
+        if (cp_db) {
+          const int grid = (int)std::min<long long>(col_items, (long long)a.sms * std::max(1, cp_per_sm));
+          MRIACL_LAUNCH(colpass640_kernel<true>, grid, CP_T, CP_SMEM_BYTES_DB, a.st, cp);
+        } else {
+          cp.persist = cp_per_sm > 0 ? 1 : 0;
+          const int grid = cp.persist ? (int)std::min<long long>(col_items, (long long)a.sms * cp_per_sm) : (int)col_items;
+          MRIACL_LAUNCH(colpass640_kernel<false>, grid, CP_T, CP_SMEM_BYTES_SB, a.st, cp);
+        }
       }
       if (do_row) {
         auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>;

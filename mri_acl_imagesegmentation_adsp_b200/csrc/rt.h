@@ -23,7 +23,7 @@ inline int rt_device() { return 0; }
 inline int rt_sm_count(int) { return 2; }
 inline const char* rt_last_error_string() { return "emulation"; }
 inline int rt_check() { return 0; }
-inline int rt_allow_smem(const void*, int) { return 0; }
+inline int rt_allow_smem(const void*, int, int = -1) { return 0; }
 typedef int rt_event_t;
 inline int rt_stream_create_high_priority(rt_stream_t* s) { *s = nullptr; return 0; }
 inline int rt_event_create(rt_event_t* e) { *e = 0; return 0; }
@@ -48,11 +48,13 @@ inline int rt_sm_count(int dev) {
 }
 inline const char* rt_last_error_string() { return cudaGetErrorString(cudaGetLastError()); }
 inline int rt_check() { return cudaPeekAtLastError() == cudaSuccess ? 0 : 1; }
-inline int rt_allow_smem(const void* fn, int bytes) {
-  // opt in to large dynamic shared memory and ask for the largest shared-memory carveout, so that the SM is
-  // already configured for co-resident CTAs of our other kernels (a carveout change needs an idle SM)
+// opt in to large dynamic shared memory; carveout_pct >= 0 additionally sets the preferred shared-memory
+// carveout (percent of the SM's 228 KB; a carveout change needs an idle SM, so kernels meant to be
+// co-resident must agree on it)
+inline int rt_allow_smem(const void* fn, int bytes, int carveout_pct = -1) {
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 1;
-  return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess ? 0 : 1;
+  if (carveout_pct < 0) return 0;
+  return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct) == cudaSuccess ? 0 : 1;
 }
 typedef cudaEvent_t rt_event_t;
 inline int rt_stream_create_high_priority(rt_stream_t* s) {
