@@ -203,7 +203,10 @@ __global__ void __launch_bounds__(CP_T, DB ? 2 : 4) colpass640_kernel(ColPassPar
     } else {
       __syncthreads();   // this buffer is free for the gather issued in the next iteration
     }
-    if (!DB && !p.persist) break;
+    if (!DB) {           // single buffer: the next gather can only start now (other CTAs of the SM cover the latency)
+      if (!p.persist) break;
+      if (next < n_items) issue_gather(next, 0);
+    }
   }
 }
 
