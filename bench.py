@@ -146,12 +146,13 @@ def reference_arm(args) -> None:
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed regions run."""
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed regions run.
+    (Polling NVML every 20 ms visibly perturbed sub-millisecond steps; 100 ms does not.)"""
     REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index: int, period: float = 0.02):
+    def __init__(self, index: int, period: float = 0.1):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reason_bits, self.active = [], 0, False

@@ -210,4 +210,165 @@ __global__ void __launch_bounds__(CP_T, DB ? 2 : 4) colpass640_kernel(ColPassPar
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised column pass: 5 compute warps + 1 producer warp per CTA, two item buffers.
+// An LDGSTS whose queue is full stalls the issuing warp, so when the compute warps issue their own
+// gather the load phase cannot overlap their arithmetic.  Here the producer warp does nothing but
+// gather (it may sit in the memory-queue stall for as long as it likes) and hands buffers to the compute
+// warps through named barriers FULL[b] / EMPTY[b]; the compute warps synchronise among themselves on a
+// 160-thread barrier, so the gather of item i+1 streams in during passes 1-3 of item i.
+// ---------------------------------------------------------------------------------------------
+constexpr int CP_WS_T = CP_T + 32;
+constexpr int CP_BAR_FULL = 1, CP_BAR_EMPTY = 3, CP_BAR_COMPUTE = 5;   // FULL: 1,2  EMPTY: 3,4
+
+__global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams p) {
+  MRIACL_DYN_SMEM(cf, sm);
+  const int tid = threadIdx.x;
+  const int n_items = p.n_frames * p.n_groups;
+  if (tid >= CP_T) {
+    // ------------------------------ producer warp ------------------------------
+    const int lane = tid - CP_T;
+    const int k_ld = lane & 7, hs = lane >> 3;          // 8 columns x 4 rows per instruction
+    const long long row_step = 4LL * p.W;
+    auto issue_gather = [&](int item, int buf) {
+      const int fl = item / p.n_groups, g = item - fl * p.n_groups;
+      const int f = p.frame0 + fl;
+      const int b = f / (p.A * p.C), a = (f / p.C) % p.A, c = f % p.C;
+      const int j0 = g * CP_G;
+      if (j0 + k_ld < p.n_act) {
+        const cf* src = p.ksp + b * p.sb + a * p.sa + ((long long)c * CP_N + hs) * p.W + p.act_w[j0 + k_ld];
+        cf* dst = sm + buf * CP_BUF + k_ld * CP_PITCH + hs;
+#pragma unroll 1
+        for (int blk = 0; blk < 8; ++blk) {
+          cf* d = dst + CP_BLK * ((blk + 4) & 7);
+#pragma unroll
+          for (int q = 0; q < 20; ++q) {
+            cp_async8(d + 4 * q, src);
+            src += row_step;
+          }
+        }
+      }
+      cp_async_commit_group();
+    };
+    int k = 0;
+    if (blockIdx.x < n_items) issue_gather(blockIdx.x, 0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+      const int next = item + gridDim.x;
+      if (next < n_items) {
+        if (k + 1 >= 2) named_bar_sync(CP_BAR_EMPTY + ((k + 1) & 1), CP_WS_T);   // buffer released by the compute warps
+        issue_gather(next, (k + 1) & 1);
+        cp_async_wait_group<1>();
+      } else {
+        cp_async_wait_group<0>();
+      }
+      named_bar_arrive(CP_BAR_FULL + (k & 1), CP_WS_T);                          // item k has landed
+    }
+    return;
+  }
+
+  // ------------------------------ compute warps ------------------------------
+  const int sub = tid / 80, pos = tid - sub * 80;
+  cf tw1[8], tw2[8];
+  const int base2 = (pos / 10) * CP_BLK + (pos % 10);
+  {
+    const int n3 = pos % 10;
+#pragma unroll
+    for (int m = 1; m < 8; ++m) {
+      tw1[m] = p.tw[(pos * m) % CP_N];
+      tw2[m] = p.tw[(8 * n3 * m) % CP_N];
+    }
+  }
+  const int sub3 = tid / 64, r3 = tid - sub3 * 64;
+  const int base3 = (r3 % 8) * CP_BLK + (r3 / 8) * 10;
+  int rr3[10];
+#pragma unroll
+  for (int m3 = 0; m3 < 10; ++m3) {
+    const int rfull = phys_of_logical(r3 + 64 * m3, CP_N);
+    const int rr = (p.flip ? CP_N - 1 - rfull : rfull) - p.row0;
+    rr3[m3] = (rr >= 0 && rr < p.oh) ? rr : -1;
+  }
+
+  int k = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+    const int fl = item / p.n_groups, g = item - fl * p.n_groups;
+    const int j0 = g * CP_G;
+    const int ncols = min(CP_G, p.n_act - j0);
+    cf* cur = sm + (k & 1) * CP_BUF;
+    named_bar_sync(CP_BAR_FULL + (k & 1), CP_WS_T);
+
+    // ---- pass 1: radix-8 over n1 (stride 90), mask multiply, twiddle w640^{pos * m1}; two columns in flight ----
+    for (int kc = sub; kc < ncols; kc += 4) {
+      const bool two = kc + 2 < ncols;
+      cf* colA = cur + kc * CP_PITCH + pos;
+      cf* colB = colA + (two ? 2 * CP_PITCH : 0);
+      cf va[8], vb[8];
+#pragma unroll
+      for (int n1 = 0; n1 < 8; ++n1) { va[n1] = colA[n1 * CP_BLK]; vb[n1] = colB[n1 * CP_BLK]; }
+      if (!p.unit_mask) {
+        const float ma = p.act_m[j0 + kc], mb = p.act_m[j0 + (two ? kc + 2 : kc)];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) { va[n1] = cscale(va[n1], ma); vb[n1] = cscale(vb[n1], mb); }
+      }
+      radix8<true>(va);
+      radix8<true>(vb);
+      colA[0] = va[0];
+#pragma unroll
+      for (int m1 = 1; m1 < 8; ++m1) colA[m1 * CP_BLK] = cmul(va[m1], tw1[m1]);
+      if (two) {
+        colB[0] = vb[0];
+#pragma unroll
+        for (int m1 = 1; m1 < 8; ++m1) colB[m1 * CP_BLK] = cmul(vb[m1], tw1[m1]);
+      }
+    }
+    named_bar_sync(CP_BAR_COMPUTE, CP_T);
+
+    // ---- pass 2: radix-8 over n2 (stride 10), twiddle w80^{n3 * m2} ----
+    for (int kc = sub; kc < ncols; kc += 4) {
+      const bool two = kc + 2 < ncols;
+      cf* colA = cur + kc * CP_PITCH + base2;
+      cf* colB = colA + (two ? 2 * CP_PITCH : 0);
+      cf va[8], vb[8];
+#pragma unroll
+      for (int n2 = 0; n2 < 8; ++n2) { va[n2] = colA[n2 * 10]; vb[n2] = colB[n2 * 10]; }
+      radix8<true>(va);
+      radix8<true>(vb);
+      colA[0] = va[0];
+#pragma unroll
+      for (int m2 = 1; m2 < 8; ++m2) colA[m2 * 10] = cmul(va[m2], tw2[m2]);
+      if (two) {
+        colB[0] = vb[0];
+#pragma unroll
+        for (int m2 = 1; m2 < 8; ++m2) colB[m2 * 10] = cmul(vb[m2], tw2[m2]);
+      }
+    }
+    named_bar_sync(CP_BAR_COMPUTE, CP_T);
+
+    // ---- pass 3: radix-10 over n3 (contiguous), crop/shift/flip on the way out ----
+    if (tid < 128) {
+      for (int kc = sub3; kc < ncols; kc += 2) {
+        const float4* col4 = reinterpret_cast<const float4*>(cur + kc * CP_PITCH + base3);
+        cf v[10];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const float4 t = col4[q];
+          v[2 * q] = cf_make(t.x, t.y);
+          v[2 * q + 1] = cf_make(t.z, t.w);
+        }
+        radix10<true>(v);
+        cf* dst = p.T + ((long long)fl * p.n_act + j0 + kc) * p.ohp;
+#pragma unroll
+        for (int m3 = 0; m3 < 10; ++m3)
+          if (rr3[m3] >= 0) dst[rr3[m3]] = v[m3];
+      }
+    }
+    if (p.done) {
+      __threadfence();
+      named_bar_sync(CP_BAR_COMPUTE, CP_T);
+      if (tid == 0) atomicAdd(p.done + fl / (p.A * p.C), 1);
+    }
+    if (item + 2 * (int)gridDim.x < n_items) named_bar_arrive(CP_BAR_EMPTY + (k & 1), CP_WS_T);   // producer may refill
+  }
+}
+
 }  // namespace mriacl

@@ -47,6 +47,22 @@ __device__ __forceinline__ cf ld_stream(const cf* p) {
 #endif
 }
 
+// named barriers: `count` threads (a multiple of 32) take part; sync waits, arrive does not
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+#if defined(MRIACL_EMU)
+  mriacl_emu_bar_sync(id, count);
+#else
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+#if defined(MRIACL_EMU)
+  mriacl_emu_bar_arrive(id, count);
+#else
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
 // physical index of logical (un-shifted) FFT index i, and back, for a centred transform
 // of length n:  ifftshift(x)[i] = x[(i + n/2) % n]  and  fftshift(y)[(m + n/2) % n] = y[m]
 // (np.fft.ifftshift / fftshift, REF/src/utils/kspace.py:6-8,13-15).

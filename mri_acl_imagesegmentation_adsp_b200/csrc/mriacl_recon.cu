@@ -70,6 +70,7 @@ int ensure_smem_attrs(int dev) {
   const int cp_carve = env_int("MRIACL_CP_CARVEOUT", -1);
   const int ovl = env_int("MRIACL_OVERLAP", 0);
   bad |= rt_allow_smem((const void*)colpass640_kernel<true>, CP_SMEM_BYTES_DB, cp_carve);
+  bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB, cp_carve);
   bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, ovl ? 100 : cp_carve);
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX, 100);
@@ -373,7 +374,11 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       if (n_groups > 0 && do_col) {
         // tuning knobs: MRIACL_CP_DB=0 single-buffer CTAs, MRIACL_CP_PER_SM=k persistent CTAs per SM (0 = one item per CTA)
         static const int cp_db = env_int("MRIACL_CP_DB", 1), cp_per_sm = env_int("MRIACL_CP_PER_SM", 2);
-        if (cp_db) {
+        static const int cp_ws = env_int("MRIACL_CP_WS", 1);    // warp-specialised gather (default)
+        if (cp_ws && cp_db) {
+          const int grid = (int)std::min<long long>(col_items, (long long)a.sms * std::max(1, cp_per_sm));
+          MRIACL_LAUNCH(colpass640_ws_kernel, grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+        } else if (cp_db) {
           const int grid = (int)std::min<long long>(col_items, (long long)a.sms * std::max(1, cp_per_sm));
           MRIACL_LAUNCH(colpass640_kernel<true>, grid, CP_T, CP_SMEM_BYTES_DB, a.st, cp);
         } else {

@@ -50,7 +50,21 @@ class Barrier {
   std::mutex m_; std::condition_variable cv_; int n_, count_ = 0, gen_ = 0;
 };
 
+// CUDA named barrier (bar.sync / bar.arrive with an explicit thread count)
+class NamedBarrier {
+ public:
+  void arrive(int n, bool wait) {
+    std::unique_lock<std::mutex> lk(m_);
+    int gen = gen_;
+    if (++count_ >= n) { count_ = 0; ++gen_; cv_.notify_all(); }
+    else if (wait) cv_.wait(lk, [&] { return gen != gen_; });
+  }
+ private:
+  std::mutex m_; std::condition_variable cv_; int count_ = 0, gen_ = 0;
+};
+
 struct BlockCtx {
+  NamedBarrier named[16];
   Barrier* block_bar;
   std::vector<Barrier*> warp_bar;
   std::vector<uint64_t> shfl;   // one 8-byte slot per thread
@@ -114,6 +128,8 @@ template <class T> inline T shfl_generic(T v, int src_lane) {
 #define gridDim (emu::t_gridDim)
 
 static inline void __syncthreads() { emu::t_ctx->block_bar->wait(); }
+static inline void mriacl_emu_bar_sync(int id, int nthreads) { emu::t_ctx->named[id].arrive(nthreads, true); }
+static inline void mriacl_emu_bar_arrive(int id, int nthreads) { emu::t_ctx->named[id].arrive(nthreads, false); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::t_ctx->warp_bar[emu::t_linear_tid / 32]->wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
