@@ -52,6 +52,7 @@ struct ColPassParams {
   int n_frames;
   int* done;                     // optional [n_slices]: += 1 per finished item of the slice (row pass waits on it)
   int persist;                   // single-buffer variant: 1 = grid-stride over items, 0 = one item per CTA
+  int debug_skip;                // profiling only: 1 = no gather, 2 = no arithmetic, 4 = no stores (results are garbage)
 };
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): the gather needs one complex64 out of
@@ -224,19 +225,25 @@ constexpr int CP_BAR_FULL = 1, CP_BAR_EMPTY = 3, CP_BAR_COMPUTE = 5;   // FULL: 
 
 __global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams p) {
   MRIACL_DYN_SMEM(cf, sm);
+  __shared__ FullBarrier full_bar[2];
   const int tid = threadIdx.x;
   const int n_items = p.n_frames * p.n_groups;
+  if (tid == 0) { full_init(&full_bar[0], 32); full_init(&full_bar[1], 32); }
+  __syncthreads();
   if (tid >= CP_T) {
     // ------------------------------ producer warp ------------------------------
     const int lane = tid - CP_T;
     const int k_ld = lane & 7, hs = lane >> 3;          // 8 columns x 4 rows per instruction
     const long long row_step = 4LL * p.W;
-    auto issue_gather = [&](int item, int buf) {
+    int k = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+      const int buf = k & 1;
+      if (k >= 2) named_bar_sync(CP_BAR_EMPTY + buf, CP_WS_T);   // buffer released by the compute warps
       const int fl = item / p.n_groups, g = item - fl * p.n_groups;
       const int f = p.frame0 + fl;
       const int b = f / (p.A * p.C), a = (f / p.C) % p.A, c = f % p.C;
       const int j0 = g * CP_G;
-      if (j0 + k_ld < p.n_act) {
+      if (j0 + k_ld < p.n_act && !(p.debug_skip & 1)) {
         const cf* src = p.ksp + b * p.sb + a * p.sa + ((long long)c * CP_N + hs) * p.W + p.act_w[j0 + k_ld];
         cf* dst = sm + buf * CP_BUF + k_ld * CP_PITCH + hs;
 #pragma unroll 1
@@ -249,21 +256,10 @@ __global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams
           }
         }
       }
-      cp_async_commit_group();
-    };
-    int k = 0;
-    if (blockIdx.x < n_items) issue_gather(blockIdx.x, 0);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
-      const int next = item + gridDim.x;
-      if (next < n_items) {
-        if (k + 1 >= 2) named_bar_sync(CP_BAR_EMPTY + ((k + 1) & 1), CP_WS_T);   // buffer released by the compute warps
-        issue_gather(next, (k + 1) & 1);
-        cp_async_wait_group<1>();
-      } else {
-        cp_async_wait_group<0>();
-      }
-      named_bar_arrive(CP_BAR_FULL + (k & 1), CP_WS_T);                          // item k has landed
+      // fires when this lane's copies have landed; the warp moves straight on to the next item's gather
+      full_signal_async(&full_bar[buf], CP_BAR_FULL + buf, CP_WS_T);
     }
+    cp_async_wait_group<0>();
     return;
   }
 
@@ -295,10 +291,11 @@ __global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams
     const int j0 = g * CP_G;
     const int ncols = min(CP_G, p.n_act - j0);
     cf* cur = sm + (k & 1) * CP_BUF;
-    named_bar_sync(CP_BAR_FULL + (k & 1), CP_WS_T);
+    full_wait(&full_bar[k & 1], (k >> 1) & 1, CP_BAR_FULL + (k & 1), CP_WS_T);
 
+    const int ncols_c = (p.debug_skip & 2) ? 0 : ncols;
     // ---- pass 1: radix-8 over n1 (stride 90), mask multiply, twiddle w640^{pos * m1}; two columns in flight ----
-    for (int kc = sub; kc < ncols; kc += 4) {
+    for (int kc = sub; kc < ncols_c; kc += 4) {
       const bool two = kc + 2 < ncols;
       cf* colA = cur + kc * CP_PITCH + pos;
       cf* colB = colA + (two ? 2 * CP_PITCH : 0);
@@ -324,7 +321,7 @@ __global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams
     named_bar_sync(CP_BAR_COMPUTE, CP_T);
 
     // ---- pass 2: radix-8 over n2 (stride 10), twiddle w80^{n3 * m2} ----
-    for (int kc = sub; kc < ncols; kc += 4) {
+    for (int kc = sub; kc < ncols_c; kc += 4) {
       const bool two = kc + 2 < ncols;
       cf* colA = cur + kc * CP_PITCH + base2;
       cf* colB = colA + (two ? 2 * CP_PITCH : 0);
@@ -346,7 +343,7 @@ __global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams
 
     // ---- pass 3: radix-10 over n3 (contiguous), crop/shift/flip on the way out ----
     if (tid < 128) {
-      for (int kc = sub3; kc < ncols; kc += 2) {
+      for (int kc = sub3; kc < ncols_c; kc += 2) {
         const float4* col4 = reinterpret_cast<const float4*>(cur + kc * CP_PITCH + base3);
         cf v[10];
 #pragma unroll
@@ -357,9 +354,11 @@ __global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams
         }
         radix10<true>(v);
         cf* dst = p.T + ((long long)fl * p.n_act + j0 + kc) * p.ohp;
+        if (!(p.debug_skip & 4)) {
 #pragma unroll
-        for (int m3 = 0; m3 < 10; ++m3)
-          if (rr3[m3] >= 0) dst[rr3[m3]] = v[m3];
+          for (int m3 = 0; m3 < 10; ++m3)
+            if (rr3[m3] >= 0) dst[rr3[m3]] = v[m3];
+        } else if (v[0].x == 1.2345f) dst[0] = v[1];
       }
     }
     if (p.done) {

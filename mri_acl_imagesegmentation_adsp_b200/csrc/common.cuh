@@ -63,6 +63,43 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
 #endif
 }
 
+// ---- "buffer full" signal driven by the completion of cp.async copies ---------------------------------
+// Device: an mbarrier in shared memory; every producer lane appends a cp.async.mbarrier.arrive.noinc after
+// its copies, so the barrier phase completes when all of them have LANDED -- the producer itself never
+// waits and can go on issuing the next gather.  Emulator (copies are synchronous): a named barrier.
+struct FullBarrier { unsigned long long word; };
+
+__device__ __forceinline__ void full_init(FullBarrier* b, int producer_lanes) {
+#if !defined(MRIACL_EMU)
+  const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(producer_lanes) : "memory");
+#endif
+}
+// producer lane: after issuing this item's cp.async copies
+__device__ __forceinline__ void full_signal_async(FullBarrier* b, int emu_id, int emu_count) {
+#if defined(MRIACL_EMU)
+  named_bar_arrive(emu_id, emu_count);
+#else
+  const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+#endif
+}
+// consumer thread: wait for phase `parity` (0, 1, 0, ... per use of this barrier)
+__device__ __forceinline__ void full_wait(FullBarrier* b, int parity, int emu_id, int emu_count) {
+#if defined(MRIACL_EMU)
+  named_bar_sync(emu_id, emu_count);
+#else
+  const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "MRIACL_FULL_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra MRIACL_FULL_DONE_%=;\n\t"
+      "bra MRIACL_FULL_WAIT_%=;\n\t"
+      "MRIACL_FULL_DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+#endif
+}
+
 // physical index of logical (un-shifted) FFT index i, and back, for a centred transform
 // of length n:  ifftshift(x)[i] = x[(i + n/2) % n]  and  fftshift(y)[(m + n/2) % n] = y[m]
 // (np.fft.ifftshift / fftshift, REF/src/utils/kspace.py:6-8,13-15).

@@ -352,6 +352,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
     cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
     cp.tw = pl->twH; cp.T = T; cp.oh = a.oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
     cp.frame0 = s0 * a.A * a.C; cp.n_frames = ns * a.A * a.C; cp.done = nullptr;
+    cp.debug_skip = env_int("MRIACL_CP_DEBUG_SKIP", 0);
     const long long col_items = (long long)cp.n_frames * n_groups;
 
     RowPassParams rp{};
