@@ -146,13 +146,14 @@ def reference_arm(args) -> None:
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed regions run.
-    (Polling NVML every 20 ms visibly perturbed sub-millisecond steps; 100 ms does not.)"""
+    """Samples SM clock and throttle reasons of one GPU through NVML.  It polls from before the warm-up
+    (the first NVML queries take milliseconds and contend with kernel launches for the driver) and keeps
+    only the samples that fall inside the timed regions (`active`)."""
     REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index: int, period: float = 0.1):
+    def __init__(self, index: int, period: float = 0.05):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reason_bits, self.active = [], 0, False
@@ -165,25 +166,30 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self._query()
             self.ok = True
         except Exception:
             self.ok = False
+
+    def _query(self):
+        mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+        try:
+            bits = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            bits = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        return mhz, int(bits)
 
     def run(self):
         if not self.ok:
             return
         while not self.stop_flag.is_set():
-            if self.active:
-                try:
-                    mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
-                    try:
-                        bits = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                    except Exception:
-                        bits = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            try:
+                mhz, bits = self._query()
+                if self.active:
                     self.samples.append(mhz)
-                    self.reason_bits |= int(bits)
-                except Exception:
-                    pass
+                    self.reason_bits |= bits
+            except Exception:
+                pass
             time.sleep(self.period)
 
     def summary(self) -> dict:
