@@ -358,7 +358,7 @@ def ours(args) -> None:
             "what": "whole fused stage per step (colpass640 + rowpass + normalise launches): algorithmic "
                     f"{BYTES_PER_SLICE} B/slice x {B} slices / step time",
             "kernels_ms": kern,
-            "dominant_kernel": {"name": "colpass640_kernel",
+            "dominant_kernel": {"name": "colpass640_ws_kernel",
                                 "achieved": step_bytes / (kern["colpass640"] * 1e-3) / 1e9 if kern else None,
                                 "frac": step_bytes / (kern["colpass640"] * 1e-3) / 1e9 / peak if kern else None,
                                 "note": "reads all of k-space once; timed alone with CUDA events (ONLY_COLPASS)"}}

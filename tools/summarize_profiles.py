@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Turn gpurun_out/ captures into the tracked summaries under profiles/.
+usage: python tools/summarize_profiles.py <tag> <launches.csv> <prof.ncu-rep> [bench.json]"""
+import csv, json, os, subprocess, sys, collections
+
+tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+bench = sys.argv[4] if len(sys.argv) > 4 else None
+out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
+os.makedirs(out_dir, exist_ok=True)
+
+# ---- launch list: per-kernel totals and shares ------------------------------------------------
+rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
+per = collections.OrderedDict()
+for r in rows:
+    name, dur = r[4], float(r[-1])
+    short = name.split("(")[0].replace("void ", "").replace("mriacl::", "")
+    if not any(s in short for s in ("colpass", "rowpass", "normalize", "generic", "rss", "crop", "complex_abs")):
+        short = "other(torch): " + short[:60]
+    per.setdefault(short, []).append(dur)
+mine = {k: v for k, v in per.items() if not k.startswith("other")}
+tot = sum(sum(v) for v in mine.values())
+lines = [f"# ncu launch list ({tag}): gpu__time_duration.sum per launch, --clock-control none",
+         "# command: python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1   (under ncu: cold-cache, serialised; compare SHARES)",
+         "kernel,launches,mean_us,total_us,share_of_library_time"]
+for k, v in mine.items():
+    lines.append(f"{k},{len(v)},{sum(v)/len(v)/1e3:.1f},{sum(v)/1e3:.1f},{sum(v)/tot:.3f}")
+open(os.path.join(out_dir, f"{tag}_launches.csv"), "w").write("\n".join(lines) + "\n")
+
+# ---- full capture: key counters per kernel ----------------------------------------------------
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(raw.splitlines()))
+hdr, units = rr[0], rr[1]
+keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+summary = []
+for r in rr[2:]:
+    d = {}
+    for k in keys:
+        if k in hdr:
+            i = hdr.index(k)
+            d[k] = r[i] + (" " + units[i] if units[i] else "")
+    summary.append(d)
+doc = {"tag": tag, "command": "ncu --set full --clock-control none --import-source on -k regex:colpass|rowpass|normalize -s 3 -c 3 "
+                              "python tools/profile_step.py --batch 64 --steps 2 --chunk 64", "kernels": summary}
+if bench and os.path.isfile(bench):
+    doc["bench_line"] = json.load(open(bench))
+json.dump(doc, open(os.path.join(out_dir, f"{tag}_ncu_summary.json"), "w"), indent=1)
+for d in summary:
+    print(d.get("Kernel Name", "?")[:50], d.get("gpu__time_duration.sum"), "| dram rd", d.get("dram__bytes_read.sum"), "wr", d.get("dram__bytes_write.sum"),
+          "| dram%", d.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), "| issue%", d.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+          "| bank conflicts", d.get("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"), "of", d.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"))
