@@ -17,6 +17,7 @@
 #include "generic_kernels.cuh"
 #include "colpass640.cuh"
 #include "rowpass.cuh"
+#include "rowpass16.cuh"
 
 using namespace mriacl;
 
@@ -74,6 +75,9 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, ovl ? 100 : cp_carve);
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX, 100);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
   if (!bad) d.smem_set = true;
   return bad;
 }
@@ -126,6 +130,9 @@ struct FusedPlanDev {
   FusedPlanHost host;            // schedule for RP_NW_SEQ warps
   FusedPlanHost host_ovl;        // schedule for RP_NW_OVL warps (same columns, same sptw)
   int* sched_ovl = nullptr;
+  std::vector<int> pairs12, pairs16;   // 16-row kernel: pair schedules for 12 and 16 warps
+  int* sched_p12 = nullptr;
+  int* sched_p16 = nullptr;
   std::vector<float> mask_copy;
   bool has_mask = false;
   int* act_w = nullptr;
@@ -173,6 +180,13 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     if (rt_malloc(&s2, sizeof(int) * pl->host_ovl.sched.size()) ||
         rt_upload(s2, pl->host_ovl.sched.data(), sizeof(int) * pl->host_ovl.sched.size())) return nullptr;
     pl->sched_ovl = (int*)s2;
+    build_pair_schedule(pl->host, 12, pl->pairs12);
+    build_pair_schedule(pl->host, 16, pl->pairs16);
+    void *s3 = nullptr, *s4 = nullptr;
+    if (rt_malloc(&s3, sizeof(int) * pl->pairs12.size()) || rt_upload(s3, pl->pairs12.data(), sizeof(int) * pl->pairs12.size()) ||
+        rt_malloc(&s4, sizeof(int) * pl->pairs16.size()) || rt_upload(s4, pl->pairs16.data(), sizeof(int) * pl->pairs16.size()))
+      return nullptr;
+    pl->sched_p12 = (int*)s3; pl->sched_p16 = (int*)s4;
     pl->act_w = (int*)a; pl->act_m = (float*)m; pl->sched = (int*)s; pl->sptw = (cf*)t;
     for (float v : h.act_m) if (v != 1.0f) pl->unit_mask = false;
     pl->twH = get_twiddles(dev, H, +1);
@@ -188,7 +202,8 @@ bool fused_shape(int H, int Wp) { return H == CP_N && Wp == FUSED_P * FUSED_Q; }
 
 struct ReconGeom {
   bool fused;
-  int n_act, n_tiles;
+  int n_act, n_tiles;   // n_tiles: 32-row tiles (T row pitch = 32 * n_tiles)
+  int n_tiles16;
   size_t per_slice;     // workspace bytes per slice in flight
   size_t t_bytes;       // intermediate bytes per slice
 };
@@ -197,13 +212,14 @@ int recon_geom(int A, int C, int H, int W, int pad_left, int Wp, int oh, int ow,
                unsigned flags, ReconGeom& g) {
   g.fused = fused_shape(H, Wp) && !(flags & MRIACL_FORCE_GENERIC);
   g.n_tiles = (oh + RP_ROWS - 1) / RP_ROWS;
+  g.n_tiles16 = (oh + RP16_ROWS - 1) / RP16_ROWS;
   if (g.fused) {
     int n_act = 0;
     for (int w = 0; w < W; ++w) n_act += (!mask || mask[w] != 0.0f) ? 1 : 0;
     g.n_act = n_act;
     const size_t ohp = (size_t)g.n_tiles * RP_ROWS;
     g.t_bytes = align_up((size_t)A * C * (size_t)(n_act > 0 ? n_act : 1) * ohp * sizeof(cf), 256);
-    g.per_slice = g.t_bytes + align_up((size_t)g.n_tiles * 3 * sizeof(float), 256) + 256;   // + completion counter
+    g.per_slice = g.t_bytes + align_up((size_t)g.n_tiles16 * 3 * sizeof(float), 256) + 256;   // + completion counter
   } else {
     g.n_act = W;
     g.t_bytes = align_up((size_t)A * C * H * Wp * sizeof(cf), 256);
@@ -336,7 +352,9 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
     n_bufs_ws = 1;
   }
   const size_t buf_bytes = g.per_slice * (size_t)chunk;
-  const size_t part_bytes = align_up((size_t)g.n_tiles * 3 * sizeof(float), 256);
+  const size_t part_bytes = align_up((size_t)g.n_tiles16 * 3 * sizeof(float), 256);
+  // row-pass kernel: 0 = 32-row tiles (16 warps), 1 = 16-row tiles 12 warps x 2 CTAs/SM, 2 = 12 warps x 1, 3 = 16 warps x 1
+  static const int rp16_cfg = env_int("MRIACL_RP16_CFG", 1);
 
   int group = 0;
   for (int s0 = 0; s0 < a.B; s0 += chunk, ++group) {
@@ -388,10 +406,37 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
           MRIACL_LAUNCH(colpass640_kernel<false>, grid, CP_T, CP_SMEM_BYTES_SB, a.st, cp);
         }
       }
-      if (do_row) {
+      if (do_row && rp16_cfg == 0) {
         auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>;
         MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_SEQ * 32, rp_smem, a.st, rp);
+      } else if (do_row) {
+        const bool w16 = rp16_cfg == 3;
+        RowPass16Params q{};
+        q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+        q.sched = w16 ? pl->sched_p16 : pl->sched_p12;
+        q.sched_len = (int)(w16 ? pl->pairs16.size() : pl->pairs12.size());
+        q.sptw = pl->sptw; q.sptw_len = sptw_len; q.tw = pl->twW;
+        q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
+        q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
+        q.n_buf = 2;
+        int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
+        const int limit = rp16_cfg == 1 ? SMEM_MAX / 2 : SMEM_MAX;
+        if (smem16 > limit) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
+        if (smem16 > limit) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
+        const int items16 = ns * g.n_tiles16;
+        np.n_part = g.n_tiles16;
+        if (rp16_cfg == 1) {
+          auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>;
+          MRIACL_LAUNCH(kfn, std::min(items16, 2 * a.sms), 12 * 32, smem16, a.st, q);
+        } else if (rp16_cfg == 2) {
+          auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>;
+          MRIACL_LAUNCH(kfn, std::min(items16, a.sms), 12 * 32, smem16, a.st, q);
+        } else {
+          auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>;
+          MRIACL_LAUNCH(kfn, std::min(items16, a.sms), 16 * 32, smem16, a.st, q);
+        }
       }
+      if (rp16_cfg != 0 && !do_row) np.n_part = g.n_tiles16;
       if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, a.st, np);
     } else {
       // T buffer wb: its previous reader (row pass of group - n_bufs_ws) must be done

@@ -145,6 +145,78 @@ inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow,
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Pair schedule for the 16-row row pass (rowpass16.cuh): the two half-warps of a warp run two units of the
+// same kind (dense piece type / sparse nnz) side by side.
+//   sched[w], w < n_warps   offset of warp w's list
+//   list: n_pairs, then per pair: type, nnz, offA, offB   (offB = -1: second half-warp idles)
+//   unit payload at offA / offB: n2, then  dense: P column indices (or -1);  sparse: sptw offset, nnz column indices
+// Built from the 32-row schedule's units (same columns, same sptw rows), so both kernels do the same arithmetic.
+inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vector<int>& out) {
+  // recover the units from the 32-row schedule
+  struct U { int n2, type, nnz; std::vector<int> payload; double cost; };
+  std::vector<U> units;
+  const int nw32 = pl.sched.empty() ? 0 : pl.sched[0];   // first list starts right after the offset table
+  for (int w = 0; w < nw32; ++w) {
+    int off = pl.sched[w];
+    const int n_units = pl.sched[off++];
+    for (int u = 0; u < n_units; ++u) {
+      U x; x.n2 = pl.sched[off]; x.type = pl.sched[off + 1]; x.nnz = pl.sched[off + 2]; off += 3;
+      const int len = x.type != 0 ? pl.P : 1 + x.nnz;
+      x.payload.assign(pl.sched.begin() + off, pl.sched.begin() + off + len);
+      off += len;
+      const double hp = (pl.P - 1) / 2;
+      const double full = 2.0 * pl.P + 2.2 * (pl.P - 1) + hp * (4.0 * hp + 26.0);
+      x.cost = x.type == 1 ? full : x.type != 0 ? 0.5 * full + 30.0 : 20.0 + pl.P * (2.5 * x.nnz + 1.5);
+      units.push_back(x);
+    }
+  }
+  std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) {
+    if (a.type != b.type) return a.type > b.type;
+    if (a.nnz != b.nnz) return a.nnz > b.nnz;
+    return a.n2 < b.n2;
+  });
+  struct Pair { int a, b; double cost; };
+  std::vector<Pair> pairs;
+  for (size_t i = 0; i < units.size();) {
+    if (i + 1 < units.size() && units[i].type == units[i + 1].type && units[i].nnz == units[i + 1].nnz) {
+      pairs.push_back({(int)i, (int)i + 1, units[i].cost}); i += 2;
+    } else { pairs.push_back({(int)i, -1, units[i].cost}); i += 1; }
+  }
+  std::vector<int> order(pairs.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pairs[a].cost > pairs[b].cost; });
+  std::vector<std::vector<int>> per_warp(n_warps);
+  std::vector<double> load(n_warps, 0.0);
+  for (int pi : order) {
+    int best = 0;
+    for (int w = 1; w < n_warps; ++w) if (load[w] < load[best]) best = w;
+    per_warp[best].push_back(pi);
+    load[best] += pairs[pi].cost;
+  }
+  out.assign(n_warps, 0);
+  std::vector<std::pair<int, int>> patch;   // (position in out, unit index)
+  for (int w = 0; w < n_warps; ++w) {
+    out[w] = (int)out.size();
+    out.push_back((int)per_warp[w].size());
+    for (int pi : per_warp[w]) {
+      const Pair& pr = pairs[pi];
+      out.push_back(units[pr.a].type); out.push_back(units[pr.a].nnz);
+      patch.push_back({(int)out.size(), pr.a}); out.push_back(0);
+      if (pr.b >= 0) { patch.push_back({(int)out.size(), pr.b}); out.push_back(0); } else out.push_back(-1);
+    }
+  }
+  std::vector<int> unit_off(units.size(), -1);
+  for (auto& pu : patch) {
+    if (unit_off[pu.second] < 0) {
+      unit_off[pu.second] = (int)out.size();
+      out.push_back(units[pu.second].n2);
+      out.insert(out.end(), units[pu.second].payload.begin(), units[pu.second].payload.end());
+    }
+    out[pu.first] = unit_off[pu.second];
+  }
+}
+
 // FNV-1a over the plan-defining inputs: cache key for device-resident plans
 inline uint64_t plan_key(const int* dims, int n_dims, const float* mask, int mask_len) {
   uint64_t h = 1469598103934665603ull;

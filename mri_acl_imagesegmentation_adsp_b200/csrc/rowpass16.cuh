@@ -1,0 +1,273 @@
+// rowpass16.cuh -- fused row pass on 16-row tiles: the two half-warps of a warp work on two different
+// plan units (stage 1) / two different k1 (stage 2) of the SAME 16 rows, lane & 15 = row.
+//
+// Compared with the 32-row kernel in rowpass.cuh this halves the shared-memory tile (Y: 47 KB), halves
+// the |X|^2 accumulators a thread keeps across the coil loop (16 instead of 32-48), doubles the number
+// of work items (finer tail) and leaves room on the SM for column-pass CTAs (overlapped schedule).
+// Every shared-memory access is still two fully used 128-byte segments per warp: no bank conflicts.
+//
+// Algorithm per coil frame (identical arithmetic to rowpass.cuh, so results are bit-identical):
+//   prefetch [n_act][16 rows] of T with cp.async one frame ahead;
+//   stage 1: pruned P-point DFTs of the sampled columns (dense residues: symmetric direct DFT, split in two
+//            output halves; sparse residues: tabulated twiddles), two units per warp, paired by the host
+//            plan so that both half-warps run the same code path;
+//   stage 2: two 16-point register FFTs per warp (k1 = 2 pair, 2 pair + 1), accumulate |X|^2.
+#pragma once
+#include "rowpass.cuh"
+
+namespace mriacl {
+
+constexpr int RP16_ROWS = 16;
+
+struct RowPass16Params {
+  const cf* T;           // [n_slices*A*C][n_act][ohp]
+  int n_act, oh, ohp;
+  const int* sched;      // pair schedule, see plan.h (build_pair_schedule)
+  int sched_len;
+  const cf* sptw;
+  int sptw_len;
+  const cf* tw;          // w_N^k = exp(+2 pi i k / N)
+  float* out;
+  float* partials;       // [n_slices][n_tiles][3]
+  int ow, col0;
+  int A, C;
+  float scale;
+  int n_slices, n_tiles; // n_tiles = ceil(oh / 16)
+  int n_buf;
+  const int* done;
+  int done_target;
+  int* error_flag;
+};
+
+inline int rowpass16_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_act, int n_buf, int ow, int A) {
+  return P * Q * RP16_ROWS * 8 + P * Q * 8 + rp_round16(sptw_len * 8) + rp_round16(sched_len * 4) +
+         n_buf * n_act * RP16_ROWS * 8 + (A > 1 ? RP16_ROWS * (ow + 1) * 4 : 0);
+}
+
+template <int P, int Q, int NNZ>
+__device__ __forceinline__ void rp16_sparse_unit(const int* pay, const cf* tb, const cf* sptw, cf* ycol, bool active) {
+  constexpr int PITCH = 24;
+  cf xe[NNZ > 0 ? NNZ : 1];
+  const float4* tw4 = reinterpret_cast<const float4*>(sptw + pay[1]);
+#pragma unroll
+  for (int e = 0; e < NNZ; ++e) xe[e] = tb[pay[2 + e] * RP16_ROWS];
+#pragma unroll
+  for (int kp = 0; kp < PITCH / 2; ++kp) {
+    float re0 = 0.f, im0 = 0.f, re1 = 0.f, im1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < NNZ; ++e) {
+      const float4 w = tw4[e * (PITCH / 2) + kp];
+      re0 = fmaf(xe[e].x, w.x, fmaf(-xe[e].y, w.y, re0));
+      im0 = fmaf(xe[e].x, w.y, fmaf(xe[e].y, w.x, im0));
+      re1 = fmaf(xe[e].x, w.z, fmaf(-xe[e].y, w.w, re1));
+      im1 = fmaf(xe[e].x, w.w, fmaf(xe[e].y, w.z, im1));
+    }
+    if (active) {
+      ycol[(2 * kp) * Q * RP16_ROWS] = cf_make(re0, im0);
+      if (2 * kp + 1 < P) ycol[(2 * kp + 1) * Q * RP16_ROWS] = cf_make(re1, im1);
+    }
+  }
+}
+
+template <int P, int Q, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Params p) {
+  static_assert(Q == 16, "stage 2 is the register-level 16-point FFT");
+  constexpr int N = P * Q;
+  constexpr int NT = NW * 32;
+  constexpr int NPAIR = (P + 1) / 2;                 // stage-2 pairs of k1
+  constexpr int KPW = (NPAIR + NW - 1) / NW;
+  constexpr int HP = (P - 1) / 2;
+  constexpr int HSPLIT = (HP + 2) / 2;
+  MRIACL_DYN_SMEM(cf, Y);                            // [P][Q][16]
+  cf* twsm = Y + N * RP16_ROWS;
+  cf* sptwsm = twsm + N;
+  int* schsm = reinterpret_cast<int*>(reinterpret_cast<char*>(sptwsm) + rp_round16(p.sptw_len * 8));
+  cf* tbuf = reinterpret_cast<cf*>(reinterpret_cast<char*>(schsm) + rp_round16(p.sched_len * 4));   // [n_buf][n_act][16]
+  float* avsm = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * p.n_act * RP16_ROWS);
+  float* osm = reinterpret_cast<float*>(Y);          // output tile [16][ow+1], aliases Y
+  __shared__ float red[NW];
+  __shared__ int ready;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = lane >> 4, r = lane & 15;
+  const int opitch = p.ow + 1;
+  for (int i = tid; i < N; i += NT) twsm[i] = p.tw[i];
+  for (int i = tid; i < p.sched_len; i += NT) schsm[i] = p.sched[i];
+  for (int i = tid; i < p.sptw_len; i += NT) sptwsm[i] = p.sptw[i];
+  __syncthreads();
+
+  const int my_off = schsm[warp];
+  const int n_items = p.n_slices * p.n_tiles;
+  const int n_frames = p.A * p.C;
+  const long long frame_elems = (long long)p.n_act * p.ohp;
+  const int tile_elems = p.n_act * RP16_ROWS;
+  const int n_copies = p.n_act * (RP16_ROWS / 2);    // 16-byte copies per block (8 per column)
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int s = item / p.n_tiles, tile = item - s * p.n_tiles;
+    const cf* Tit = p.T + (long long)s * n_frames * frame_elems + tile * RP16_ROWS;
+
+    auto prefetch = [&](int f, int buf) {
+      const cf* src = Tit + (long long)f * frame_elems + (long long)(tid >> 3) * p.ohp + 2 * (tid & 7);
+      cf* dst = tbuf + (size_t)buf * tile_elems + (tid >> 3) * RP16_ROWS + 2 * (tid & 7);
+      for (int i = tid; i < n_copies; i += NT) {
+        cp_async16(dst, src);
+        src += (long long)(NT / 8) * p.ohp;
+        dst += (NT / 8) * RP16_ROWS;
+      }
+      cp_async_commit();
+    };
+
+    if (p.done) {
+      if (tid == 0) {
+        ready = rp_wait_count(p.done + s, p.done_target, p.error_flag) ? 1 : 0;
+        if (!ready && p.error_flag) atomicAdd(p.error_flag, 1);
+      }
+      __syncthreads();
+      if (!ready) return;
+    }
+    if (p.A > 1) for (int i = tid; i < RP16_ROWS * opitch; i += NT) avsm[i] = 0.f;
+    prefetch(0, 0);
+
+    float acc[KPW][Q];
+    for (int f = 0; f < n_frames; ++f) {
+      const int buf = p.n_buf == 2 ? (f & 1) : 0;
+      if (f % p.C == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KPW; ++kk)
+#pragma unroll
+          for (int k2 = 0; k2 < Q; ++k2) acc[kk][k2] = 0.f;
+      }
+      if (p.n_buf == 2) {
+        if (f + 1 < n_frames) { prefetch(f + 1, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+
+      // ---------------- stage 1: two units per warp ----------------
+      {
+        const cf* tb = tbuf + (size_t)buf * tile_elems + r;
+        const int n_pairs = schsm[my_off];
+        int off = my_off + 1;
+        for (int u = 0; u < n_pairs; ++u, off += 4) {
+          const int type = schsm[off], nnz = schsm[off + 1];
+          const int offB = schsm[off + 3];
+          const bool active = half == 0 || offB >= 0;
+          const int* pay = schsm + ((half == 0 || offB < 0) ? schsm[off + 2] : offB);
+          const int n2 = pay[0];
+          cf* ycol = Y + n2 * RP16_ROWS + r;             // + k1 * Q * 16
+          if (type != 0) {
+            cf x[P];
+#pragma unroll
+            for (int n1 = 0; n1 < P; ++n1) {
+              const int j = pay[1 + n1];
+              x[n1] = j >= 0 ? tb[j * RP16_ROWS] : cf_make(0.f, 0.f);
+            }
+            auto emit = [&](auto kc, cf val) {
+              constexpr int k1 = decltype(kc)::value;
+              if (k1 != 0) val = cmul(val, twsm[(n2 * k1) % N]);
+              if (active) ycol[k1 * Q * RP16_ROWS] = val;
+            };
+            if (type == 1) dft_odd_sym_part<P, true, 1, HP + 1, true>(x, emit);
+            else if (type == 2) dft_odd_sym_part<P, true, 1, HSPLIT, true>(x, emit);
+            else dft_odd_sym_part<P, true, HSPLIT, HP + 1, false>(x, emit);
+          } else {
+            switch (nnz) {
+              case 0: rp16_sparse_unit<P, Q, 0>(pay, tb, sptwsm, ycol, active); break;
+              case 1: rp16_sparse_unit<P, Q, 1>(pay, tb, sptwsm, ycol, active); break;
+              case 2: rp16_sparse_unit<P, Q, 2>(pay, tb, sptwsm, ycol, active); break;
+              case 3: rp16_sparse_unit<P, Q, 3>(pay, tb, sptwsm, ycol, active); break;
+              case 4: rp16_sparse_unit<P, Q, 4>(pay, tb, sptwsm, ycol, active); break;
+              case 5: rp16_sparse_unit<P, Q, 5>(pay, tb, sptwsm, ycol, active); break;
+              default: rp16_sparse_unit<P, Q, 6>(pay, tb, sptwsm, ycol, active); break;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (p.n_buf == 1 && f + 1 < n_frames) prefetch(f + 1, 0);
+
+      // ---------------- stage 2: two 16-point FFTs per warp ----------------
+#pragma unroll
+      for (int kk = 0; kk < KPW; ++kk) {
+        const int pair = warp + NW * kk;
+        const int k1 = 2 * pair + half;
+        if (pair < NPAIR) {
+          const int k1c = k1 < P ? k1 : P - 1;           // odd P: the last pair has one idle half
+          cf v[Q];
+          const cf* yrow = Y + k1c * Q * RP16_ROWS + r;
+#pragma unroll
+          for (int n2 = 0; n2 < Q; ++n2) v[n2] = yrow[n2 * RP16_ROWS];
+          fft16<true>(v);
+#pragma unroll
+          for (int k2 = 0; k2 < Q; ++k2) acc[kk][k2] = cnorm2_acc(v[k2], acc[kk][k2]);
+        }
+      }
+
+      if (p.A > 1 && (f + 1) % p.C == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KPW; ++kk) {
+          const int pair = warp + NW * kk;
+          const int k1 = 2 * pair + half;
+          if (pair < NPAIR && k1 < P) {
+#pragma unroll
+            for (int k2 = 0; k2 < Q; ++k2) {
+              const int cc = phys_of_logical(k1 + P * k2, N) - p.col0;
+              if (cc >= 0 && cc < p.ow) avsm[r * opitch + cc] += sqrtf(acc[kk][k2]) * p.scale;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (p.A == 1) {
+#pragma unroll
+      for (int kk = 0; kk < KPW; ++kk) {
+        const int pair = warp + NW * kk;
+        const int k1 = 2 * pair + half;
+        if (pair < NPAIR && k1 < P) {
+#pragma unroll
+          for (int k2 = 0; k2 < Q; ++k2) {
+            const int cc = phys_of_logical(k1 + P * k2, N) - p.col0;
+            if (cc >= 0 && cc < p.ow) osm[r * opitch + cc] = sqrtf(acc[kk][k2]) * p.scale;
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    const float* tile_sm = p.A > 1 ? avsm : osm;
+    const float inv_a = 1.0f / (float)p.A;
+    const int rows_here = min(RP16_ROWS, p.oh - tile * RP16_ROWS);
+    const int n_here = rows_here * p.ow;
+    float* dst = p.out + ((long long)s * p.oh + tile * RP16_ROWS) * p.ow;
+    float lsum = 0.f;
+    for (int e = tid; e < n_here; e += NT) {
+      const int rr = e / p.ow, cc = e - rr * p.ow;
+      float v = tile_sm[rr * opitch + cc];
+      if (p.A > 1) v *= inv_a;
+      dst[e] = v;
+      lsum += v;
+    }
+    if (p.partials) {
+      const float mean = rp_block_sum<NW>(lsum, red) / (float)n_here;
+      float lq = 0.f;
+      for (int e = tid; e < n_here; e += NT) {
+        const int rr = e / p.ow, cc = e - rr * p.ow;
+        float v = tile_sm[rr * opitch + cc];
+        if (p.A > 1) v *= inv_a;
+        const float d = v - mean;
+        lq = fmaf(d, d, lq);
+      }
+      const float m2 = rp_block_sum<NW>(lq, red);
+      if (tid == 0) {
+        float* q = p.partials + ((long long)s * p.n_tiles + tile) * 3;
+        q[0] = (float)n_here; q[1] = mean; q[2] = m2;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mriacl
