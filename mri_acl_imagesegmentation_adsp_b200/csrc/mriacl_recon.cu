@@ -131,6 +131,8 @@ struct FusedPlanDev {
   FusedPlanHost host_ovl;        // schedule for RP_NW_OVL warps (same columns, same sptw)
   int* sched_ovl = nullptr;
   std::vector<int> pairs12, pairs16;   // 16-row kernel: pair schedules for 12 and 16 warps
+  std::vector<HostCf> sptw16;
+  cf* sptw16_dev = nullptr;
   int* sched_p12 = nullptr;
   int* sched_p16 = nullptr;
   std::vector<float> mask_copy;
@@ -180,9 +182,12 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     if (rt_malloc(&s2, sizeof(int) * pl->host_ovl.sched.size()) ||
         rt_upload(s2, pl->host_ovl.sched.data(), sizeof(int) * pl->host_ovl.sched.size())) return nullptr;
     pl->sched_ovl = (int*)s2;
-    build_pair_schedule(pl->host, 12, pl->pairs12);
-    build_pair_schedule(pl->host, 16, pl->pairs16);
-    void *s3 = nullptr, *s4 = nullptr;
+    build_pair_schedule(pl->host, 12, pl->pairs12, pl->sptw16);
+    build_pair_schedule(pl->host, 16, pl->pairs16, pl->sptw16);
+    void *s3 = nullptr, *s4 = nullptr, *t16 = nullptr;
+    if (rt_malloc(&t16, sizeof(HostCf) * pl->sptw16.size()) ||
+        (!pl->sptw16.empty() && rt_upload(t16, pl->sptw16.data(), sizeof(HostCf) * pl->sptw16.size()))) return nullptr;
+    pl->sptw16_dev = (cf*)t16;
     if (rt_malloc(&s3, sizeof(int) * pl->pairs12.size()) || rt_upload(s3, pl->pairs12.data(), sizeof(int) * pl->pairs12.size()) ||
         rt_malloc(&s4, sizeof(int) * pl->pairs16.size()) || rt_upload(s4, pl->pairs16.data(), sizeof(int) * pl->pairs16.size()))
       return nullptr;
@@ -415,13 +420,13 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
         q.sched = w16 ? pl->sched_p16 : pl->sched_p12;
         q.sched_len = (int)(w16 ? pl->pairs16.size() : pl->pairs12.size());
-        q.sptw = pl->sptw; q.sptw_len = sptw_len; q.tw = pl->twW;
+        q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size();
         q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
         q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
         q.n_buf = 2;
-        int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
+        int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
         const int limit = rp16_cfg == 1 ? SMEM_MAX / 2 : SMEM_MAX;
-        if (smem16 > limit) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
+        if (smem16 > limit) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
         if (smem16 > limit) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
         const int items16 = ns * g.n_tiles16;
         np.n_part = g.n_tiles16;

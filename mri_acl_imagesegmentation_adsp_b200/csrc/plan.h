@@ -150,9 +150,12 @@ inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow,
 // same kind (dense piece type / sparse nnz) side by side.
 //   sched[w], w < n_warps   offset of warp w's list
 //   list: n_pairs, then per pair: type, nnz, offA, offB   (offB = -1: second half-warp idles)
-//   unit payload at offA / offB: n2, then  dense: P column indices (or -1);  sparse: sptw offset, nnz column indices
+//   unit payload at offA / offB: n2, then  dense: twiddle-row offset, P column indices (or -1);
+//                                          sparse: twiddle-row offset, nnz column indices
+//   sptw16 = the sparse twiddle rows followed by one row w_N^{n2 k1} per dense residue
+//   an idle second half-warp (offB = -1) repeats unit A but stores into the spare residue column n2 = Q
 // Built from the 32-row schedule's units (same columns, same sptw rows), so both kernels do the same arithmetic.
-inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vector<int>& out) {
+inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vector<int>& out, std::vector<HostCf>& sptw16) {
   // recover the units from the 32-row schedule
   struct U { int n2, type, nnz; std::vector<int> payload; double cost; };
   std::vector<U> units;
@@ -194,6 +197,16 @@ inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vecto
     per_warp[best].push_back(pi);
     load[best] += pairs[pi].cost;
   }
+  // twiddle rows of the dense residues: dtw[n2][k1] = w_N^{n2 k1}, appended to a copy of sptw
+  sptw16 = pl.sptw;
+  const std::vector<HostCf> twN = make_twiddles(pl.Wp, +1);
+  std::vector<int> dense_row(pl.Q, -1);
+  for (auto& u : units)
+    if (u.type != 0 && dense_row[u.n2] < 0) {
+      dense_row[u.n2] = (int)sptw16.size();
+      for (int k1 = 0; k1 < SPTW_PITCH; ++k1)
+        sptw16.push_back(k1 < pl.P ? twN[(size_t)(((long long)u.n2 * k1) % pl.Wp)] : HostCf{0.f, 0.f});
+    }
   out.assign(n_warps, 0);
   std::vector<std::pair<int, int>> patch;   // (position in out, unit index)
   for (int w = 0; w < n_warps; ++w) {
@@ -211,6 +224,7 @@ inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vecto
     if (unit_off[pu.second] < 0) {
       unit_off[pu.second] = (int)out.size();
       out.push_back(units[pu.second].n2);
+      if (units[pu.second].type != 0) out.push_back(dense_row[units[pu.second].n2]);
       out.insert(out.end(), units[pu.second].payload.begin(), units[pu.second].payload.end());
     }
     out[pu.first] = unit_off[pu.second];

@@ -24,9 +24,8 @@ struct RowPass16Params {
   int n_act, oh, ohp;
   const int* sched;      // pair schedule, see plan.h (build_pair_schedule)
   int sched_len;
-  const cf* sptw;
+  const cf* sptw;        // sparse twiddle rows followed by the dense residues' rows w_N^{n2 k1} (pitch 24)
   int sptw_len;
-  const cf* tw;          // w_N^k = exp(+2 pi i k / N)
   float* out;
   float* partials;       // [n_slices][n_tiles][3]
   int ow, col0;
@@ -40,12 +39,13 @@ struct RowPass16Params {
 };
 
 inline int rowpass16_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_act, int n_buf, int ow, int A) {
-  return P * Q * RP16_ROWS * 8 + P * Q * 8 + rp_round16(sptw_len * 8) + rp_round16(sched_len * 4) +
+  return P * (Q + 1) * RP16_ROWS * 8 + rp_round16(sptw_len * 8) + rp_round16(sched_len * 4) +
          n_buf * n_act * RP16_ROWS * 8 + (A > 1 ? RP16_ROWS * (ow + 1) * 4 : 0);
 }
 
 template <int P, int Q, int NNZ>
-__device__ __forceinline__ void rp16_sparse_unit(const int* pay, const cf* tb, const cf* sptw, cf* ycol, bool active) {
+__device__ __forceinline__ void rp16_sparse_unit(const int* pay, const cf* tb, const cf* sptw, cf* ycol) {
+  constexpr int YS = (Q + 1) * RP16_ROWS;   // Y stride between k1
   constexpr int PITCH = 24;
   cf xe[NNZ > 0 ? NNZ : 1];
   const float4* tw4 = reinterpret_cast<const float4*>(sptw + pay[1]);
@@ -62,10 +62,8 @@ __device__ __forceinline__ void rp16_sparse_unit(const int* pay, const cf* tb, c
       re1 = fmaf(xe[e].x, w.z, fmaf(-xe[e].y, w.w, re1));
       im1 = fmaf(xe[e].x, w.w, fmaf(xe[e].y, w.z, im1));
     }
-    if (active) {
-      ycol[(2 * kp) * Q * RP16_ROWS] = cf_make(re0, im0);
-      if (2 * kp + 1 < P) ycol[(2 * kp + 1) * Q * RP16_ROWS] = cf_make(re1, im1);
-    }
+    ycol[(2 * kp) * YS] = cf_make(re0, im0);
+    if (2 * kp + 1 < P) ycol[(2 * kp + 1) * YS] = cf_make(re1, im1);
   }
 }
 
@@ -78,9 +76,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
   constexpr int KPW = (NPAIR + NW - 1) / NW;
   constexpr int HP = (P - 1) / 2;
   constexpr int HSPLIT = (HP + 2) / 2;
-  MRIACL_DYN_SMEM(cf, Y);                            // [P][Q][16]
-  cf* twsm = Y + N * RP16_ROWS;
-  cf* sptwsm = twsm + N;
+  constexpr int YS = (Q + 1) * RP16_ROWS;            // residue column Q is a write-only spare for idle half-warps
+  MRIACL_DYN_SMEM(cf, Y);                            // [P][Q + 1][16]
+  cf* sptwsm = Y + P * YS;
   int* schsm = reinterpret_cast<int*>(reinterpret_cast<char*>(sptwsm) + rp_round16(p.sptw_len * 8));
   cf* tbuf = reinterpret_cast<cf*>(reinterpret_cast<char*>(schsm) + rp_round16(p.sched_len * 4));   // [n_buf][n_act][16]
   float* avsm = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * p.n_act * RP16_ROWS);
@@ -91,7 +89,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int half = lane >> 4, r = lane & 15;
   const int opitch = p.ow + 1;
-  for (int i = tid; i < N; i += NT) twsm[i] = p.tw[i];
   for (int i = tid; i < p.sched_len; i += NT) schsm[i] = p.sched[i];
   for (int i = tid; i < p.sptw_len; i += NT) sptwsm[i] = p.sptw[i];
   __syncthreads();
@@ -153,34 +150,34 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
         for (int u = 0; u < n_pairs; ++u, off += 4) {
           const int type = schsm[off], nnz = schsm[off + 1];
           const int offB = schsm[off + 3];
-          const bool active = half == 0 || offB >= 0;
           const int* pay = schsm + ((half == 0 || offB < 0) ? schsm[off + 2] : offB);
-          const int n2 = pay[0];
-          cf* ycol = Y + n2 * RP16_ROWS + r;             // + k1 * Q * 16
+          const int n2 = (half == 1 && offB < 0) ? Q : pay[0];     // idle half: spare column
+          cf* ycol = Y + n2 * RP16_ROWS + r;                       // + k1 * YS
           if (type != 0) {
             cf x[P];
 #pragma unroll
             for (int n1 = 0; n1 < P; ++n1) {
-              const int j = pay[1 + n1];
+              const int j = pay[2 + n1];
               x[n1] = j >= 0 ? tb[j * RP16_ROWS] : cf_make(0.f, 0.f);
             }
+            const cf* dtw = sptwsm + pay[1];
             auto emit = [&](auto kc, cf val) {
               constexpr int k1 = decltype(kc)::value;
-              if (k1 != 0) val = cmul(val, twsm[(n2 * k1) % N]);
-              if (active) ycol[k1 * Q * RP16_ROWS] = val;
+              if (k1 != 0) val = cmul(val, dtw[k1]);
+              ycol[k1 * YS] = val;
             };
             if (type == 1) dft_odd_sym_part<P, true, 1, HP + 1, true>(x, emit);
             else if (type == 2) dft_odd_sym_part<P, true, 1, HSPLIT, true>(x, emit);
             else dft_odd_sym_part<P, true, HSPLIT, HP + 1, false>(x, emit);
           } else {
             switch (nnz) {
-              case 0: rp16_sparse_unit<P, Q, 0>(pay, tb, sptwsm, ycol, active); break;
-              case 1: rp16_sparse_unit<P, Q, 1>(pay, tb, sptwsm, ycol, active); break;
-              case 2: rp16_sparse_unit<P, Q, 2>(pay, tb, sptwsm, ycol, active); break;
-              case 3: rp16_sparse_unit<P, Q, 3>(pay, tb, sptwsm, ycol, active); break;
-              case 4: rp16_sparse_unit<P, Q, 4>(pay, tb, sptwsm, ycol, active); break;
-              case 5: rp16_sparse_unit<P, Q, 5>(pay, tb, sptwsm, ycol, active); break;
-              default: rp16_sparse_unit<P, Q, 6>(pay, tb, sptwsm, ycol, active); break;
+              case 0: rp16_sparse_unit<P, Q, 0>(pay, tb, sptwsm, ycol); break;
+              case 1: rp16_sparse_unit<P, Q, 1>(pay, tb, sptwsm, ycol); break;
+              case 2: rp16_sparse_unit<P, Q, 2>(pay, tb, sptwsm, ycol); break;
+              case 3: rp16_sparse_unit<P, Q, 3>(pay, tb, sptwsm, ycol); break;
+              case 4: rp16_sparse_unit<P, Q, 4>(pay, tb, sptwsm, ycol); break;
+              case 5: rp16_sparse_unit<P, Q, 5>(pay, tb, sptwsm, ycol); break;
+              default: rp16_sparse_unit<P, Q, 6>(pay, tb, sptwsm, ycol); break;
             }
           }
         }
@@ -196,7 +193,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
         if (pair < NPAIR) {
           const int k1c = k1 < P ? k1 : P - 1;           // odd P: the last pair has one idle half
           cf v[Q];
-          const cf* yrow = Y + k1c * Q * RP16_ROWS + r;
+          const cf* yrow = Y + k1c * YS + r;
 #pragma unroll
           for (int n2 = 0; n2 < Q; ++n2) v[n2] = yrow[n2 * RP16_ROWS];
           fft16<true>(v);
