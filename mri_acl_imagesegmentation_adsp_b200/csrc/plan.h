@@ -169,9 +169,20 @@ inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vecto
       x.payload.assign(pl.sched.begin() + off, pl.sched.begin() + off + len);
       off += len;
       const double hp = (pl.P - 1) / 2;
-      const double full = 2.0 * pl.P + 2.2 * (pl.P - 1) + hp * (4.0 * hp + 26.0);
-      x.cost = x.type == 1 ? full : x.type != 0 ? 0.5 * full + 30.0 : 20.0 + pl.P * (2.5 * x.nnz + 1.5);
-      units.push_back(x);
+      const double shared = 2.0 * pl.P + 2.2 * (pl.P - 1);            // loads + a_n / b_n, repeated by every part
+      const double per_pair = 4.0 * hp + 26.0;
+      if (x.type == 0) {
+        x.cost = 20.0 + pl.P * (2.5 * x.nnz + 1.5);
+        units.push_back(x);
+      } else if (x.type != 3) {     // one entry per dense residue (the 32-row schedule lists halves 2 and 3)
+        // 16-row kernel: thirds of the output pairs, types 2, 3, 4
+        const int n0 = (int)hp / 3, n1 = ((int)hp - n0 + 1) / 2, n2 = (int)hp - n0 - n1;
+        const int cnt[3] = {n0, n1, n2};
+        for (int part = 0; part < 3; ++part) {
+          U y = x; y.type = 2 + part; y.cost = shared + per_pair * cnt[part] + (part == 0 ? 30.0 : 0.0);
+          units.push_back(y);
+        }
+      }
     }
   }
   std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) {

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
   constexpr int NPAIR = (P + 1) / 2;                 // stage-2 pairs of k1
   constexpr int KPW = (NPAIR + NW - 1) / NW;
   constexpr int HP = (P - 1) / 2;
-  constexpr int HSPLIT = (HP + 2) / 2;
+  // dense residues are shared by three warps-halves: output pairs [1, B1) (+ X0), [B1, B2), [B2, HP]
+  constexpr int B1 = 1 + HP / 3, B2 = B1 + (HP - HP / 3 + 1) / 2;
   constexpr int YS = (Q + 1) * RP16_ROWS;            // residue column Q is a write-only spare for idle half-warps
   MRIACL_DYN_SMEM(cf, Y);                            // [P][Q + 1][16]
   cf* sptwsm = Y + P * YS;
@@ -104,9 +105,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
     const int s = item / p.n_tiles, tile = item - s * p.n_tiles;
     const cf* Tit = p.T + (long long)s * n_frames * frame_elems + tile * RP16_ROWS;
 
+    const cf* src0 = Tit + (long long)(tid >> 3) * p.ohp + 2 * (tid & 7);
+    cf* dst0 = tbuf + (tid >> 3) * RP16_ROWS + 2 * (tid & 7);
     auto prefetch = [&](int f, int buf) {
-      const cf* src = Tit + (long long)f * frame_elems + (long long)(tid >> 3) * p.ohp + 2 * (tid & 7);
-      cf* dst = tbuf + (size_t)buf * tile_elems + (tid >> 3) * RP16_ROWS + 2 * (tid & 7);
+      const cf* src = src0 + (long long)f * frame_elems;
+      cf* dst = dst0 + (size_t)buf * tile_elems;
       for (int i = tid; i < n_copies; i += NT) {
         cp_async16(dst, src);
         src += (long long)(NT / 8) * p.ohp;
@@ -127,9 +130,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
     prefetch(0, 0);
 
     float acc[KPW][Q];
+    int coil = 0;
     for (int f = 0; f < n_frames; ++f) {
       const int buf = p.n_buf == 2 ? (f & 1) : 0;
-      if (f % p.C == 0) {
+      if (coil == 0) {
 #pragma unroll
         for (int kk = 0; kk < KPW; ++kk)
 #pragma unroll
@@ -166,9 +170,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
               if (k1 != 0) val = cmul(val, dtw[k1]);
               ycol[k1 * YS] = val;
             };
-            if (type == 1) dft_odd_sym_part<P, true, 1, HP + 1, true>(x, emit);
-            else if (type == 2) dft_odd_sym_part<P, true, 1, HSPLIT, true>(x, emit);
-            else dft_odd_sym_part<P, true, HSPLIT, HP + 1, false>(x, emit);
+            if (type == 2) dft_odd_sym_part<P, true, 1, B1, true>(x, emit);
+            else if (type == 3) dft_odd_sym_part<P, true, B1, B2, false>(x, emit);
+            else dft_odd_sym_part<P, true, B2, HP + 1, false>(x, emit);
           } else {
             switch (nnz) {
               case 0: rp16_sparse_unit<P, Q, 0>(pay, tb, sptwsm, ycol); break;
@@ -202,16 +206,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
         }
       }
 
-      if (p.A > 1 && (f + 1) % p.C == 0) {
+      if (++coil == p.C) {
+        coil = 0;
+        if (p.A > 1) {
 #pragma unroll
-        for (int kk = 0; kk < KPW; ++kk) {
-          const int pair = warp + NW * kk;
-          const int k1 = 2 * pair + half;
-          if (pair < NPAIR && k1 < P) {
+          for (int kk = 0; kk < KPW; ++kk) {
+            const int pair = warp + NW * kk;
+            const int k1 = 2 * pair + half;
+            if (pair < NPAIR && k1 < P) {
 #pragma unroll
-            for (int k2 = 0; k2 < Q; ++k2) {
-              const int cc = phys_of_logical(k1 + P * k2, N) - p.col0;
-              if (cc >= 0 && cc < p.ow) avsm[r * opitch + cc] += sqrtf(acc[kk][k2]) * p.scale;
+              for (int k2 = 0; k2 < Q; ++k2) {
+                const int cc = phys_of_logical(k1 + P * k2, N) - p.col0;
+                if (cc >= 0 && cc < p.ow) avsm[r * opitch + cc] += sqrtf(acc[kk][k2]) * p.scale;
+              }
             }
           }
         }
