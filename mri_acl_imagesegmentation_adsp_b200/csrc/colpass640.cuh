@@ -223,20 +223,19 @@ __global__ void __launch_bounds__(CP_T, DB ? 2 : 4) colpass640_kernel(ColPassPar
 constexpr int CP_WS_T = CP_T + 32;
 constexpr int CP_BAR_FULL = 1, CP_BAR_EMPTY = 3, CP_BAR_COMPUTE = 5;   // FULL: 1,2  EMPTY: 3,4
 
-__global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams p) {
-  MRIACL_DYN_SMEM(cf, sm);
-  __shared__ FullBarrier full_bar[2];
-  const int tid = threadIdx.x;
-  const int n_items = p.n_frames * p.n_groups;
-  if (tid == 0) { full_init(&full_bar[0], 32); full_init(&full_bar[1], 32); }
-  __syncthreads();
+// Runs the items first, first + stride, ... (count of them) through the producer / consumer pipeline.
+// Called by CP_WS_T consecutive threads (tid 0 .. CP_WS_T-1) with two item buffers at `sm`.  uses[b] counts
+// how often buffer b has been filled since full_init (it selects the mbarrier phase), so the function can be
+// called again and again by a persistent CTA.
+__device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, FullBarrier* full_bar, int tid,
+                                               int first, int stride, int count, int* uses) {
   if (tid >= CP_T) {
     // ------------------------------ producer warp ------------------------------
     const int lane = tid - CP_T;
     const int k_ld = lane & 7, hs = lane >> 3;          // 8 columns x 4 rows per instruction
     const long long row_step = 4LL * p.W;
-    int k = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+    for (int k = 0; k < count; ++k) {
+      const int item = first + k * stride;
       const int buf = k & 1;
       if (k >= 2) named_bar_sync(CP_BAR_EMPTY + buf, CP_WS_T);   // buffer released by the compute warps
       const int fl = item / p.n_groups, g = item - fl * p.n_groups;
@@ -285,13 +284,14 @@ __global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams
     rr3[m3] = (rr >= 0 && rr < p.oh) ? rr : -1;
   }
 
-  int k = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+  for (int k = 0; k < count; ++k) {
+    const int item = first + k * stride;
     const int fl = item / p.n_groups, g = item - fl * p.n_groups;
     const int j0 = g * CP_G;
     const int ncols = min(CP_G, p.n_act - j0);
-    cf* cur = sm + (k & 1) * CP_BUF;
-    full_wait(&full_bar[k & 1], (k >> 1) & 1, CP_BAR_FULL + (k & 1), CP_WS_T);
+    const int buf = k & 1;
+    cf* cur = sm + buf * CP_BUF;
+    full_wait(&full_bar[buf], (uses[buf] + (k >> 1)) & 1, CP_BAR_FULL + buf, CP_WS_T);
 
     const int ncols_c = (p.debug_skip & 2) ? 0 : ncols;
     // ---- pass 1: radix-8 over n1 (stride 90), mask multiply, twiddle w640^{pos * m1}; two columns in flight ----
@@ -366,8 +366,20 @@ __global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams
       named_bar_sync(CP_BAR_COMPUTE, CP_T);
       if (tid == 0) atomicAdd(p.done + fl / (p.A * p.C), 1);
     }
-    if (item + 2 * (int)gridDim.x < n_items) named_bar_arrive(CP_BAR_EMPTY + (k & 1), CP_WS_T);   // producer may refill
+    if (k + 2 < count) named_bar_arrive(CP_BAR_EMPTY + buf, CP_WS_T);   // producer may refill
   }
+}
+
+__global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams p) {
+  MRIACL_DYN_SMEM(cf, sm);
+  __shared__ FullBarrier full_bar[2];
+  const int n_items = p.n_frames * p.n_groups;
+  if (threadIdx.x == 0) { full_init(&full_bar[0], 32); full_init(&full_bar[1], 32); }
+  __syncthreads();
+  int uses[2] = {0, 0};
+  const int first = blockIdx.x;
+  if (first < n_items)
+    colpass_ws_run(p, sm, full_bar, threadIdx.x, first, gridDim.x, (n_items - first + gridDim.x - 1) / gridDim.x, uses);
 }
 
 }  // namespace mriacl

@@ -18,6 +18,7 @@
 #include "colpass640.cuh"
 #include "rowpass.cuh"
 #include "rowpass16.cuh"
+#include "fused640x368.cuh"
 
 using namespace mriacl;
 
@@ -75,6 +76,7 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, ovl ? 100 : cp_carve);
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX, 100);
+  bad |= rt_allow_smem((const void*)fused640_kernel<FUSED_P, FUSED_Q>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
@@ -130,7 +132,8 @@ struct FusedPlanDev {
   FusedPlanHost host;            // schedule for RP_NW_SEQ warps
   FusedPlanHost host_ovl;        // schedule for RP_NW_OVL warps (same columns, same sptw)
   int* sched_ovl = nullptr;
-  std::vector<int> pairs12, pairs16;   // 16-row kernel: pair schedules for 12 and 16 warps
+  std::vector<int> pairs12, pairs16, pairs8;   // 16-row kernel: pair schedules for 12, 16 and 8 warps
+  int* sched_p8 = nullptr;
   std::vector<HostCf> sptw16;
   cf* sptw16_dev = nullptr;
   int* sched_p12 = nullptr;
@@ -192,6 +195,10 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
         rt_malloc(&s4, sizeof(int) * pl->pairs16.size()) || rt_upload(s4, pl->pairs16.data(), sizeof(int) * pl->pairs16.size()))
       return nullptr;
     pl->sched_p12 = (int*)s3; pl->sched_p16 = (int*)s4;
+    build_pair_schedule(pl->host, FZ_ROW_WARPS, pl->pairs8, pl->sptw16);
+    void* s5 = nullptr;
+    if (rt_malloc(&s5, sizeof(int) * pl->pairs8.size()) || rt_upload(s5, pl->pairs8.data(), sizeof(int) * pl->pairs8.size())) return nullptr;
+    pl->sched_p8 = (int*)s5;
     pl->act_w = (int*)a; pl->act_m = (float*)m; pl->sched = (int*)s; pl->sptw = (cf*)t;
     for (float v : h.act_m) if (v != 1.0f) pl->unit_mask = false;
     pl->twH = get_twiddles(dev, H, +1);
@@ -331,7 +338,14 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
   const bool do_norm = !only || (only & MRIACL_ONLY_NORM);
   // (the overlapped schedule is opt-in: see DESIGN.md for what it needs from the column-pass gather)
   static const bool overlap_env = env_int("MRIACL_OVERLAP", 0) != 0;
-  const bool overlap = overlap_env && !only && !(a.flags & MRIACL_SEQUENTIAL) && n_groups > 0;
+  // MRIACL_FUSED=1 (default on the device): the single persistent kernel of fused640x368.cuh
+#ifdef MRIACL_EMU
+  static const bool fused_env = env_int("MRIACL_FUSED", 0) != 0;
+#else
+  static const bool fused_env = env_int("MRIACL_FUSED", 1) != 0;
+#endif
+  const bool fused_mode = fused_env && !only && !(a.flags & MRIACL_SEQUENTIAL) && n_groups > 0;
+  const bool overlap = !fused_mode && overlap_env && !only && !(a.flags & MRIACL_SEQUENTIAL) && n_groups > 0;
 
   const FusedPlanHost& hp = overlap ? pl->host_ovl : pl->host;
   const int sched_len = (int)hp.sched.size(), sptw_len = (int)hp.sptw.size();
@@ -394,7 +408,32 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
     np.n_split = want_norm ? std::max(1, std::min(16, (int)(np.n / 8192))) : 1;
     const bool run_norm = (want_norm || a.mean_std) && do_norm;
 
-    if (!overlap) {
+    if (fused_mode) {
+      // one persistent launch: column items publish per-slice counters, row items are claimed when ready
+      if (rt_memset_async(counters, 0, 256 * (size_t)ns, a.st)) return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
+      FusedParams fp{};
+      fp.cp = cp; fp.cp.done = counters;
+      RowPass16Params& q = fp.rp;
+      q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+      q.sched = pl->sched_p8; q.sched_len = (int)pl->pairs8.size();
+      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size();
+      q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
+      q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
+      q.n_buf = 2;
+      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
+      if (smem16 > SMEM_MAX / 2) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
+      const int fz_smem = std::max(smem16, CP_SMEM_BYTES_DB);
+      if (fz_smem > SMEM_MAX / 2) return fail(MRIACL_ERR_UNSUPPORTED, "fused tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
+      fp.state = counters + ns;            // two ints after the per-slice counters (the region is 64 ints per slice)
+      fp.n_col_items = (int)col_items; fp.n_row_items = ns * g.n_tiles16;
+      static const int col_batch = std::max(1, env_int("MRIACL_FZ_COL_BATCH", 5));
+      fp.col_batch = col_batch; fp.done_target = a.A * a.C * n_groups;
+      np.n_part = g.n_tiles16;
+      const int work = (fp.n_col_items + col_batch - 1) / col_batch + fp.n_row_items;
+      auto kfn = fused640_kernel<FUSED_P, FUSED_Q>;
+      MRIACL_LAUNCH(kfn, std::min(work, 2 * a.sms), FZ_T, fz_smem, a.st, fp);
+      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, a.st, np);
+    } else if (!overlap) {
       if (n_groups > 0 && do_col) {
         // tuning knobs: MRIACL_CP_DB=0 single-buffer CTAs, MRIACL_CP_PER_SM=k persistent CTAs per SM (0 = one item per CTA)
         static const int cp_db = env_int("MRIACL_CP_DB", 1), cp_per_sm = env_int("MRIACL_CP_PER_SM", 2);

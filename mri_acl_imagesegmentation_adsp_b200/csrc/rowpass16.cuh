@@ -67,8 +67,30 @@ __device__ __forceinline__ void rp16_sparse_unit(const int* pay, const cf* tb, c
   }
 }
 
-template <int P, int Q, int NW, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Params p) {
+// shared-memory carve-up of one row-pass CTA
+template <int P, int Q> struct Rp16Smem {
+  cf* Y; cf* sptw; int* sch; cf* tbuf; float* av; float* osm;
+  __device__ __forceinline__ Rp16Smem(void* base, const RowPass16Params& p) {
+    constexpr int YS = (Q + 1) * RP16_ROWS;
+    Y = reinterpret_cast<cf*>(base);                                     // [P][Q + 1][16]
+    sptw = Y + P * YS;
+    sch = reinterpret_cast<int*>(reinterpret_cast<char*>(sptw) + rp_round16(p.sptw_len * 8));
+    tbuf = reinterpret_cast<cf*>(reinterpret_cast<char*>(sch) + rp_round16(p.sched_len * 4));   // [n_buf][n_act][16]
+    av = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * p.n_act * RP16_ROWS);
+    osm = reinterpret_cast<float*>(Y);                                   // output tile [16][ow+1], aliases Y
+  }
+};
+
+// copy the plan tables into shared memory (all NT threads; followed by a barrier at the caller)
+template <int NT> __device__ __forceinline__ void rp16_load_tables(const RowPass16Params& p, cf* sptwsm, int* schsm, int tid) {
+  for (int i = tid; i < p.sched_len; i += NT) schsm[i] = p.sched[i];
+  for (int i = tid; i < p.sptw_len; i += NT) sptwsm[i] = p.sptw[i];
+}
+
+// one work item = (slice, 16-row tile); called by all NW*32 threads of the (sub-)CTA; tables already loaded
+template <int P, int Q, int NW>
+__device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* smem_base, int item, int tid,
+                                               float* red, int* ready_flag) {
   static_assert(Q == 16, "stage 2 is the register-level 16-point FFT");
   constexpr int N = P * Q;
   constexpr int NT = NW * 32;
@@ -78,41 +100,35 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
   // dense residues are shared by three warps-halves: output pairs [1, B1) (+ X0), [B1, B2), [B2, HP]
   constexpr int B1 = 1 + HP / 3, B2 = B1 + (HP - HP / 3 + 1) / 2;
   constexpr int YS = (Q + 1) * RP16_ROWS;            // residue column Q is a write-only spare for idle half-warps
-  MRIACL_DYN_SMEM(cf, Y);                            // [P][Q + 1][16]
-  cf* sptwsm = Y + P * YS;
-  int* schsm = reinterpret_cast<int*>(reinterpret_cast<char*>(sptwsm) + rp_round16(p.sptw_len * 8));
-  cf* tbuf = reinterpret_cast<cf*>(reinterpret_cast<char*>(schsm) + rp_round16(p.sched_len * 4));   // [n_buf][n_act][16]
-  float* avsm = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * p.n_act * RP16_ROWS);
-  float* osm = reinterpret_cast<float*>(Y);          // output tile [16][ow+1], aliases Y
-  __shared__ float red[NW];
-  __shared__ int ready;
+  Rp16Smem<P, Q> S(smem_base, p);
+  cf* Y = S.Y; cf* sptwsm = S.sptw; int* schsm = S.sch; cf* tbuf = S.tbuf; float* avsm = S.av; float* osm = S.osm;
+  int& ready = *ready_flag;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = tid & 31, warp = tid >> 5;
   const int half = lane >> 4, r = lane & 15;
   const int opitch = p.ow + 1;
-  for (int i = tid; i < p.sched_len; i += NT) schsm[i] = p.sched[i];
-  for (int i = tid; i < p.sptw_len; i += NT) sptwsm[i] = p.sptw[i];
-  __syncthreads();
-
   const int my_off = schsm[warp];
-  const int n_items = p.n_slices * p.n_tiles;
   const int n_frames = p.A * p.C;
   const long long frame_elems = (long long)p.n_act * p.ohp;
   const int tile_elems = p.n_act * RP16_ROWS;
   const int n_copies = p.n_act * (RP16_ROWS / 2);    // 16-byte copies per block (8 per column)
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  {
+
     const int s = item / p.n_tiles, tile = item - s * p.n_tiles;
     const cf* Tit = p.T + (long long)s * n_frames * frame_elems + tile * RP16_ROWS;
 
     const cf* src0 = Tit + (long long)(tid >> 3) * p.ohp + 2 * (tid & 7);
     cf* dst0 = tbuf + (tid >> 3) * RP16_ROWS + 2 * (tid & 7);
+    const long long src_step = (long long)(NT / 8) * p.ohp;
+    const int n_iter = tid < n_copies ? (n_copies - tid + NT - 1) / NT : 0;
     auto prefetch = [&](int f, int buf) {
       const cf* src = src0 + (long long)f * frame_elems;
       cf* dst = dst0 + (size_t)buf * tile_elems;
-      for (int i = tid; i < n_copies; i += NT) {
+#pragma unroll 1
+      for (int i = 0; i < n_iter; ++i) {
         cp_async16(dst, src);
-        src += (long long)(NT / 8) * p.ohp;
+        src += src_step;
         dst += (NT / 8) * RP16_ROWS;
       }
       cp_async_commit();
@@ -272,6 +288,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
     }
     __syncthreads();
   }
+}
+
+template <int P, int Q, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Params p) {
+  MRIACL_DYN_SMEM(cf, smem);
+  __shared__ float red[NW];
+  __shared__ int ready;
+  Rp16Smem<P, Q> S(smem, p);
+  rp16_load_tables<NW * 32>(p, S.sptw, S.sch, threadIdx.x);
+  __syncthreads();
+  const int n_items = p.n_slices * p.n_tiles;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+    rowpass16_item<P, Q, NW>(p, smem, item, threadIdx.x, red, &ready);
 }
 
 }  // namespace mriacl

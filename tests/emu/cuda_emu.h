@@ -156,6 +156,7 @@ static inline double atomicAdd(double* p, double v) {
 }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return reinterpret_cast<std::atomic<unsigned>*>(p)->fetch_add(v); }
 static inline int atomicAdd(int* p, int v) { return reinterpret_cast<std::atomic<int>*>(p)->fetch_add(v); }
+static inline int atomicCAS(int* p, int cmp, int val) { reinterpret_cast<std::atomic<int>*>(p)->compare_exchange_strong(cmp, val); return cmp; }
 
 static inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
