@@ -25,6 +25,7 @@ struct FusedParams {
   int n_col_items, n_row_items;
   int col_batch;           // column items claimed at a time
   int done_target;         // column items per slice
+  int row_ctas_first;      // which half of the grid prefers row items (tuning)
 };
 
 __device__ __forceinline__ int fz_ld(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -39,22 +40,28 @@ __global__ void __launch_bounds__(FZ_T, 2) fused640_kernel(FusedParams p) {
   if (tid == 0) { full_init(&full_bar[0], 32); full_init(&full_bar[1], 32); }
   __syncthreads();
   int uses[2] = {0, 0};
+  const bool prefer_row = p.row_ctas_first ? blockIdx.x < gridDim.x / 2 : blockIdx.x >= gridDim.x / 2;
 
   while (true) {
     if (tid == 0) {
       int kind = FZ_IDLE, first = 0, count = 0;
-      const int r = fz_ld(p.state + 1);
-      if (r < p.n_row_items) {
-        if (fz_ld(p.cp.done + r / p.rp.n_tiles) >= p.done_target) {
-          if (atomicCAS(p.state + 1, r, r + 1) == r) { kind = FZ_ROW; first = r; __threadfence(); }
-        }
-        if (kind == FZ_IDLE && fz_ld(p.state) < p.n_col_items) {
-          const int c = atomicAdd(p.state, p.col_batch);
-          if (c < p.n_col_items) { kind = FZ_COL; first = c; count = min(p.col_batch, p.n_col_items - c); }
-        }
-      } else {
-        kind = FZ_EXIT;      // every row item has an owner; column items were all claimed long before
-      }
+      auto try_row = [&]() {
+        const int r = fz_ld(p.state + 1);
+        if (r >= p.n_row_items) return;
+        if (fz_ld(p.cp.done + r / p.rp.n_tiles) < p.done_target) return;
+        if (atomicCAS(p.state + 1, r, r + 1) == r) { kind = FZ_ROW; first = r; __threadfence(); }
+      };
+      auto try_col = [&]() {
+        if (fz_ld(p.state) >= p.n_col_items) return;
+        const int c = atomicAdd(p.state, p.col_batch);
+        if (c < p.n_col_items) { kind = FZ_COL; first = c; count = min(p.col_batch, p.n_col_items - c); }
+      };
+      // Static role preference keeps a steady mix on the chip (and on every SM): the first wave of CTAs streams
+      // columns, the second wave transforms rows; each falls back to the other kind of work when its own queue
+      // is empty or not ready yet, so nobody idles while there is work and nobody ever waits for anybody.
+      if (prefer_row) { try_row(); if (kind == FZ_IDLE) try_col(); }
+      else            { try_col(); if (kind == FZ_IDLE) try_row(); }
+      if (kind == FZ_IDLE && fz_ld(p.state + 1) >= p.n_row_items) kind = FZ_EXIT;
       s_kind = kind; s_first = first; s_count = count;
     }
     __syncthreads();

@@ -428,6 +428,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       fp.n_col_items = (int)col_items; fp.n_row_items = ns * g.n_tiles16;
       static const int col_batch = std::max(1, env_int("MRIACL_FZ_COL_BATCH", 5));
       fp.col_batch = col_batch; fp.done_target = a.A * a.C * n_groups;
+      fp.row_ctas_first = env_int("MRIACL_FZ_ROW_FIRST", 0);
       np.n_part = g.n_tiles16;
       const int work = (fp.n_col_items + col_batch - 1) / col_batch + fp.n_row_items;
       auto kfn = fused640_kernel<FUSED_P, FUSED_Q>;
