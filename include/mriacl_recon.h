@@ -45,8 +45,11 @@ extern "C" {
 #define MRIACL_FLIP_ROWS      0x1u  /* np.flipud of each combined image (ZIP!/fastmri_prostate/reconstruction/t2/prostate_t2_recon.py:101) */
 #define MRIACL_NORM_INSTANCE  0x2u  /* (x-mean)/(std+eps), unbiased std (ZIP!/DL_reconstruction/data/transforms.py:143-162) */
 #define MRIACL_FORCE_GENERIC  0x4u  /* testing: use the generic (any-size) kernels even where a fused plan exists */
-#define MRIACL_SEQUENTIAL     0x8u  /* fused plan: run column pass, row pass, normalise back to back on the caller's
-                                       stream instead of the overlapped two-stream schedule */
+/* kernel schedule of the fused 640x368 plan (default: MRIACL_SEQUENTIAL unless the environment variable
+ * MRIACL_SCHEDULE=fused|overlapped says otherwise; all three produce identical images) */
+#define MRIACL_SEQUENTIAL     0x8u   /* column pass -> row pass -> normalise, back to back on the caller's stream */
+#define MRIACL_SCHED_FUSED    0x10u  /* experimental: one persistent kernel, CTAs switch between column and row items */
+#define MRIACL_SCHED_OVERLAP  0x20u  /* experimental: persistent row pass on a side stream fed by per-slice counters */
 /* profiling only (bench.py's per-kernel timing): run just the named phase(s) of the fused plan;
  * none set = the whole stage.  The workspace must still hold the previous phase's output. */
 #define MRIACL_ONLY_COLPASS   0x100u

@@ -70,10 +70,9 @@ int ensure_smem_attrs(int dev) {
   int bad = 0;
   bad |= rt_allow_smem((const void*)generic_fft_kernel, GEN_SMEM_BYTES);
   const int cp_carve = env_int("MRIACL_CP_CARVEOUT", -1);
-  const int ovl = env_int("MRIACL_OVERLAP", 0);
   bad |= rt_allow_smem((const void*)colpass640_kernel<true>, CP_SMEM_BYTES_DB, cp_carve);
   bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB, cp_carve);
-  bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, ovl ? 100 : cp_carve);
+  bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, 100);   // co-resident with rowpass<8>: same carveout
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX, 100);
   bad |= rt_allow_smem((const void*)fused640_kernel<FUSED_P, FUSED_Q>, SMEM_MAX / 2);
@@ -336,16 +335,21 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
   const bool do_col = !only || (only & MRIACL_ONLY_COLPASS);
   const bool do_row = !only || (only & MRIACL_ONLY_ROWPASS);
   const bool do_norm = !only || (only & MRIACL_ONLY_NORM);
-  // (the overlapped schedule is opt-in: see DESIGN.md for what it needs from the column-pass gather)
-  static const bool overlap_env = env_int("MRIACL_OVERLAP", 0) != 0;
-  // MRIACL_FUSED=1 (default on the device): the single persistent kernel of fused640x368.cuh
-#ifdef MRIACL_EMU
-  static const bool fused_env = env_int("MRIACL_FUSED", 0) != 0;
-#else
-  static const bool fused_env = env_int("MRIACL_FUSED", 1) != 0;
-#endif
-  const bool fused_mode = fused_env && !only && !(a.flags & MRIACL_SEQUENTIAL) && n_groups > 0;
-  const bool overlap = !fused_mode && overlap_env && !only && !(a.flags & MRIACL_SEQUENTIAL) && n_groups > 0;
+  // schedule: flags win, then MRIACL_SCHEDULE=sequential|fused|overlapped, default sequential (the fastest measured;
+  // DESIGN.md section 4.5 has the numbers for the two experimental schedules)
+  static const int sched_env = [] {
+    const char* e = getenv("MRIACL_SCHEDULE");
+    if (e && !strcmp(e, "fused")) return 1;
+    if (e && !strcmp(e, "overlapped")) return 2;
+    return 0;
+  }();
+  int sched = sched_env;
+  if (a.flags & MRIACL_SEQUENTIAL) sched = 0;
+  else if (a.flags & MRIACL_SCHED_FUSED) sched = 1;
+  else if (a.flags & MRIACL_SCHED_OVERLAP) sched = 2;
+  if (only || n_groups == 0) sched = 0;
+  const bool fused_mode = sched == 1;
+  const bool overlap = sched == 2;
 
   const FusedPlanHost& hp = overlap ? pl->host_ovl : pl->host;
   const int sched_len = (int)hp.sched.size(), sptw_len = (int)hp.sptw.size();

@@ -30,7 +30,8 @@ def _crop_start(n: int, out: int) -> int:
 def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int]] = (320, 320),
                     normalize: Optional[str] = "instance", eps: float = 0.0, flip_rows: bool = False,
                     average_axis: Optional[int] = None, pad: Optional[Tuple[int, int]] = None,
-                    *, chunk_slices: Optional[int] = None, force_generic: bool = False, sequential: bool = False):
+                    *, chunk_slices: Optional[int] = None, force_generic: bool = False, sequential: bool = False,
+                    schedule: Optional[str] = None):
     """k-space -> cropped (normalised) RSS magnitude images.
 
     kspace   complex64 ``(C,H,W)``, ``(S,C,H,W)`` or, with ``average_axis`` 0 or 1,
@@ -44,8 +45,8 @@ def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int
     flip_rows  ``np.flipud`` of every combined image (prostate chain).
     average_axis  mean of the per-average RSS images (after the coil combine).
     pad      ``(left, right)`` zero-padding of the W axis before the transform.
-    chunk_slices / sequential / force_generic  tuning and testing knobs: slices the workspace holds,
-             back-to-back instead of overlapped kernel schedule, generic instead of fused kernels.
+    chunk_slices / schedule / force_generic  tuning and testing knobs: slices the workspace holds, kernel
+             schedule of the fused plan ("sequential" default, "fused", "overlapped"), generic kernels.
 
     Returns ``(image, mean, std)``: image float32 ``(S,oh,ow)`` (``(oh,ow)`` for a single slice),
     mean/std float32 ``(S,)`` (0-d for a single slice) of the un-normalised crop.  Types follow
@@ -83,6 +84,11 @@ def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int
     m = D.host_mask(mask, W)
     flags = (cabi.NORM_INSTANCE if normalize == "instance" else 0) | (cabi.FLIP_ROWS if flip_rows else 0) \
         | (cabi.FORCE_GENERIC if force_generic else 0) | (cabi.SEQUENTIAL if sequential else 0)
+    if schedule is not None:
+        try:
+            flags |= {"sequential": cabi.SEQUENTIAL, "fused": cabi.SCHED_FUSED, "overlapped": cabi.SCHED_OVERLAP}[schedule]
+        except KeyError:
+            raise ValueError(f"schedule must be sequential, fused or overlapped, got {schedule!r}") from None
 
     lib = D.lib()
     out = torch.empty((S, oh, ow), dtype=torch.float32, device=k.device)

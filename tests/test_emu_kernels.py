@@ -115,6 +115,19 @@ def test_fused_variants(emu):
     assert O.rel_l2(out, gen) <= TOL
 
 
+def test_fused_schedules_agree(emu):
+    """the persistent fused kernel (dynamic claiming of column / row items) and the overlapped schedule's kernels
+    produce the same bits as the sequential schedule (the emulator runs the launches one after another)."""
+    k = synth.gaussian_kspace((2, 1, 3, 640, 368), 17)
+    m = synth.knee_mask()
+    ref, _ = recon(emu, k, m, (320, 320), cabi.SEQUENTIAL)
+    for flag in (cabi.SCHED_FUSED, cabi.SCHED_OVERLAP):
+        out, _ = recon(emu, k, m, (320, 320), flag)
+        np.testing.assert_array_equal(out, ref)
+        out1, _ = recon(emu, k, m, (320, 320), flag, chunk=1)
+        np.testing.assert_array_equal(out1, ref)
+
+
 def test_fused_single_coil_full(emu, golden):
     k = synth.gaussian_kspace((640, 368), 1)
     out = np.zeros((1, 640, 368), np.float32)

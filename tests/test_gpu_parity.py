@@ -124,29 +124,33 @@ def test_mask_and_crop_indexing_bit_exact():
     c1, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=1)
     assert torch.equal(c1, raw)
     # the overlapped (two-stream) and the back-to-back kernel schedules do the same arithmetic
-    seq, _, _ = zero_filled_rss(k, m, synth.CROP, None, sequential=True)
-    assert torch.equal(seq, raw)
+    for schedule in ("sequential", "fused", "overlapped"):
+        alt, _, _ = zero_filled_rss(k, m, synth.CROP, None, schedule=schedule)
+        assert torch.equal(alt, raw), schedule
 
 
-def test_overlapped_schedule_many_groups():
-    """batch larger than the workspace: groups alternate between two intermediate buffers."""
+@pytest.mark.parametrize("schedule", ["fused", "overlapped"])
+def test_experimental_schedules_many_groups(schedule):
+    """the persistent-kernel schedules (dynamic work claiming, per-slice counters, side stream) give the same
+    images as the back-to-back one, also when the batch is larger than the workspace (two alternating buffers)."""
     g = torch.Generator(device="cuda").manual_seed(3)
     k = torch.view_as_complex(torch.randn((13, 15, 640, 368, 2), device="cuda", generator=g))
     m = synth.knee_mask()
-    ref, _, _ = zero_filled_rss(k, m, synth.CROP, None, sequential=True, chunk_slices=13)
-    nref, rmean, rstd = zero_filled_rss(k, m, synth.CROP, "instance", sequential=True, chunk_slices=13)
+    ref, _, _ = zero_filled_rss(k, m, synth.CROP, None, schedule="sequential", chunk_slices=13)
+    nref, rmean, rstd = zero_filled_rss(k, m, synth.CROP, "instance", schedule="sequential", chunk_slices=13)
     for chunk in (13, 6, 4, 2, 1):
-        out, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=chunk)
+        out, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=chunk, schedule=schedule)
         assert torch.equal(out, ref), chunk            # same arithmetic, bit for bit
-        nout, mean, std = zero_filled_rss(k, m, synth.CROP, "instance", chunk_slices=chunk)
-        # (the tile statistics are reduced over 8 instead of 16 warps: last-bit differences only)
+        nout, mean, std = zero_filled_rss(k, m, synth.CROP, "instance", chunk_slices=chunk, schedule=schedule)
+        # (tile statistics are reduced over a different number of warps / tiles: last-bit differences only)
         torch.testing.assert_close(nout, nref, rtol=0, atol=2e-6)
         torch.testing.assert_close(mean, rmean, rtol=1e-6, atol=0)
         torch.testing.assert_close(std, rstd, rtol=1e-6, atol=0)
-    # repeated calls reuse counters, events and the side stream
-    for _ in range(5):
-        out, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=5)
+    for _ in range(5):      # repeated calls reuse counters, events and the side stream
+        out, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=5, schedule=schedule)
     assert torch.equal(out, ref)
+    with pytest.raises(ValueError):
+        zero_filled_rss(k, m, synth.CROP, None, schedule="bogus")
 
 
 def test_fused_variants_against_oracle():
