@@ -221,6 +221,7 @@ def ours(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MRIACL_NCCL_DEBUG", "WARN")   # no version banner on stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = cabi.library()
     B = args.batch
