@@ -71,12 +71,12 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)generic_fft_kernel, GEN_SMEM_BYTES);
   const int cp_carve = env_int("MRIACL_CP_CARVEOUT", -1);
   bad |= rt_allow_smem((const void*)colpass640_kernel<true>, CP_SMEM_BYTES_DB, cp_carve);
-  bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB, cp_carve);
+  bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB, cp_carve < 0 ? 86 : cp_carve);   // 196 KB: fits 2 CTAs, or 1 + a row-pass CTA
   bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, 100);   // co-resident with rowpass<8>: same carveout
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX, 100);
   bad |= rt_allow_smem((const void*)fused640_kernel<FUSED_P, FUSED_Q>, SMEM_MAX / 2);
-  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2, 86);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
   if (!bad) d.smem_set = true;
@@ -494,18 +494,35 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
           rt_stream_wait_event(ov->side, ov->ev_start[wb]))
         return fail(MRIACL_ERR_CUDA, "overlap setup failed: %s", rt_last_error_string());
       cp.done = counters;
-      rp.done = counters; rp.done_target = a.A * a.C * n_groups; rp.error_flag = ov->error_flag;
-      // the row pass goes first so that it is resident (one CTA per SM) when the column-pass CTAs arrive
-      auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>;
+      // row pass: the 16-row kernel, one 12-warp CTA per SM, spinning on the per-slice counters; column pass: the
+      // warp-specialised kernel, one (or MRIACL_OVL_COL_PER_SM) persistent CTA per SM beside it
+      RowPass16Params q{};
+      q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+      q.sched = pl->sched_p12; q.sched_len = (int)pl->pairs12.size();
+      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size();
+      q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
+      q.n_slices = ns; q.n_tiles = g.n_tiles16;
+      q.done = counters; q.done_target = a.A * a.C * n_groups; q.error_flag = ov->error_flag;
+      q.n_buf = 2;
+      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
+      if (smem16 > SMEM_MAX / 2) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
+      if (smem16 > SMEM_MAX / 2) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
+      np.n_part = g.n_tiles16;
+      const int items16 = ns * g.n_tiles16;
+      static const int reserve = std::max(0, env_int("MRIACL_OVL_RESERVE_SMS", 4));
+      static const int row_per_sm = std::max(1, env_int("MRIACL_OVL_ROW_PER_SM", 1));
+      static const int col_per_sm = std::max(1, env_int("MRIACL_OVL_COL_PER_SM", 1));
+      const int row_grid = std::min(items16, std::max(1, (a.sms - reserve) * row_per_sm));
+      const int col_grid = (int)std::min<long long>(col_items, (long long)a.sms * col_per_sm);
+      auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>;
 #ifdef MRIACL_EMU   // the emulator runs launches one after another: producer first
-      MRIACL_LAUNCH(colpass640_kernel<false>, (int)col_items, CP_T, CP_SMEM_BYTES_SB, a.st, cp);
-      MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_OVL * 32, rp_smem, ov->side, rp);
+      MRIACL_LAUNCH(colpass640_ws_kernel, col_grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+      MRIACL_LAUNCH(kfn, row_grid, 12 * 32, smem16, ov->side, q);
 #else
-      // a few SMs are left without a row-pass CTA: the column pass can always make progress there, whatever
-      // the block scheduler decides about co-residency on the others
-      static const int reserve = std::max(0, env_int("MRIACL_OVL_RESERVE_SMS", 8));
-      MRIACL_LAUNCH(kfn, std::min(row_items, std::max(1, a.sms - reserve)), RP_NW_OVL * 32, rp_smem, ov->side, rp);
-      MRIACL_LAUNCH(colpass640_kernel<false>, (int)col_items, CP_T, CP_SMEM_BYTES_SB, a.st, cp);
+      // the row pass goes first so that its CTAs are resident when the column-pass CTAs arrive; a few SMs are
+      // left without a row-pass CTA, so the column pass can always make progress whatever the block scheduler does
+      MRIACL_LAUNCH(kfn, row_grid, 12 * 32, smem16, ov->side, q);
+      MRIACL_LAUNCH(colpass640_ws_kernel, col_grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
 #endif
       if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, ov->side, np);
       if (rt_event_record(ov->ev_row[wb], ov->side)) return fail(MRIACL_ERR_CUDA, "event record failed");
