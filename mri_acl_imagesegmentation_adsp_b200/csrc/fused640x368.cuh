@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(FZ_T, 2) fused640_kernel(FusedParams p) {
       uses[1] += count >> 1;
     } else if (kind == FZ_ROW) {
       Rp16Smem<P, Q> S(sm, p.rp);
-      rp16_load_tables<FZ_T>(p.rp, S.sptw, S.sch, tid);
+      rp16_load_tables<FZ_T>(p.rp, S.sptw, S.sch, S.tbuf, tid);
       __syncthreads();
       rowpass16_item<P, Q, FZ_ROW_WARPS>(p.rp, sm, first, tid, red, &s_ready);
     } else {

@@ -166,43 +166,59 @@ struct NormParams {
   int normalize;
 };
 
-// grid = B * n_split: block (b, part) normalises its 1/n_split share of image b (every block
-// re-derives the statistics: from the partials that is a handful of FMAs).
-__global__ void __launch_bounds__(512) normalize_instance_kernel(NormParams p) {
+// grid = B * n_split: block (b, part) normalises its 1/n_split share of image b.  With partials the statistics
+// are merged by one thread and broadcast (a handful of FMAs); the share is then streamed with 128-bit accesses.
+__global__ void __launch_bounds__(256) normalize_instance_kernel(NormParams p) {
   __shared__ double red[33];
+  __shared__ float s_mean, s_std;
   const int b = blockIdx.x / p.n_split, part = blockIdx.x - b * p.n_split;
   const float* x = p.in + (long long)b * p.n;
-  double mean, m2;
   if (p.partials) {
-    // every thread merges the same few triples; cheap and avoids a broadcast
-    double cnt = 0.0; mean = 0.0; m2 = 0.0;
-    for (int t = 0; t < p.n_part; ++t) {
-      const float* q = p.partials + ((long long)b * p.n_part + t) * 3;
-      const double nb = q[0], mb = q[1], sb = q[2];
-      if (nb > 0.0) {
-        const double d = mb - mean, tot = cnt + nb;
-        mean += d * nb / tot;
-        m2 += sb + d * d * cnt * nb / tot;
-        cnt = tot;
+    if (threadIdx.x == 0) {
+      double cnt = 0.0, mean = 0.0, m2 = 0.0;
+      for (int t = 0; t < p.n_part; ++t) {
+        const float* q = p.partials + ((long long)b * p.n_part + t) * 3;
+        const double nb = q[0], mb = q[1], sb = q[2];
+        if (nb > 0.0) {
+          const double d = mb - mean, tot = cnt + nb;
+          mean += d * nb / tot;
+          m2 += sb + d * d * cnt * nb / tot;
+          cnt = tot;
+        }
       }
+      s_mean = (float)mean;
+      s_std = (float)sqrt(m2 / (double)(p.n - 1));
     }
+    __syncthreads();
   } else {
     double s = 0.0;
     for (long long i = threadIdx.x; i < p.n; i += blockDim.x) s += (double)x[i];
-    mean = block_sum_double(s, red) / (double)p.n;
+    const double mean = block_sum_double(s, red) / (double)p.n;
     double q = 0.0;
     for (long long i = threadIdx.x; i < p.n; i += blockDim.x) { const double d = (double)x[i] - mean; q += d * d; }
-    m2 = block_sum_double(q, red);
+    const double m2 = block_sum_double(q, red);
+    if (threadIdx.x == 0) { s_mean = (float)mean; s_std = (float)sqrt(m2 / (double)(p.n - 1)); }
+    __syncthreads();
   }
-  const float fmean = (float)mean;
-  const float fstd = (float)sqrt(m2 / (double)(p.n - 1));
+  const float fmean = s_mean, fstd = s_std;
   if (threadIdx.x == 0 && part == 0 && p.mean_std) { p.mean_std[2 * b] = fmean; p.mean_std[2 * b + 1] = fstd; }
   if (p.normalize && p.out) {
     float* y = p.out + (long long)b * p.n;
     const float den = fstd + p.eps;
     const long long per = (p.n + p.n_split - 1) / p.n_split;
     const long long lo = part * per, hi = lo + per < p.n ? lo + per : p.n;
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) y[i] = (x[i] - fmean) / den;
+    const bool vec = ((p.n | lo | hi) & 3) == 0 && ((((unsigned long long)x) | ((unsigned long long)y)) & 15) == 0;
+    if (vec) {
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      float4* y4 = reinterpret_cast<float4*>(y);
+      for (long long i = lo / 4 + threadIdx.x; i < hi / 4; i += blockDim.x) {
+        float4 v = x4[i];
+        v.x = (v.x - fmean) / den; v.y = (v.y - fmean) / den; v.z = (v.z - fmean) / den; v.w = (v.w - fmean) / den;
+        y4[i] = v;
+      }
+    } else {
+      for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) y[i] = (x[i] - fmean) / den;
+    }
   }
 }
 

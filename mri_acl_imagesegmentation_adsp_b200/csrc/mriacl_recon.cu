@@ -437,7 +437,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       const int work = (fp.n_col_items + col_batch - 1) / col_batch + fp.n_row_items;
       auto kfn = fused640_kernel<FUSED_P, FUSED_Q>;
       MRIACL_LAUNCH(kfn, std::min(work, 2 * a.sms), FZ_T, fz_smem, a.st, fp);
-      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, a.st, np);
+      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
     } else if (!overlap) {
       if (n_groups > 0 && do_col) {
         // tuning knobs: MRIACL_CP_DB=0 single-buffer CTAs, MRIACL_CP_PER_SM=k persistent CTAs per SM (0 = one item per CTA)
@@ -486,7 +486,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         }
       }
       if (rp16_cfg != 0 && !do_row) np.n_part = g.n_tiles16;
-      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, a.st, np);
+      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
     } else {
       // T buffer wb: its previous reader (row pass of group - n_bufs_ws) must be done
       if (group >= n_bufs_ws && rt_stream_wait_event(a.st, ov->ev_row[wb])) return fail(MRIACL_ERR_CUDA, "stream wait failed");
@@ -524,7 +524,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       MRIACL_LAUNCH(kfn, row_grid, 12 * 32, smem16, ov->side, q);
       MRIACL_LAUNCH(colpass640_ws_kernel, col_grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
 #endif
-      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 512, 0, ov->side, np);
+      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, ov->side, np);
       if (rt_event_record(ov->ev_row[wb], ov->side)) return fail(MRIACL_ERR_CUDA, "event record failed");
     }
   }
@@ -614,7 +614,7 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
         NormParams np{};
         np.in = rc.out; np.out = rc.out; np.mean_std = mean_std ? mean_std + 2 * (size_t)s0 : nullptr;
         np.partials = nullptr; np.n_part = 0; np.n_split = 1; np.n = (long long)oh * ow; np.eps = eps; np.normalize = want_norm ? 1 : 0;
-        MRIACL_LAUNCH(normalize_instance_kernel, ns, 512, 0, st, np);
+        MRIACL_LAUNCH(normalize_instance_kernel, ns, 256, 0, st, np);
       }
     }
   }
@@ -691,7 +691,7 @@ int mriacl_normalize_instance_f32(const float* in, float* out, float* mean_std, 
   NormParams np{};
   np.in = in; np.out = out; np.mean_std = mean_std; np.partials = nullptr; np.n_part = 0; np.n_split = 1;
   np.n = (long long)n; np.eps = eps; np.normalize = 1;
-  MRIACL_LAUNCH(normalize_instance_kernel, B, 512, 0, (rt_stream_t)cuda_stream, np);
+  MRIACL_LAUNCH(normalize_instance_kernel, B, 256, 0, (rt_stream_t)cuda_stream, np);
   if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
   return MRIACL_OK;
 }

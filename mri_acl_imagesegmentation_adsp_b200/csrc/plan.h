@@ -150,7 +150,7 @@ inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow,
 // same kind (dense piece type / sparse nnz) side by side.
 //   sched[w], w < n_warps   offset of warp w's list
 //   list: n_pairs, then per pair: type, nnz, offA, offB   (offB = -1: second half-warp idles)
-//   unit payload at offA / offB: n2, then  dense: twiddle-row offset, P column indices (or -1);
+//   unit payload at offA / offB: n2, then  dense: twiddle-row offset, P column indices (n_act = the zero column);
 //                                          sparse: twiddle-row offset, nnz column indices
 //   sptw16 = the sparse twiddle rows followed by one row w_N^{n2 k1} per dense residue
 //   an idle second half-warp (offB = -1) repeats unit A but stores into the spare residue column n2 = Q
@@ -235,8 +235,13 @@ inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vecto
     if (unit_off[pu.second] < 0) {
       unit_off[pu.second] = (int)out.size();
       out.push_back(units[pu.second].n2);
-      if (units[pu.second].type != 0) out.push_back(dense_row[units[pu.second].n2]);
-      out.insert(out.end(), units[pu.second].payload.begin(), units[pu.second].payload.end());
+      if (units[pu.second].type != 0) {
+        out.push_back(dense_row[units[pu.second].n2]);
+        // unsampled positions of a dense residue read the all-zero column n_act of the staged block
+        for (int j : units[pu.second].payload) out.push_back(j >= 0 ? j : (int)pl.act_w.size());
+      } else {
+        out.insert(out.end(), units[pu.second].payload.begin(), units[pu.second].payload.end());
+      }
     }
     out[pu.first] = unit_off[pu.second];
   }

@@ -40,7 +40,7 @@ struct RowPass16Params {
 
 inline int rowpass16_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_act, int n_buf, int ow, int A) {
   return P * (Q + 1) * RP16_ROWS * 8 + rp_round16(sptw_len * 8) + rp_round16(sched_len * 4) +
-         n_buf * n_act * RP16_ROWS * 8 + (A > 1 ? RP16_ROWS * (ow + 1) * 4 : 0);
+         n_buf * (n_act + 1) * RP16_ROWS * 8 + (A > 1 ? RP16_ROWS * (ow + 1) * 4 : 0);
 }
 
 template <int P, int Q, int NNZ>
@@ -75,16 +75,18 @@ template <int P, int Q> struct Rp16Smem {
     Y = reinterpret_cast<cf*>(base);                                     // [P][Q + 1][16]
     sptw = Y + P * YS;
     sch = reinterpret_cast<int*>(reinterpret_cast<char*>(sptw) + rp_round16(p.sptw_len * 8));
-    tbuf = reinterpret_cast<cf*>(reinterpret_cast<char*>(sch) + rp_round16(p.sched_len * 4));   // [n_buf][n_act][16]
-    av = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * p.n_act * RP16_ROWS);
+    tbuf = reinterpret_cast<cf*>(reinterpret_cast<char*>(sch) + rp_round16(p.sched_len * 4));   // [n_buf][n_act + 1][16], last column zero
+    av = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * (p.n_act + 1) * RP16_ROWS);
     osm = reinterpret_cast<float*>(Y);                                   // output tile [16][ow+1], aliases Y
   }
 };
 
 // copy the plan tables into shared memory (all NT threads; followed by a barrier at the caller)
-template <int NT> __device__ __forceinline__ void rp16_load_tables(const RowPass16Params& p, cf* sptwsm, int* schsm, int tid) {
+template <int NT> __device__ __forceinline__ void rp16_load_tables(const RowPass16Params& p, cf* sptwsm, int* schsm, cf* tbuf, int tid) {
   for (int i = tid; i < p.sched_len; i += NT) schsm[i] = p.sched[i];
   for (int i = tid; i < p.sptw_len; i += NT) sptwsm[i] = p.sptw[i];
+  if (tid < p.n_buf * RP16_ROWS)       // the zero column of every staging buffer
+    tbuf[((size_t)(tid / RP16_ROWS) * (p.n_act + 1) + p.n_act) * RP16_ROWS + tid % RP16_ROWS] = cf_make(0.f, 0.f);
 }
 
 // one work item = (slice, 16-row tile); called by all NW*32 threads of the (sub-)CTA; tables already loaded
@@ -110,7 +112,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
   const int my_off = schsm[warp];
   const int n_frames = p.A * p.C;
   const long long frame_elems = (long long)p.n_act * p.ohp;
-  const int tile_elems = p.n_act * RP16_ROWS;
+  const int tile_elems = (p.n_act + 1) * RP16_ROWS;
   const int n_copies = p.n_act * (RP16_ROWS / 2);    // 16-byte copies per block (8 per column)
 
   {
@@ -177,8 +179,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
             cf x[P];
 #pragma unroll
             for (int n1 = 0; n1 < P; ++n1) {
-              const int j = pay[2 + n1];
-              x[n1] = j >= 0 ? tb[j * RP16_ROWS] : cf_make(0.f, 0.f);
+              x[n1] = tb[pay[2 + n1] * RP16_ROWS];
             }
             const cf* dtw = sptwsm + pay[1];
             auto emit = [&](auto kc, cf val) {
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Param
   __shared__ float red[NW];
   __shared__ int ready;
   Rp16Smem<P, Q> S(smem, p);
-  rp16_load_tables<NW * 32>(p, S.sptw, S.sch, threadIdx.x);
+  rp16_load_tables<NW * 32>(p, S.sptw, S.sch, S.tbuf, threadIdx.x);
   __syncthreads();
   const int n_items = p.n_slices * p.n_tiles;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x)
