@@ -71,12 +71,12 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)generic_fft_kernel, GEN_SMEM_BYTES);
   const int cp_carve = env_int("MRIACL_CP_CARVEOUT", -1);
   bad |= rt_allow_smem((const void*)colpass640_kernel<true>, CP_SMEM_BYTES_DB, cp_carve);
-  bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB, cp_carve < 0 ? 86 : cp_carve);   // 196 KB: fits 2 CTAs, or 1 + a row-pass CTA
+  bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB, cp_carve);   // default carveout: 2 CTAs -> 196 KB, 60 KB of L1 left for the gather
   bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, 100);   // co-resident with rowpass<8>: same carveout
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX, 100);
   bad |= rt_allow_smem((const void*)fused640_kernel<FUSED_P, FUSED_Q>, SMEM_MAX / 2);
-  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2, 86);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
   if (!bad) d.smem_set = true;
