@@ -35,32 +35,31 @@ template <bool INV> __device__ __forceinline__ void radix8(cf* v) {
   // even / odd 4-point transforms
   radix4<INV>(v[0], v[2], v[4], v[6]);   // E[0..3] in v[0],v[2],v[4],v[6]
   radix4<INV>(v[1], v[3], v[5], v[7]);   // O[0..3] in v[1],v[3],v[5],v[7]
-  // O[m] * w8^m
+  // X[m], X[m+4] = E[m] +- O[m] w8^m with w8 = (1 +- i)/sqrt 2:  O1 w8 = c (O1 +- i O1),  O3 w8^3 = c (+-i O3 - O3);
+  // the scale c rides on the final packed FMA
   const float c = MRIACL_SQRT1_2;
-  cf o0 = v[1];
-  cf o1 = INV ? cf_make(c * (v[3].x - v[3].y), c * (v[3].x + v[3].y))
-              : cf_make(c * (v[3].x + v[3].y), c * (v[3].y - v[3].x));
-  cf o2 = mul_i<INV>(v[5]);
-  cf o3 = INV ? cf_make(-c * (v[7].x + v[7].y), c * (v[7].x - v[7].y))
-              : cf_make(c * (v[7].y - v[7].x), -c * (v[7].x + v[7].y));
-  cf e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  const cf o0 = v[1];
+  const cf t1 = cadd(v[3], mul_i<INV>(v[3]));
+  const cf o2 = mul_i<INV>(v[5]);
+  const cf t3 = csub(mul_i<INV>(v[7]), v[7]);
+  const cf e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
   v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
-  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[1] = pk_fma(t1, bc(c), e1); v[5] = pk_fma(t1, bc(-c), e1);
   v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
-  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+  v[3] = pk_fma(t3, bc(c), e3); v[7] = pk_fma(t3, bc(-c), e3);
 }
 
 // 5-point DFT in place
 template <bool INV> __device__ __forceinline__ void radix5(cf& a0, cf& a1, cf& a2, cf& a3, cf& a4) {
   constexpr float c1 = DftConsts<5>::c(1), c2 = DftConsts<5>::c(2);
   constexpr float s1 = DftConsts<5>::s(1), s2 = DftConsts<5>::s(2);
-  cf p1 = cadd(a1, a4), p2 = cadd(a2, a3), d1 = csub(a1, a4), d2 = csub(a2, a3);
-  cf r1 = cf_make(fmaf(c2, p2.x, fmaf(c1, p1.x, a0.x)), fmaf(c2, p2.y, fmaf(c1, p1.y, a0.y)));
-  cf r2 = cf_make(fmaf(c1, p2.x, fmaf(c2, p1.x, a0.x)), fmaf(c1, p2.y, fmaf(c2, p1.y, a0.y)));
-  cf i1 = cf_make(fmaf(s2, d2.x, s1 * d1.x), fmaf(s2, d2.y, s1 * d1.y));
-  cf i2 = cf_make(fmaf(-s1, d2.x, s2 * d1.x), fmaf(-s1, d2.y, s2 * d1.y));
+  const cf p1 = cadd(a1, a4), p2 = cadd(a2, a3), d1 = csub(a1, a4), d2 = csub(a2, a3);
+  const cf r1 = pk_fma(p2, bc(c2), pk_fma(p1, bc(c1), a0));
+  const cf r2 = pk_fma(p2, bc(c1), pk_fma(p1, bc(c2), a0));
+  const cf i1 = pk_fma(d2, bc(s2), pk_mul(d1, bc(s1)));
+  const cf i2 = pk_fma(d2, bc(-s1), pk_mul(d1, bc(s2)));
   a0 = cadd(a0, cadd(p1, p2));
-  cf j1 = mul_i<INV>(i1), j2 = mul_i<INV>(i2);
+  const cf j1 = mul_i<INV>(i1), j2 = mul_i<INV>(i2);
   a1 = cadd(r1, j1); a4 = csub(r1, j1);
   a2 = cadd(r2, j2); a3 = csub(r2, j2);
 }
@@ -80,8 +79,7 @@ template <bool INV> __device__ __forceinline__ void radix10(cf* v) {
                              -0.30901699437494742410f, -0.80901699437494742410f};
     constexpr float sw[5] = {0.0f, 0.58778525229247312917f, 0.95105651629515357212f,
                              0.95105651629515357212f, 0.58778525229247312917f};
-    cf w = cf_make(cw[m], INV ? sw[m] : -sw[m]);
-    o[m] = cmul(v[2 * m + 1], w);
+    o[m] = cmul_k(v[2 * m + 1], cw[m], INV ? sw[m] : -sw[m]);
   });
   static_for<5>([&](auto mm) {
     constexpr int m = mm.value;
@@ -104,8 +102,10 @@ template <bool INV> __device__ __forceinline__ void fft16(cf* v) {
     static_for<3>([&](auto cc) {
       constexpr int c = cc.value + 1;
       constexpr int e = b * c;  // 1..9
-      cf w = cf_make(cw[e], INV ? sw[e] : -sw[e]);
-      v[4 * c + b] = cmul(v[4 * c + b], w);
+      constexpr float wc = cw[e], ws = INV ? sw[e] : -sw[e];
+      if constexpr (wc == 0.f) v[4 * c + b] = cscale(mul_i<true>(v[4 * c + b]), ws);                 // +-i
+      else if constexpr (wc == ws) v[4 * c + b] = cscale(cadd(v[4 * c + b], mul_i<true>(v[4 * c + b])), wc);
+      else v[4 * c + b] = cmul_k(v[4 * c + b], wc, ws);
     });
   });
   // step 3: for each c, 4-point DFT over b of v[4c + b] -> X[c + 4d] at v[4c + d]
@@ -145,18 +145,17 @@ __device__ __forceinline__ void dft_odd_sym_part(const cf* x, Emit&& emit) {
   }
   static_for<KHI - KLO>([&](auto kk) {
     constexpr int k = kk.value + KLO;
-    float ar = x0.x, ai = x0.y, br = 0.f, bi = 0.f;
+    cf A = x0, B = cf_make(0.f, 0.f);
     static_for<Hh>([&](auto nn) {
       constexpr int n = nn.value + 1;
       constexpr float c = DftConsts<P>::c((n * k) % P);
       constexpr float s = DftConsts<P>::s((n * k) % P);
-      ar = fmaf(a[n - 1].x, c, ar);
-      ai = fmaf(a[n - 1].y, c, ai);
-      br = fmaf(b[n - 1].x, s, br);
-      bi = fmaf(b[n - 1].y, s, bi);
+      A = pk_fma(a[n - 1], bc(c), A);
+      B = nn.value == 0 ? pk_mul(b[n - 1], bc(s)) : pk_fma(b[n - 1], bc(s), B);
     });
     // A + iB and A - iB
-    cf plus = cf_make(ar - bi, ai + br), minus = cf_make(ar + bi, ai - br);
+    const cf iB = mul_i<true>(B);
+    const cf plus = cadd(A, iB), minus = csub(A, iB);
     emit(std::integral_constant<int, k>{}, INV ? plus : minus);
     emit(std::integral_constant<int, P - k>{}, INV ? minus : plus);
   });

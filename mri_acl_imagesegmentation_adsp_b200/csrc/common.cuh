@@ -18,23 +18,49 @@ namespace mriacl {
 typedef float2 cf;  // complex64: x = re, y = im
 
 __device__ __forceinline__ cf cf_make(float re, float im) { return make_float2(re, im); }
-__device__ __forceinline__ cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ cf cmul(cf a, cf b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
-// a * conj(b)
-__device__ __forceinline__ cf cmulc(cf a, cf b) {
-  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
-}
-__device__ __forceinline__ cf cscale(cf a, float s) { return make_float2(a.x * s, a.y * s); }
-// multiply by +i (INV) or -i (!INV)
+
+// ---- packed fp32x2 arithmetic -------------------------------------------------------------------
+// sm_100a has two-wide fp32 instructions (FFMA2 / FADD2 / FMUL2 in SASS, fma/add/mul.rn.f32x2 in PTX)
+// that work on an aligned register PAIR -- exactly one complex64.  They run at half the issue rate of the
+// scalar forms (same flops per clock, measured: tools/microbench/fp32x2_tput.cu) but need half the issue
+// slots, and their operand modifiers make the usual complex idioms free: a scalar register broadcast to
+// both halves (x, x), an immediate broadcast, and the half-swap with one negation, i.e. multiplication
+// by +-i.  Every butterfly below is written on these three primitives so that the FFT passes, which are
+// bound by instruction issue, execute about half as many instructions as with scalar FFMA/FADD.
+#if defined(MRIACL_EMU)
+__device__ __forceinline__ cf pk_add(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cf pk_mul(cf a, cf b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ cf pk_fma(cf a, cf b, cf c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#else
+__device__ __forceinline__ cf pk_add(cf a, cf b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ cf pk_mul(cf a, cf b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ cf pk_fma(cf a, cf b, cf c) { return __ffma2_rn(a, b, c); }
+#endif
+__device__ __forceinline__ cf bc(float s) { return make_float2(s, s); }            // broadcast operand
+__device__ __forceinline__ cf cneg(cf a) { return make_float2(-a.x, -a.y); }       // folds into a modifier
+__device__ __forceinline__ cf cadd(cf a, cf b) { return pk_add(a, b); }
+__device__ __forceinline__ cf csub(cf a, cf b) { return pk_add(a, cneg(b)); }
+// multiply by +i (INV) or -i (!INV): a half-swap with one sign flip, folded into the consumer's operand
 template <bool INV> __device__ __forceinline__ cf mul_i(cf a) {
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
+// a * b for two variable operands: (a.x, a.x) * b + (a.y, a.y) * (i b)
+// (ptxas folds the swap-and-negate into the FIRST multiplicand only, so the rotated operand goes first)
+__device__ __forceinline__ cf cmul(cf a, cf b) { return pk_fma(mul_i<true>(b), bc(a.y), pk_mul(b, bc(a.x))); }
+// a * conj(b)
+__device__ __forceinline__ cf cmulc(cf a, cf b) {
+  return pk_fma(mul_i<false>(b), bc(-a.y), pk_mul(make_float2(b.x, -b.y), bc(a.x)));
+}
+// a * (c + i s) for constants c, s (immediates after inlining): c a + s (i a)
+__device__ __forceinline__ cf cmul_k(cf a, float c, float s) { return pk_fma(mul_i<true>(a), bc(s), pk_mul(a, bc(c))); }
+// acc + a * (c + i s)
+__device__ __forceinline__ cf cmac_k(cf a, float c, float s, cf acc) { return pk_fma(mul_i<true>(a), bc(s), pk_fma(a, bc(c), acc)); }
+__device__ __forceinline__ cf cscale(cf a, float s) { return pk_mul(a, bc(s)); }
 __device__ __forceinline__ float cnorm2(cf a) { return fmaf(a.x, a.x, a.y * a.y); }
 // acc + |a|^2
 __device__ __forceinline__ float cnorm2_acc(cf a, float acc) { return fmaf(a.x, a.x, fmaf(a.y, a.y, acc)); }
+// packed form: acc.x += re^2, acc.y += im^2 (the two halves are summed once, after the coil loop)
+__device__ __forceinline__ cf cnorm2_acc2(cf a, cf acc) { return pk_fma(a, a, acc); }
 
 // Streaming 8-byte global load: k-space is read exactly once, keep it out of L1.
 __device__ __forceinline__ cf ld_stream(const cf* p) {

@@ -18,6 +18,7 @@
 #include "colpass640.cuh"
 #include "rowpass.cuh"
 #include "rowpass16.cuh"
+#include "rowpair.cuh"
 #include "fused640x368.cuh"
 
 using namespace mriacl;
@@ -58,6 +59,9 @@ constexpr int SMEM_MAX = 227 * 1024 - 512;     // dynamic shared memory a B200 C
 // Row-pass CTA shapes: 16 warps (one CTA owns the SM) for the sequential schedule, 8 warps for the
 // overlapped schedule, where one row-pass CTA shares each SM with column-pass CTAs.
 constexpr int RP_NW_SEQ = 16, RP_NW_OVL = 8;
+// Pair row pass (rowpair.cuh): dense residues every RPP_STEP-th, at most RPP_NE extra columns per other residue.
+// That is the 4x-equispaced + low-frequency-block mask family; other masks keep the cooperative row pass.
+constexpr int RPP_STEP = 4, RPP_NE = 2;
 
 
 
@@ -79,6 +83,8 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 1>, SMEM_MAX / 2);
+  bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 2>, SMEM_MAX / 2);
   if (!bad) d.smem_set = true;
   return bad;
 }
@@ -137,6 +143,10 @@ struct FusedPlanDev {
   cf* sptw16_dev = nullptr;
   int* sched_p12 = nullptr;
   int* sched_p16 = nullptr;
+  RowPairPlanHost rpp;             // pair row pass (ok = the mask fits its template)
+  int* rpp_slot = nullptr;
+  int* rpp_zero = nullptr;
+  float* rpp_tab = nullptr;
   std::vector<float> mask_copy;
   bool has_mask = false;
   int* act_w = nullptr;
@@ -198,6 +208,17 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     void* s5 = nullptr;
     if (rt_malloc(&s5, sizeof(int) * pl->pairs8.size()) || rt_upload(s5, pl->pairs8.data(), sizeof(int) * pl->pairs8.size())) return nullptr;
     pl->sched_p8 = (int*)s5;
+    build_rowpair_plan(pl->host, RPP_STEP, RPP_NE, pl->rpp);
+    if (pl->rpp.ok) {
+      void *q1 = nullptr, *q2 = nullptr, *q3 = nullptr;
+      const RowPairPlanHost& r = pl->rpp;
+      if (rt_malloc(&q1, sizeof(int) * r.slot_of_j.size()) || rt_malloc(&q2, sizeof(int) * (r.zero_slots.size() + 1)) ||
+          rt_malloc(&q3, sizeof(float) * r.tables.size())) return nullptr;
+      if ((!r.slot_of_j.empty() && rt_upload(q1, r.slot_of_j.data(), sizeof(int) * r.slot_of_j.size())) ||
+          (!r.zero_slots.empty() && rt_upload(q2, r.zero_slots.data(), sizeof(int) * r.zero_slots.size())) ||
+          rt_upload(q3, r.tables.data(), sizeof(float) * r.tables.size())) return nullptr;
+      pl->rpp_slot = (int*)q1; pl->rpp_zero = (int*)q2; pl->rpp_tab = (float*)q3;
+    }
     pl->act_w = (int*)a; pl->act_m = (float*)m; pl->sched = (int*)s; pl->sptw = (cf*)t;
     for (float v : h.act_m) if (v != 1.0f) pl->unit_mask = false;
     pl->twH = get_twiddles(dev, H, +1);
@@ -341,13 +362,17 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
     const char* e = getenv("MRIACL_SCHEDULE");
     if (e && !strcmp(e, "fused")) return 1;
     if (e && !strcmp(e, "overlapped")) return 2;
+    if (e && !strcmp(e, "pair")) return 3;
     return 0;
   }();
   int sched = sched_env;
   if (a.flags & MRIACL_SEQUENTIAL) sched = 0;
   else if (a.flags & MRIACL_SCHED_FUSED) sched = 1;
   else if (a.flags & MRIACL_SCHED_OVERLAP) sched = 2;
-  if (only || n_groups == 0) sched = 0;
+  else if (a.flags & MRIACL_SCHED_PAIR) sched = 3;
+  if (n_groups == 0 || (only && sched != 3)) sched = 0;
+  if (sched == 3 && (a.A != 1 || !pl->rpp.ok)) sched = 0;      // the pair row pass serves single-average plans of its mask family
+  const bool pair_rows = sched == 3;
   const bool fused_mode = sched == 1;
   const bool overlap = sched == 2;
 
@@ -455,7 +480,29 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
           MRIACL_LAUNCH(colpass640_kernel<false>, grid, CP_T, CP_SMEM_BYTES_SB, a.st, cp);
         }
       }
-      if (do_row && rp16_cfg == 0) {
+      if (do_row && pair_rows) {
+        using L = RowPairLayout<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>;
+        RowPairParams q{};
+        q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+        q.slot_of_j = pl->rpp_slot; q.zero_slots = pl->rpp_zero; q.n_zero = (int)pl->rpp.zero_slots.size();
+        q.tables = pl->rpp_tab; q.n_slots = L::N_SLOTS;
+        q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.C = a.C; q.scale = rp.scale;
+        q.n_slices = ns; q.n_tiles = g.n_tiles16;
+        static const int rpp_buf = std::min(3, std::max(2, env_int("MRIACL_RPP_BUF", 3)));
+        q.n_buf = rpp_buf;
+        const int smem = L::smem_bytes(q.n_buf, n_act, q.n_zero);
+        if (smem > SMEM_MAX / 2 || RPP_ROWS * (a.ow + 1) * 4 > L::ACC_BYTES)
+          return fail(MRIACL_ERR_UNSUPPORTED, "pair row pass does not fit shared memory (n_act=%d ow=%d)", n_act, a.ow);
+        np.n_part = g.n_tiles16;
+        static const int rpp_minb = env_int("MRIACL_RPP_MINB", 2);
+        if (rpp_minb == 2) {
+          auto kfn = rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 2>;
+          MRIACL_LAUNCH(kfn, std::min(ns * g.n_tiles16, 2 * a.sms), RPP_TT, smem, a.st, q);
+        } else {
+          auto kfn = rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 1>;
+          MRIACL_LAUNCH(kfn, std::min(ns * g.n_tiles16, a.sms), RPP_TT, smem, a.st, q);
+        }
+      } else if (do_row && rp16_cfg == 0) {
         auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>;
         MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_SEQ * 32, rp_smem, a.st, rp);
       } else if (do_row) {
@@ -485,7 +532,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
           MRIACL_LAUNCH(kfn, std::min(items16, a.sms), 16 * 32, smem16, a.st, q);
         }
       }
-      if (rp16_cfg != 0 && !do_row) np.n_part = g.n_tiles16;
+      if ((rp16_cfg != 0 || pair_rows) && !do_row) np.n_part = g.n_tiles16;
       if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
     } else {
       // T buffer wb: its previous reader (row pass of group - n_bufs_ws) must be done

@@ -247,6 +247,93 @@ inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vecto
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Plan of the pair row pass (rowpair.cuh).  The staged tile is residue-major:
+//   slot (n2 / step) * P + n1                 for the dense residues n2 = 0 mod step (unsampled positions stay zero),
+//   nd * P + si * ne + e                      entry e of the si-th sparse residue (absent entries stay zero).
+// The logical index may be rotated by `shift` (n' = n - shift mod N) so that the dense residues are the multiples of
+// `step`; a rotation multiplies X[k] by a unit phase and the path only keeps magnitudes.
+// Tables (float): coef[12][hp] (cos, sin)(2 pi n pair / P) | dtw[nd][12] (w_N^{n2 k1a}, w_N^{n2 k1b})
+//                 | sptw[(Q - nd) * ne][12] (w_N^{n' k1a}, w_N^{n' k1b}),  k1a = pair, k1b = (P - pair) mod P.
+// ---------------------------------------------------------------------------------------
+struct RowPairPlanHost {
+  bool ok = false;
+  int step = 0, ne = 0, nd = 0, n_slots = 0, shift = 0;
+  std::vector<int> slot_of_j;
+  std::vector<int> zero_slots;     // dense-region slots without a column
+  std::vector<float> tables;
+};
+
+inline void build_rowpair_plan(const FusedPlanHost& pl, int step, int ne, RowPairPlanHost& rp) {
+  const int P = pl.P, Q = pl.Q, N = P * Q, hp = (P - 1) / 2, n_pair = (P + 1) / 2;
+  rp = RowPairPlanHost();
+  rp.step = step; rp.ne = ne;
+  if (Q % step != 0 || N != pl.Wp || step < 2) return;
+  const int nd = Q / step, nsp = Q - nd, n_act = (int)pl.act_w.size();
+  rp.nd = nd; rp.n_slots = nd * P + nsp * ne;
+  std::vector<int> logical(n_act);
+  for (int j = 0; j < n_act; ++j) {
+    int n = pl.act_w[j] + pl.pad_left - pl.Wp / 2;     // physical (padded) -> logical: inverse of the ifftshift
+    if (n < 0) n += pl.Wp;
+    logical[j] = n;
+  }
+  const double two_pi = 6.283185307179586476925286766559;
+  auto tw = [&](long long e) {            // w_N^e, exact on the axes
+    e %= N; if (e < 0) e += N;
+    double c = std::cos(two_pi * (double)e / N), s = std::sin(two_pi * (double)e / N);
+    if ((4 * e) % N == 0) { const int q = (int)((4 * e) / N); c = (q == 0) ? 1.0 : (q == 2) ? -1.0 : 0.0; s = (q == 1) ? 1.0 : (q == 3) ? -1.0 : 0.0; }
+    return HostCf{(float)c, (float)s};
+  };
+  for (int shift = 0; shift < step && !rp.ok; ++shift) {
+    std::vector<int> cnt(Q, 0), slot(n_act, -1), nprime(n_act, 0);
+    std::vector<char> used(rp.n_slots, 0);
+    bool fits = true;
+    for (int j = 0; j < n_act && fits; ++j) {
+      int np = logical[j] - shift; if (np < 0) np += N;
+      nprime[j] = np;
+      const int n1 = np / Q, n2 = np % Q;
+      if (n2 % step == 0) slot[j] = (n2 / step) * P + n1;
+      else {
+        const int si = n2 - n2 / step - 1;             // index among the non-multiples of step
+        if (cnt[n2] >= ne) { fits = false; break; }
+        slot[j] = nd * P + si * ne + cnt[n2]++;
+      }
+      used[slot[j]] = 1;
+    }
+    if (!fits) continue;
+    rp.ok = true; rp.shift = shift; rp.slot_of_j = slot;
+    rp.zero_slots.clear();
+    for (int sl = 0; sl < nd * P; ++sl) if (!used[sl]) rp.zero_slots.push_back(sl);
+    rp.tables.assign((size_t)n_pair * hp * 2 + (size_t)nd * n_pair * 4 + (size_t)nsp * ne * n_pair * 4, 0.f);
+    float* coef = rp.tables.data();
+    float* dtw = coef + (size_t)n_pair * hp * 2;
+    float* sptw = dtw + (size_t)nd * n_pair * 4;
+    for (int pr = 0; pr < n_pair; ++pr) {
+      const int k1a = pr, k1b = (P - pr) % P;
+      for (int n = 1; n <= hp; ++n) {
+        const double ang = two_pi * (double)((n * pr) % P) / (double)P;
+        coef[(pr * hp + n - 1) * 2] = (float)std::cos(ang);
+        coef[(pr * hp + n - 1) * 2 + 1] = (float)std::sin(ang);
+      }
+      for (int d = 0; d < nd; ++d) {
+        const HostCf a = tw((long long)d * step * k1a), b = tw((long long)d * step * k1b);
+        float* q = dtw + ((size_t)d * n_pair + pr) * 4;
+        q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
+      }
+    }
+    for (int j = 0; j < n_act; ++j) {
+      if (slot[j] < nd * P) continue;
+      const int entry = slot[j] - nd * P;
+      for (int pr = 0; pr < n_pair; ++pr) {
+        const int k1a = pr, k1b = (P - pr) % P;
+        const HostCf a = tw((long long)nprime[j] * k1a), b = tw((long long)nprime[j] * k1b);
+        float* q = sptw + ((size_t)entry * n_pair + pr) * 4;
+        q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
+      }
+    }
+  }
+}
+
 // FNV-1a over the plan-defining inputs: cache key for device-resident plans
 inline uint64_t plan_key(const int* dims, int n_dims, const float* mask, int mask_len) {
   uint64_t h = 1469598103934665603ull;

@@ -53,17 +53,16 @@ __device__ __forceinline__ void rp16_sparse_unit(const int* pay, const cf* tb, c
   for (int e = 0; e < NNZ; ++e) xe[e] = tb[pay[2 + e] * RP16_ROWS];
 #pragma unroll
   for (int kp = 0; kp < PITCH / 2; ++kp) {
-    float re0 = 0.f, im0 = 0.f, re1 = 0.f, im1 = 0.f;
+    cf y0 = cf_make(0.f, 0.f), y1 = cf_make(0.f, 0.f);
 #pragma unroll
     for (int e = 0; e < NNZ; ++e) {
-      const float4 w = tw4[e * (PITCH / 2) + kp];
-      re0 = fmaf(xe[e].x, w.x, fmaf(-xe[e].y, w.y, re0));
-      im0 = fmaf(xe[e].x, w.y, fmaf(xe[e].y, w.x, im0));
-      re1 = fmaf(xe[e].x, w.z, fmaf(-xe[e].y, w.w, re1));
-      im1 = fmaf(xe[e].x, w.w, fmaf(xe[e].y, w.z, im1));
+      const float4 w = tw4[e * (PITCH / 2) + kp];       // twiddles of k1 = 2 kp and 2 kp + 1
+      const cf w0 = cf_make(w.x, w.y), w1 = cf_make(w.z, w.w);
+      y0 = pk_fma(mul_i<true>(w0), bc(xe[e].y), pk_fma(w0, bc(xe[e].x), y0));
+      y1 = pk_fma(mul_i<true>(w1), bc(xe[e].y), pk_fma(w1, bc(xe[e].x), y1));
     }
-    ycol[(2 * kp) * YS] = cf_make(re0, im0);
-    if (2 * kp + 1 < P) ycol[(2 * kp + 1) * YS] = cf_make(re1, im1);
+    ycol[(2 * kp) * YS] = y0;
+    if (2 * kp + 1 < P) ycol[(2 * kp + 1) * YS] = y1;
   }
 }
 

@@ -86,9 +86,10 @@ def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int
         | (cabi.FORCE_GENERIC if force_generic else 0) | (cabi.SEQUENTIAL if sequential else 0)
     if schedule is not None:
         try:
-            flags |= {"sequential": cabi.SEQUENTIAL, "fused": cabi.SCHED_FUSED, "overlapped": cabi.SCHED_OVERLAP}[schedule]
+            flags |= {"sequential": cabi.SEQUENTIAL, "fused": cabi.SCHED_FUSED, "overlapped": cabi.SCHED_OVERLAP,
+                      "pair": cabi.SCHED_PAIR}[schedule]
         except KeyError:
-            raise ValueError(f"schedule must be sequential, fused or overlapped, got {schedule!r}") from None
+            raise ValueError(f"schedule must be sequential, fused, overlapped or pair, got {schedule!r}") from None
 
     lib = D.lib()
     out = torch.empty((S, oh, ow), dtype=torch.float32, device=k.device)

@@ -153,6 +153,40 @@ def test_experimental_schedules_many_groups(schedule):
         zero_filled_rss(k, m, synth.CROP, None, schedule="bogus")
 
 
+def test_pair_row_pass_schedule():
+    """the pair row pass (rowpair.cuh) against the oracle (rel-L2 <= 1e-5) and the cooperative row pass; bit-stable
+    under chunking; masked columns never read; a mask offset that needs the index rotation; fallback outside its family."""
+    k_np = synth.gaussian_kspace((5,) + synth.KNEE_SHAPE, 51)
+    k = torch.from_numpy(k_np).cuda()
+    m = synth.knee_mask()
+    ref, _, _ = zero_filled_rss(k, m, synth.CROP, None, schedule="sequential")
+    out, _, _ = zero_filled_rss(k, m, synth.CROP, None, schedule="pair")
+    assert O.rel_l2(out.cpu().numpy(), ref.cpu().numpy()) <= 2e-6
+    want = O.knee_chain_numpy(k_np[3], m, synth.CROP, None)
+    want = want[0] if isinstance(want, tuple) else want
+    assert O.rel_l2(out[3].cpu().numpy(), want) <= TOL
+    for chunk in (1, 2, 5):
+        alt, _, _ = zero_filled_rss(k, m, synth.CROP, None, schedule="pair", chunk_slices=chunk)
+        assert torch.equal(alt, out), chunk
+    nout, mean, std = zero_filled_rss(k, m, synth.CROP, "instance", schedule="pair")
+    nref, rmean, rstd = zero_filled_rss(k, m, synth.CROP, "instance", schedule="sequential")
+    torch.testing.assert_close(nout, nref, rtol=0, atol=2e-5)
+    torch.testing.assert_close(mean, rmean, rtol=1e-5, atol=0)
+    torch.testing.assert_close(std, rstd, rtol=1e-5, atol=0)
+    k2 = k.clone()
+    k2[..., torch.from_numpy(m == 0).cuda()] = complex(1e30, -1e30)
+    alt, _, _ = zero_filled_rss(k2, m, synth.CROP, None, schedule="pair")
+    assert torch.equal(alt, out)
+    m2 = np.zeros(368, np.float32); m2[1::4] = 1.0; m2[180:190] = 0.5
+    a, _, _ = zero_filled_rss(k, m2, (77, 200), None, schedule="pair")
+    b, _, _ = zero_filled_rss(k, m2, (77, 200), None, schedule="sequential")
+    assert O.rel_l2(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6
+    m3 = np.zeros(368, np.float32); m3[0::4] = 1.0; m3[[1, 17, 33]] = 1.0
+    a, _, _ = zero_filled_rss(k, m3, synth.CROP, None, schedule="pair")
+    b, _, _ = zero_filled_rss(k, m3, synth.CROP, None, schedule="sequential")
+    assert torch.equal(a, b)
+
+
 def test_fused_variants_against_oracle():
     rng = np.random.default_rng(5)
     k = synth.gaussian_kspace((2, 2, 3, 640, 368), 7)       # (S, A, C, H, W)
