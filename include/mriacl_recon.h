@@ -49,6 +49,8 @@ extern "C" {
  * MRIACL_SCHEDULE=fused|overlapped says otherwise; all three produce identical images) */
 #define MRIACL_SEQUENTIAL     0x8u   /* column pass -> row pass -> normalise, back to back on the caller's stream */
 #define MRIACL_SCHED_FUSED    0x10u  /* experimental: one persistent kernel, CTAs switch between column and row items */
+#define MRIACL_SCHED_CORESIDENT 0x80u /* one persistent kernel, one CTA per SM: column team + row team co-resident, normalisation fused */
+#define MRIACL_SCHED_PIPELINED 0x800u /* sequential kernels on small chunks, two streams, T double-buffered in L2 (eviction hints) */
 #define MRIACL_SCHED_PAIR     0x40u  /* column pass -> pair row pass (rowpair.cuh: per-output-pair, barrier-free) -> normalise */
 #define MRIACL_SCHED_OVERLAP  0x20u  /* experimental: persistent row pass on a side stream fed by per-slice counters */
 /* profiling only (bench.py's per-kernel timing): run just the named phase(s) of the fused plan;

@@ -18,6 +18,8 @@ ABI_VERSION = 1
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
 FLIP_ROWS, NORM_INSTANCE, FORCE_GENERIC, SEQUENTIAL = 0x1, 0x2, 0x4, 0x8
 SCHED_FUSED, SCHED_OVERLAP = 0x10, 0x20    # experimental kernel schedules of the fused plan
+SCHED_CORESIDENT = 0x80                    # one persistent kernel: column team + row team on every SM, normalise fused
+SCHED_PIPELINED = 0x800                    # small chunks on two streams, T kept in L2
 SCHED_PAIR = 0x40                          # column pass -> pair row pass (rowpair.cuh) -> normalise
 ONLY_COLPASS, ONLY_ROWPASS, ONLY_NORM = 0x100, 0x200, 0x400   # profiling: single phases of the fused plan
 PATH_NONE, PATH_GENERIC, PATH_FUSED = 0, 1, 2

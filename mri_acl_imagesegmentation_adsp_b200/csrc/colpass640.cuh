@@ -53,6 +53,12 @@ struct ColPassParams {
   int* done;                     // optional [n_slices]: += 1 per finished item of the slice (row pass waits on it)
   int persist;                   // single-buffer variant: 1 = grid-stride over items, 0 = one item per CTA
   int debug_skip;                // profiling only: 1 = no gather, 2 = no arithmetic, 4 = no stores (results are garbage)
+  int l2_hints;                  // 1: k-space loads evict_first, T stores evict_last (chunk-pipelined schedule)
+  // co-resident schedule with a ring of T slots: slice s lives in slot s % ring, and its columns may only be written
+  // once every row tile of slice s - ring has been consumed (rows_done[s - ring] == rows_target); ring = 0: no ring
+  int ring;
+  const int* rows_done;
+  int rows_target;
 };
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): the gather needs one complex64 out of
@@ -63,6 +69,14 @@ __device__ __forceinline__ void cp_async8(cf* smem_dst, const cf* gsrc) {
 #else
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async8_hint(cf* smem_dst, const cf* gsrc, unsigned long long pol) {
+#if defined(MRIACL_EMU)
+  *smem_dst = *gsrc;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
 #endif
 }
 __device__ __forceinline__ void cp_async_commit_group() {
@@ -234,6 +248,7 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
     const int lane = tid - CP_T;
     const int k_ld = lane & 7, hs = lane >> 3;          // 8 columns x 4 rows per instruction
     const long long row_step = 4LL * p.W;
+    const unsigned long long pol = l2_policy_evict_first();
     for (int k = 0; k < count; ++k) {
       const int item = first + k * stride;
       const int buf = k & 1;
@@ -245,13 +260,25 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
       if (j0 + k_ld < p.n_act && !(p.debug_skip & 1)) {
         const cf* src = p.ksp + b * p.sb + a * p.sa + ((long long)c * CP_N + hs) * p.W + p.act_w[j0 + k_ld];
         cf* dst = sm + buf * CP_BUF + k_ld * CP_PITCH + hs;
+        if (p.l2_hints) {
 #pragma unroll 1
-        for (int blk = 0; blk < 8; ++blk) {
-          cf* d = dst + CP_BLK * ((blk + 4) & 7);
+          for (int blk = 0; blk < 8; ++blk) {
+            cf* d = dst + CP_BLK * ((blk + 4) & 7);
 #pragma unroll
-          for (int q = 0; q < 20; ++q) {
-            cp_async8(d + 4 * q, src);
-            src += row_step;
+            for (int q = 0; q < 20; ++q) {
+              cp_async8_hint(d + 4 * q, src, pol);
+              src += row_step;
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int blk = 0; blk < 8; ++blk) {
+            cf* d = dst + CP_BLK * ((blk + 4) & 7);
+#pragma unroll
+            for (int q = 0; q < 20; ++q) {
+              cp_async8(d + 4 * q, src);
+              src += row_step;
+            }
           }
         }
       }
@@ -284,6 +311,7 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
     rr3[m3] = (rr >= 0 && rr < p.oh) ? rr : -1;
   }
 
+  const unsigned long long pol_t = l2_policy_evict_last();
   for (int k = 0; k < count; ++k) {
     const int item = first + k * stride;
     const int fl = item / p.n_groups, g = item - fl * p.n_groups;
@@ -342,6 +370,15 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
     named_bar_sync(CP_BAR_COMPUTE, CP_T);
 
     // ---- pass 3: radix-10 over n3 (contiguous), crop/shift/flip on the way out ----
+    int t_frame = fl;
+    if (p.ring) {        // ring of T slots: wait until the slot's previous slice has been consumed by the row teams
+      const int fpf = p.A * p.C, sl = fl / fpf;
+      t_frame = (sl % p.ring) * fpf + (fl - sl * fpf);
+      if (sl >= p.ring) {
+        if (tid == 0) wait_count_ge(p.rows_done + (sl - p.ring), p.rows_target);
+        named_bar_sync(CP_BAR_COMPUTE, CP_T);
+      }
+    }
     if (tid < 128) {
       for (int kc = sub3; kc < ncols_c; kc += 2) {
         const float4* col4 = reinterpret_cast<const float4*>(cur + kc * CP_PITCH + base3);
@@ -353,8 +390,12 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
           v[2 * q + 1] = cf_make(t.z, t.w);
         }
         radix10<true>(v);
-        cf* dst = p.T + ((long long)fl * p.n_act + j0 + kc) * p.ohp;
-        if (!(p.debug_skip & 4)) {
+        cf* dst = p.T + ((long long)t_frame * p.n_act + j0 + kc) * p.ohp;
+        if (p.l2_hints) {
+#pragma unroll
+          for (int m3 = 0; m3 < 10; ++m3)
+            if (rr3[m3] >= 0) st_global_hint(dst + rr3[m3], v[m3], pol_t);
+        } else if (!(p.debug_skip & 4)) {
 #pragma unroll
           for (int m3 = 0; m3 < 10; ++m3)
             if (rr3[m3] >= 0) dst[rr3[m3]] = v[m3];

@@ -73,6 +73,36 @@ __device__ __forceinline__ cf ld_stream(const cf* p) {
 #endif
 }
 
+// ---- L2 eviction-priority hints --------------------------------------------------------------------------
+// k-space is read exactly once: its lines should be the first to leave L2 (evict_first).  The intermediate T is
+// written by the column pass and read back by the row pass a few hundred microseconds later, and its buffer is
+// reused chunk after chunk: its lines should stay (evict_last), so that T never makes the round trip through HBM.
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+#if defined(MRIACL_EMU)
+  return 0ull;
+#else
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+#endif
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+#if defined(MRIACL_EMU)
+  return 0ull;
+#else
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+#endif
+}
+__device__ __forceinline__ void st_global_hint(cf* p, cf v, unsigned long long pol) {
+#if defined(MRIACL_EMU)
+  *p = v;
+#else
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+#endif
+}
+
 // named barriers: `count` threads (a multiple of 32) take part; sync waits, arrive does not
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
 #if defined(MRIACL_EMU)
@@ -123,6 +153,25 @@ __device__ __forceinline__ void full_wait(FullBarrier* b, int parity, int emu_id
       "@p bra MRIACL_FULL_DONE_%=;\n\t"
       "bra MRIACL_FULL_WAIT_%=;\n\t"
       "MRIACL_FULL_DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+#endif
+}
+
+// one thread spins until *counter >= target (another team of this persistent kernel publishes it); bounded so that
+// a scheduling surprise cannot hang the device
+__device__ __forceinline__ bool wait_count_ge(const int* counter, int target) {
+#if defined(MRIACL_EMU)
+  for (int spin = 0; spin < 2000000; ++spin) {
+    if (reinterpret_cast<const std::atomic<int>*>(counter)->load() >= target) return true;
+    std::this_thread::yield();
+  }
+  return false;
+#else
+  const volatile int* c = counter;
+  for (int spin = 0; spin < (1 << 18); ++spin) {
+    if (*c >= target) { __threadfence(); return true; }
+    __nanosleep(100);
+  }
+  return false;
 #endif
 }
 

@@ -1,0 +1,116 @@
+// coresident640x368.cuh -- the whole knee plan as ONE persistent kernel with both passes resident on every SM.
+//
+// One CTA per SM, 18 warps:
+//   warps 0-5   column team  (colpass640.cuh: producer warp + 5 transform warps, two item buffers) -- streams
+//               k-space from HBM, writes the intermediate T and bumps a per-slice counter per finished item;
+//   warps 6-17  row team     (rowpass16.cuh, 12 warps on a named barrier) -- takes (slice, 16-row tile) items in
+//               slice order, waits until the slice's counter says every column group has landed, reads T back
+//               while it is still in L2, and writes the image tile.  The team that finishes the LAST tile of a
+//               slice also normalises the slice (mean / unbiased std from the tiles' (n, mean, M2) partials), so
+//               the stage needs no further launch.
+// Every CTA is resident (grid <= number of SMs, one CTA per SM by shared memory), column teams never wait for
+// anybody, and both kinds of items are taken in increasing slice order, so the waits cannot deadlock.  Compared
+// with two concurrent launches (the "overlapped" schedule) co-residency is guaranteed rather than hoped for: the
+// HBM-bound gather and the issue/latency-bound row transform share each SM's issue slots for the whole step.
+#pragma once
+#include "colpass640.cuh"
+#include "rowpass16.cuh"
+#include "rowpair.cuh"
+
+namespace mriacl {
+
+constexpr int KC_ROW_W = 12;
+constexpr int KC_ROW_T = KC_ROW_W * 32;
+constexpr int KC_T = CP_WS_T + KC_ROW_T;      // 576
+constexpr int KC_BAR_ROW = 6;                 // named barrier of the row team (the column team uses 1-5)
+
+struct CoresParams {
+  ColPassParams cp;          // cp.done = per-slice counters (zeroed before the launch)
+  RowPass16Params rp;        // rp.done = the same counters; rp.tiles_done / mean_std / eps / normalize: fused normalisation
+};
+
+template <int P, int Q>
+__global__ void __launch_bounds__(KC_T, 1) knee_coresident_kernel(CoresParams p) {
+  MRIACL_DYN_SMEM(unsigned char, smem);
+  __shared__ FullBarrier full_bar[2];
+  __shared__ float red[KC_ROW_W];
+  __shared__ float s_stat[2];
+  __shared__ int s_ready, s_last;
+  const int tid = threadIdx.x;
+  if (tid == 0) { full_init(&full_bar[0], 32); full_init(&full_bar[1], 32); }
+  __syncthreads();
+
+  if (tid < CP_WS_T) {
+    // ------------------------------ column team ------------------------------
+    const int n_items = p.cp.n_frames * p.cp.n_groups;
+    int uses[2] = {0, 0};
+    const int first = blockIdx.x;
+    if (first < n_items)
+      colpass_ws_run(p.cp, reinterpret_cast<cf*>(smem), full_bar, tid, first, gridDim.x,
+                     (n_items - first + gridDim.x - 1) / gridDim.x, uses);
+    return;
+  }
+
+  // ------------------------------ row team ------------------------------
+  const int t = tid - CP_WS_T;
+  unsigned char* rsm = smem + CP_SMEM_BYTES_DB;
+  const RowPass16Params& r = p.rp;
+  {
+    Rp16Smem<P, Q> S(rsm, r);
+    rp16_load_tables<KC_ROW_T>(r, S.sptw, S.sch, S.tbuf, t);
+  }
+  rp16_sync<KC_BAR_ROW, KC_ROW_T>();
+  const int n_items = r.n_slices * r.n_tiles;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    rowpass16_item<P, Q, KC_ROW_W, KC_BAR_ROW>(r, rsm, item, t, red, &s_ready);
+    if (r.done && !s_ready) return;                  // the wait for the slice timed out (error flag is set)
+    if (r.tiles_done) rowpass16_finish_slice<KC_ROW_W, KC_BAR_ROW>(r, item, t, s_stat, &s_last);
+  }
+}
+
+// ---- the same idea with the pair row pass (rowpair.cuh) as the row team: 6 compute warps + stager, no team-wide
+// barrier in the coil loop, so the row team needs fewer warps to keep its pipes busy: 13 warps per CTA in all.
+constexpr int KP_T = CP_WS_T + RPP_TT;        // 416
+constexpr int KP_BAR0 = 6;                    // row team: FULL 6-8 (emulator only), EMPTY 9-11, compute 12
+
+struct CoresPairParams {
+  ColPassParams cp;
+  RowPairParams rp;
+};
+
+template <int P, int Q, int STEP, int NE>
+__global__ void __launch_bounds__(KP_T, 1) knee_coresident_pair_kernel(CoresPairParams p) {
+  MRIACL_DYN_SMEM(unsigned char, smem);
+  __shared__ FullBarrier full_bar[2];
+  __shared__ FullBarrier row_full[3];
+  __shared__ float red[RPP_CW];
+  const int tid = threadIdx.x;
+  if (tid == 0) { full_init(&full_bar[0], 32); full_init(&full_bar[1], 32); }
+  if (tid >= 32 && tid < 35) full_init(&row_full[tid - 32], 32);
+  unsigned char* rsm = smem + CP_SMEM_BYTES_DB;
+  if (tid >= CP_WS_T) rowpair_setup<P, Q, STEP, NE>(p.rp, rsm, tid - CP_WS_T);
+  __syncthreads();
+
+  if (tid < CP_WS_T) {
+    const int n_items = p.cp.n_frames * p.cp.n_groups;
+    int uses[2] = {0, 0};
+    const int first = blockIdx.x;
+    if (first < n_items)
+      colpass_ws_run(p.cp, reinterpret_cast<cf*>(smem), full_bar, tid, first, gridDim.x,
+                     (n_items - first + gridDim.x - 1) / gridDim.x, uses);
+    return;
+  }
+  const int t = tid - CP_WS_T;
+  const int n_items = p.rp.n_slices * p.rp.n_tiles;
+  int k_stage = 0;
+  if (t < RPP_CT) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+      rowpair_compute_item<P, Q, STEP, NE>(p.rp, rsm, row_full, item, t, KP_BAR0, red, k_stage);
+  } else {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+      rowpair_stage_item<P, Q, STEP, NE>(p.rp, rsm, row_full, item, t - RPP_CT, KP_BAR0, k_stage);
+    cp_async_wait<0>();
+  }
+}
+
+}  // namespace mriacl

@@ -20,6 +20,7 @@
 #include "rowpass16.cuh"
 #include "rowpair.cuh"
 #include "fused640x368.cuh"
+#include "coresident640x368.cuh"
 
 using namespace mriacl;
 
@@ -83,6 +84,8 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)knee_coresident_kernel<FUSED_P, FUSED_Q>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)knee_coresident_pair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 1>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 2>, SMEM_MAX / 2);
   if (!bad) d.smem_set = true;
@@ -363,6 +366,8 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
     if (e && !strcmp(e, "fused")) return 1;
     if (e && !strcmp(e, "overlapped")) return 2;
     if (e && !strcmp(e, "pair")) return 3;
+    if (e && !strcmp(e, "coresident")) return 4;
+    if (e && !strcmp(e, "pipelined")) return 5;
     return 0;
   }();
   int sched = sched_env;
@@ -370,9 +375,15 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
   else if (a.flags & MRIACL_SCHED_FUSED) sched = 1;
   else if (a.flags & MRIACL_SCHED_OVERLAP) sched = 2;
   else if (a.flags & MRIACL_SCHED_PAIR) sched = 3;
+  else if (a.flags & MRIACL_SCHED_CORESIDENT) sched = 4;
+  else if (a.flags & MRIACL_SCHED_PIPELINED) sched = 5;
   if (n_groups == 0 || (only && sched != 3)) sched = 0;
   if (sched == 3 && (a.A != 1 || !pl->rpp.ok)) sched = 0;      // the pair row pass serves single-average plans of its mask family
   const bool pair_rows = sched == 3;
+  const bool coresident = sched == 4;
+  // pipelined: the sequential kernels on small chunks, column pass on the caller's stream and row pass + normalise on a
+  // side stream, two alternating T buffers that stay in L2 (eviction hints), kernel tails filled by the other stream
+  const bool pipelined = sched == 5 && !only;
   const bool fused_mode = sched == 1;
   const bool overlap = sched == 2;
 
@@ -389,10 +400,16 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
   const size_t cap_slices = a.workspace_bytes / g.per_slice;
   OverlapRes* ov = nullptr;
   int chunk, n_bufs_ws;
-  if (overlap) {
+  if (overlap || coresident || pipelined) {
     ov = get_overlap_res(a.dev, a.st);
     if (!ov) return fail(MRIACL_ERR_CUDA, "side stream / event creation failed: %s", rt_last_error_string());
-    if (cap_slices >= (size_t)a.B) { chunk = a.B; n_bufs_ws = 1; }
+    static const int pipe_chunk = std::max(1, env_int("MRIACL_PIPE_CHUNK", 8));
+    if (coresident) { chunk = (int)std::min<size_t>((size_t)a.B, cap_slices); n_bufs_ws = 1; }
+    else if (pipelined) {
+      if (cap_slices >= 2) { chunk = (int)std::min<size_t>({(size_t)a.B, (size_t)pipe_chunk, cap_slices / 2}); n_bufs_ws = 2; }
+      else { chunk = 1; n_bufs_ws = 1; }
+    }
+    else if (cap_slices >= (size_t)a.B) { chunk = a.B; n_bufs_ws = 1; }
     else if (cap_slices >= 2) { chunk = (int)(cap_slices / 2); n_bufs_ws = 2; }
     else { chunk = 1; n_bufs_ws = 1; }
   } else {
@@ -437,7 +454,74 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
     np.n_split = want_norm ? std::max(1, std::min(16, (int)(np.n / 8192))) : 1;
     const bool run_norm = (want_norm || a.mean_std) && do_norm;
 
-    if (fused_mode) {
+    static const int kc_pair = env_int("MRIACL_KC_PAIR", 1);      // co-resident schedule: pair row team when the mask allows
+    if (coresident && kc_pair && a.A == 1 && pl->rpp.ok) {
+      using L = RowPairLayout<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>;
+      if (rt_memset_async(counters, 0, 256 * (size_t)ns, a.st)) return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
+      CoresPairParams kp{};
+      kp.cp = cp; kp.cp.done = counters;
+      RowPairParams& q = kp.rp;
+      q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+      q.slot_of_j = pl->rpp_slot; q.zero_slots = pl->rpp_zero; q.n_zero = (int)pl->rpp.zero_slots.size();
+      q.tables = pl->rpp_tab; q.n_slots = L::N_SLOTS;
+      q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.C = a.C; q.scale = rp.scale;
+      q.n_slices = ns; q.n_tiles = g.n_tiles16;
+      q.n_buf = 3;
+      q.done = counters; q.done_target = a.C * n_groups; q.error_flag = ov->error_flag;
+      const int kc_ring = std::max(0, env_int("MRIACL_KC_RING", 0));    // 0 = no ring (measured faster: the row teams set the pace either way)
+      if (kc_ring > 0 && kc_ring < ns) {     // bounded lag between the column teams and the row teams: T stays in L2
+        q.ring = kc_ring; q.rows_done = counters + ns;
+        kp.cp.ring = kc_ring; kp.cp.rows_done = counters + ns; kp.cp.rows_target = g.n_tiles16;
+        kp.cp.l2_hints = 1;
+      }
+      int smem = L::smem_bytes(q.n_buf, n_act, q.n_zero);
+      if (CP_SMEM_BYTES_DB + smem > SMEM_MAX) { q.n_buf = 2; smem = L::smem_bytes(2, n_act, q.n_zero); }
+      if (CP_SMEM_BYTES_DB + smem > SMEM_MAX || RPP_ROWS * (a.ow + 1) * 4 > L::ACC_BYTES)
+        return fail(MRIACL_ERR_UNSUPPORTED, "co-resident pair tile does not fit shared memory (n_act=%d ow=%d)", n_act, a.ow);
+      static const int kc_only = env_int("MRIACL_KC_ONLY", 0);
+      if (kc_only == 1) q.n_slices = 0;
+      if (kc_only == 2) { kp.cp.n_frames = 0; q.done = nullptr; }
+      np.n_part = g.n_tiles16;
+#ifdef MRIACL_EMU
+      const int grid = 1;
+#else
+      const int grid = (int)std::min<long long>(col_items, (long long)a.sms);
+#endif
+      auto kfn = knee_coresident_pair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>;
+      MRIACL_LAUNCH(kfn, grid, KP_T, CP_SMEM_BYTES_DB + smem, a.st, kp);
+      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
+    } else if (coresident) {
+      // one persistent launch, one CTA per SM: a column team and a row team in every CTA (coresident640x368.cuh)
+      if (rt_memset_async(counters, 0, 256 * (size_t)ns, a.st)) return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
+      CoresParams kp{};
+      kp.cp = cp; kp.cp.done = counters;
+      RowPass16Params& q = kp.rp;
+      q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+      q.sched = pl->sched_p12; q.sched_len = (int)pl->pairs12.size();
+      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size();
+      q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
+      q.n_slices = ns; q.n_tiles = g.n_tiles16;
+      q.done = counters; q.done_target = a.A * a.C * n_groups; q.error_flag = ov->error_flag;
+      q.n_buf = 2;
+      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
+      if (CP_SMEM_BYTES_DB + smem16 > SMEM_MAX) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
+      if (CP_SMEM_BYTES_DB + smem16 > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "co-resident tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
+      if (want_norm || a.mean_std) {
+        q.tiles_done = counters + ns;
+        q.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
+        q.eps = a.eps; q.normalize = want_norm ? 1 : 0;
+      }
+#ifdef MRIACL_EMU   // the emulator runs the CTAs one after another: a single CTA does everything
+      const int grid = 1;
+#else
+      const int grid = (int)std::min<long long>(col_items, (long long)a.sms);
+#endif
+      static const int kc_only = env_int("MRIACL_KC_ONLY", 0);   // profiling: 1 = column teams only, 2 = row teams only (T from an earlier call)
+      if (kc_only == 1) kp.rp.n_slices = 0;
+      if (kc_only == 2) { kp.cp.n_frames = 0; kp.rp.done = nullptr; }
+      auto kfn = knee_coresident_kernel<FUSED_P, FUSED_Q>;
+      MRIACL_LAUNCH(kfn, grid, KC_T, CP_SMEM_BYTES_DB + smem16, a.st, kp);
+    } else if (fused_mode) {
       // one persistent launch: column items publish per-slice counters, row items are claimed when ready
       if (rt_memset_async(counters, 0, 256 * (size_t)ns, a.st)) return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
       FusedParams fp{};
@@ -464,6 +548,14 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       MRIACL_LAUNCH(kfn, std::min(work, 2 * a.sms), FZ_T, fz_smem, a.st, fp);
       if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
     } else if (!overlap) {
+      rt_stream_t row_st = pipelined ? ov->side : a.st;
+      if (pipelined) {
+        cp.l2_hints = 1;
+        // T buffer wb: its previous reader (row pass of group - 2) must be done
+        if (group >= n_bufs_ws && rt_stream_wait_event(a.st, ov->ev_row[wb])) return fail(MRIACL_ERR_CUDA, "stream wait failed");
+      }
+      const int fuse_norm_env = env_int("MRIACL_FUSE_NORM", 0);   // measured slower than the separate launch (the finishing CTA streams the slice alone)
+      const bool fuse_norm = fuse_norm_env && !only && !pair_rows && rp16_cfg != 0 && (want_norm || a.mean_std);
       if (n_groups > 0 && do_col) {
         // tuning knobs: MRIACL_CP_DB=0 single-buffer CTAs, MRIACL_CP_PER_SM=k persistent CTAs per SM (0 = one item per CTA)
         static const int cp_db = env_int("MRIACL_CP_DB", 1), cp_per_sm = env_int("MRIACL_CP_PER_SM", 2);
@@ -480,6 +572,10 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
           MRIACL_LAUNCH(colpass640_kernel<false>, grid, CP_T, CP_SMEM_BYTES_SB, a.st, cp);
         }
       }
+      if (pipelined && (rt_event_record(ov->ev_start[wb], a.st) || rt_stream_wait_event(ov->side, ov->ev_start[wb])))
+        return fail(MRIACL_ERR_CUDA, "pipeline hand-over failed: %s", rt_last_error_string());
+      if (fuse_norm && rt_memset_async(counters, 0, sizeof(int) * (size_t)ns, row_st))
+        return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
       if (do_row && pair_rows) {
         using L = RowPairLayout<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>;
         RowPairParams q{};
@@ -497,14 +593,14 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         static const int rpp_minb = env_int("MRIACL_RPP_MINB", 2);
         if (rpp_minb == 2) {
           auto kfn = rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 2>;
-          MRIACL_LAUNCH(kfn, std::min(ns * g.n_tiles16, 2 * a.sms), RPP_TT, smem, a.st, q);
+          MRIACL_LAUNCH(kfn, std::min(ns * g.n_tiles16, 2 * a.sms), RPP_TT, smem, row_st, q);
         } else {
           auto kfn = rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 1>;
-          MRIACL_LAUNCH(kfn, std::min(ns * g.n_tiles16, a.sms), RPP_TT, smem, a.st, q);
+          MRIACL_LAUNCH(kfn, std::min(ns * g.n_tiles16, a.sms), RPP_TT, smem, row_st, q);
         }
       } else if (do_row && rp16_cfg == 0) {
         auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>;
-        MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_SEQ * 32, rp_smem, a.st, rp);
+        MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_SEQ * 32, rp_smem, row_st, rp);
       } else if (do_row) {
         const bool w16 = rp16_cfg == 3;
         RowPass16Params q{};
@@ -515,6 +611,12 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
         q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
         q.n_buf = 2;
+        q.l2_hints = pipelined ? 1 : 0;
+        if (fuse_norm) {
+          q.tiles_done = counters;
+          q.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
+          q.eps = a.eps; q.normalize = want_norm ? 1 : 0;
+        }
         int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
         const int limit = rp16_cfg == 1 ? SMEM_MAX / 2 : SMEM_MAX;
         if (smem16 > limit) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
@@ -523,17 +625,18 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         np.n_part = g.n_tiles16;
         if (rp16_cfg == 1) {
           auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>;
-          MRIACL_LAUNCH(kfn, std::min(items16, 2 * a.sms), 12 * 32, smem16, a.st, q);
+          MRIACL_LAUNCH(kfn, std::min(items16, 2 * a.sms), 12 * 32, smem16, row_st, q);
         } else if (rp16_cfg == 2) {
           auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>;
-          MRIACL_LAUNCH(kfn, std::min(items16, a.sms), 12 * 32, smem16, a.st, q);
+          MRIACL_LAUNCH(kfn, std::min(items16, a.sms), 12 * 32, smem16, row_st, q);
         } else {
           auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>;
-          MRIACL_LAUNCH(kfn, std::min(items16, a.sms), 16 * 32, smem16, a.st, q);
+          MRIACL_LAUNCH(kfn, std::min(items16, a.sms), 16 * 32, smem16, row_st, q);
         }
       }
       if ((rp16_cfg != 0 || pair_rows) && !do_row) np.n_part = g.n_tiles16;
-      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
+      if (run_norm && !fuse_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, row_st, np);
+      if (pipelined && rt_event_record(ov->ev_row[wb], ov->side)) return fail(MRIACL_ERR_CUDA, "event record failed");
     } else {
       // T buffer wb: its previous reader (row pass of group - n_bufs_ws) must be done
       if (group >= n_bufs_ws && rt_stream_wait_event(a.st, ov->ev_row[wb])) return fail(MRIACL_ERR_CUDA, "stream wait failed");
@@ -575,7 +678,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       if (rt_event_record(ov->ev_row[wb], ov->side)) return fail(MRIACL_ERR_CUDA, "event record failed");
     }
   }
-  if (overlap) {   // join: everything on the side stream happens-before whatever the caller enqueues next
+  if (overlap || pipelined) {   // join: everything on the side stream happens-before whatever the caller enqueues next
     const int used = std::min(group, n_bufs_ws);
     for (int i = 0; i < used; ++i)
       if (rt_stream_wait_event(a.st, ov->ev_row[i])) return fail(MRIACL_ERR_CUDA, "stream join failed");

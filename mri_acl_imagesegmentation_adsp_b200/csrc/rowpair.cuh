@@ -51,6 +51,11 @@ struct RowPairParams {
   float scale;
   int n_slices, n_tiles;     // n_tiles = ceil(oh / 16)
   int n_buf;                 // tile ring depth (2 or 3)
+  const int* done;           // optional [n_slices]: column-pass items finished per slice (co-resident schedule)
+  int done_target;
+  int* error_flag;
+  int ring;                  // co-resident schedule: slice s lives in T slot s % ring (0 = no ring)
+  int* rows_done;            // [n_slices] += 1 per consumed tile (the column teams wait on it before reusing a slot)
 };
 
 template <int P, int Q, int STEP, int NE> struct RowPairLayout {
@@ -258,6 +263,7 @@ __device__ __forceinline__ void rowpair_compute_item(const RowPairParams& p, voi
     }
   }
   named_bar_sync(bar_c, RPP_CT);                                      // tile consumed before the next item's first store
+  if (p.rows_done && t == 0) atomicAdd(p.rows_done + s, 1);           // every T word of this tile has been copied out
 }
 
 // stager warp: the coil tiles of one item.  Copies only; the mbarrier of the buffer flips when they have landed.
@@ -268,8 +274,12 @@ __device__ __forceinline__ void rowpair_stage_item(const RowPairParams& p, void*
   RowPairSmem<P, Q, STEP, NE> S(smem_base, p);
   const int s = item / p.n_tiles, tile = item - s * p.n_tiles;
   const long long frame_elems = (long long)p.n_act * p.ohp;
-  const cf* Tit = p.T + (long long)s * p.C * frame_elems + tile * RPP_ROWS;
+  const cf* Tit = p.T + (long long)(p.ring ? s % p.ring : s) * p.C * frame_elems + tile * RPP_ROWS;
   const int n_copies = p.n_act * (RPP_ROWS / 2);          // 16-byte pieces: 8 per column
+  if (p.done) {     // co-resident schedule: the slice's columns are written by column teams running beside us
+    if (lane == 0 && !rp_wait_count(p.done + s, p.done_target, p.error_flag) && p.error_flag) atomicAdd(p.error_flag, 1);
+    __syncwarp();
+  }
   for (int f = 0; f < p.C; ++f, ++k_stage) {
     const int buf = k_stage % p.n_buf;
     if (k_stage >= p.n_buf) named_bar_sync(bar0 + 3 + buf, RPP_TT);   // the compute warps are done with this buffer

@@ -57,7 +57,12 @@ inline int rowpass_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_a
 // abortable through a device-wide flag, so that a scheduling surprise ends in an error flag, not a hung device.
 __device__ __forceinline__ bool rp_wait_count(const int* counter, int target, int* error_flag) {
 #if defined(MRIACL_EMU)
-  return *counter >= target;
+  // emulator: producers may be sibling threads of the same CTA (co-resident kernel), so poll for a while
+  for (int spin = 0; spin < 2000000; ++spin) {
+    if (reinterpret_cast<const std::atomic<int>*>(counter)->load() >= target) return true;
+    std::this_thread::yield();
+  }
+  return false;
 #else
   const volatile int* c = counter;
   const volatile int* err = error_flag;
@@ -76,6 +81,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 #else
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gsrc, unsigned long long pol) {
+#if defined(MRIACL_EMU)
+  reinterpret_cast<float4*>(smem_dst)[0] = reinterpret_cast<const float4*>(gsrc)[0];
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
 #endif
 }
 __device__ __forceinline__ void cp_async_commit() {

@@ -36,11 +36,33 @@ struct RowPass16Params {
   const int* done;
   int done_target;
   int* error_flag;
+  // fused instance normalisation: the team that finishes the last tile of a slice normalises the slice
+  int* tiles_done;       // [n_slices] zeroed before the launch, or nullptr (statistics / normalisation by a later launch)
+  float* mean_std;       // [n_slices][2] or nullptr
+  float eps;
+  int normalize;         // 1: (x - mean) / (std + eps) in place
+  int l2_hints;          // 1: T is read with an evict_last hint (chunk-pipelined schedule)
 };
 
 inline int rowpass16_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_act, int n_buf, int ow, int A) {
   return P * (Q + 1) * RP16_ROWS * 8 + rp_round16(sptw_len * 8) + rp_round16(sched_len * 4) +
          n_buf * (n_act + 1) * RP16_ROWS * 8 + (A > 1 ? RP16_ROWS * (ow + 1) * 4 : 0);
+}
+
+// team barrier: BAR = 0 is the CTA barrier; BAR > 0 a named barrier over the NT threads of a sub-CTA team
+template <int BAR, int NT> __device__ __forceinline__ void rp16_sync() {
+  if constexpr (BAR == 0) __syncthreads(); else named_bar_sync(BAR, NT);
+}
+template <int NW, int BAR> __device__ __forceinline__ float rp16_team_sum(float v, float* red /* NW floats */, int tid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  rp16_sync<BAR, NW * 32>();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  rp16_sync<BAR, NW * 32>();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) t += red[w];
+  return t;
 }
 
 template <int P, int Q, int NNZ>
@@ -89,7 +111,7 @@ template <int NT> __device__ __forceinline__ void rp16_load_tables(const RowPass
 }
 
 // one work item = (slice, 16-row tile); called by all NW*32 threads of the (sub-)CTA; tables already loaded
-template <int P, int Q, int NW>
+template <int P, int Q, int NW, int BAR = 0>
 __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* smem_base, int item, int tid,
                                                float* red, int* ready_flag) {
   static_assert(Q == 16, "stage 2 is the register-level 16-point FFT");
@@ -123,14 +145,24 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
     cf* dst0 = tbuf + (tid >> 3) * RP16_ROWS + 2 * (tid & 7);
     const long long src_step = (long long)(NT / 8) * p.ohp;
     const int n_iter = tid < n_copies ? (n_copies - tid + NT - 1) / NT : 0;
+    const unsigned long long pol_t = l2_policy_evict_last();
     auto prefetch = [&](int f, int buf) {
       const cf* src = src0 + (long long)f * frame_elems;
       cf* dst = dst0 + (size_t)buf * tile_elems;
+      if (p.l2_hints) {
 #pragma unroll 1
-      for (int i = 0; i < n_iter; ++i) {
-        cp_async16(dst, src);
-        src += src_step;
-        dst += (NT / 8) * RP16_ROWS;
+        for (int i = 0; i < n_iter; ++i) {
+          cp_async16_hint(dst, src, pol_t);
+          src += src_step;
+          dst += (NT / 8) * RP16_ROWS;
+        }
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < n_iter; ++i) {
+          cp_async16(dst, src);
+          src += src_step;
+          dst += (NT / 8) * RP16_ROWS;
+        }
       }
       cp_async_commit();
     };
@@ -140,7 +172,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
         ready = rp_wait_count(p.done + s, p.done_target, p.error_flag) ? 1 : 0;
         if (!ready && p.error_flag) atomicAdd(p.error_flag, 1);
       }
-      __syncthreads();
+      rp16_sync<BAR, NT>();
       if (!ready) return;
     }
     if (p.A > 1) for (int i = tid; i < RP16_ROWS * opitch; i += NT) avsm[i] = 0.f;
@@ -161,7 +193,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
       } else {
         cp_async_wait<0>();
       }
-      __syncthreads();
+      rp16_sync<BAR, NT>();
 
       // ---------------- stage 1: two units per warp ----------------
       {
@@ -202,7 +234,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
           }
         }
       }
-      __syncthreads();
+      rp16_sync<BAR, NT>();
       if (p.n_buf == 1 && f + 1 < n_frames) prefetch(f + 1, 0);
 
       // ---------------- stage 2: two 16-point FFTs per warp ----------------
@@ -240,7 +272,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
         }
       }
     }
-    __syncthreads();
+    rp16_sync<BAR, NT>();
     if (p.A == 1) {
 #pragma unroll
       for (int kk = 0; kk < KPW; ++kk) {
@@ -254,7 +286,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
           }
         }
       }
-      __syncthreads();
+      rp16_sync<BAR, NT>();
     }
 
     const float* tile_sm = p.A > 1 ? avsm : osm;
@@ -271,7 +303,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
       lsum += v;
     }
     if (p.partials) {
-      const float mean = rp_block_sum<NW>(lsum, red) / (float)n_here;
+      const float mean = rp16_team_sum<NW, BAR>(lsum, red, tid) / (float)n_here;
       float lq = 0.f;
       for (int e = tid; e < n_here; e += NT) {
         const int rr = e / p.ow, cc = e - rr * p.ow;
@@ -280,27 +312,99 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
         const float d = v - mean;
         lq = fmaf(d, d, lq);
       }
-      const float m2 = rp_block_sum<NW>(lq, red);
+      const float m2 = rp16_team_sum<NW, BAR>(lq, red, tid);
       if (tid == 0) {
         float* q = p.partials + ((long long)s * p.n_tiles + tile) * 3;
         q[0] = (float)n_here; q[1] = mean; q[2] = m2;
       }
     }
-    __syncthreads();
+    rp16_sync<BAR, NT>();
   }
+}
+
+__device__ __forceinline__ float rp16_ld_cg(const float* p) {
+#if defined(MRIACL_EMU)
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ float4 rp16_ld_cg4(const float4* p) {
+#if defined(MRIACL_EMU)
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+
+// Called by the whole team after rowpass16_item when p.tiles_done is set: publishes the tile, and if it was the
+// last tile of its slice, merges the tiles' (n, mean, M2) partials (Chan) into mean / unbiased std
+// (ZIP!/DL_reconstruction/data/transforms.py:143-162) and normalises the slice in place.  Tiles of other CTAs are
+// read with ld.cg (L2): they were published with a device-wide fence before the counter moved.
+template <int NW, int BAR>
+__device__ __forceinline__ void rowpass16_finish_slice(const RowPass16Params& r, int item, int t, float* s_stat, int* s_last) {
+  constexpr int NT = NW * 32;
+  const int s = item / r.n_tiles;
+  __threadfence();
+  rp16_sync<BAR, NT>();
+  if (t == 0) {
+    const int prev = atomicAdd(r.tiles_done + s, 1);
+    *s_last = prev == r.n_tiles - 1 ? 1 : 0;
+    if (*s_last) __threadfence();
+  }
+  rp16_sync<BAR, NT>();
+  if (*s_last) {
+    const long long n = (long long)r.oh * r.ow;
+    if (t == 0) {
+      double cnt = 0.0, mean = 0.0, m2 = 0.0;
+      for (int i = 0; i < r.n_tiles; ++i) {
+        const float* q = r.partials + ((long long)s * r.n_tiles + i) * 3;
+        const double nb = rp16_ld_cg(q), mb = rp16_ld_cg(q + 1), sb = rp16_ld_cg(q + 2);
+        if (nb > 0.0) {
+          const double d = mb - mean, tot = cnt + nb;
+          mean += d * nb / tot;
+          m2 += sb + d * d * cnt * nb / tot;
+          cnt = tot;
+        }
+      }
+      s_stat[0] = (float)mean;
+      s_stat[1] = (float)sqrt(m2 / (double)(n - 1));
+      if (r.mean_std) { r.mean_std[2 * s] = s_stat[0]; r.mean_std[2 * s + 1] = s_stat[1]; }
+    }
+    rp16_sync<BAR, NT>();
+    if (r.normalize) {
+      const float fmean = s_stat[0], den = s_stat[1] + r.eps;
+      float* y = r.out + (long long)s * n;
+      if ((n & 3) == 0 && (((unsigned long long)y) & 15) == 0) {
+        float4* y4 = reinterpret_cast<float4*>(y);
+        for (long long i = t; i < n / 4; i += NT) {
+          float4 v = rp16_ld_cg4(y4 + i);
+          v.x = (v.x - fmean) / den; v.y = (v.y - fmean) / den; v.z = (v.z - fmean) / den; v.w = (v.w - fmean) / den;
+          y4[i] = v;
+        }
+      } else {
+        for (long long i = t; i < n; i += NT) y[i] = (rp16_ld_cg(y + i) - fmean) / den;
+      }
+    }
+  }
+  rp16_sync<BAR, NT>();
 }
 
 template <int P, int Q, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) rowpass16_kernel(RowPass16Params p) {
   MRIACL_DYN_SMEM(cf, smem);
   __shared__ float red[NW];
-  __shared__ int ready;
+  __shared__ float s_stat[2];
+  __shared__ int ready, s_last;
   Rp16Smem<P, Q> S(smem, p);
   rp16_load_tables<NW * 32>(p, S.sptw, S.sch, S.tbuf, threadIdx.x);
   __syncthreads();
   const int n_items = p.n_slices * p.n_tiles;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     rowpass16_item<P, Q, NW>(p, smem, item, threadIdx.x, red, &ready);
+    if (p.done && !ready) return;
+    if (p.tiles_done) rowpass16_finish_slice<NW, 0>(p, item, threadIdx.x, s_stat, &s_last);
+  }
 }
 
 }  // namespace mriacl

@@ -87,9 +87,10 @@ def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int
     if schedule is not None:
         try:
             flags |= {"sequential": cabi.SEQUENTIAL, "fused": cabi.SCHED_FUSED, "overlapped": cabi.SCHED_OVERLAP,
-                      "pair": cabi.SCHED_PAIR}[schedule]
+                      "pair": cabi.SCHED_PAIR, "coresident": cabi.SCHED_CORESIDENT,
+                      "pipelined": cabi.SCHED_PIPELINED}[schedule]
         except KeyError:
-            raise ValueError(f"schedule must be sequential, fused, overlapped or pair, got {schedule!r}") from None
+            raise ValueError(f"schedule must be sequential, fused, overlapped, pair, coresident or pipelined, got {schedule!r}") from None
 
     lib = D.lib()
     out = torch.empty((S, oh, ow), dtype=torch.float32, device=k.device)

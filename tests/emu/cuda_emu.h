@@ -32,6 +32,7 @@ static inline float4 make_float4(float a, float b, float c, float d) { return fl
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static
 #define __align__(n) alignas(n)
 

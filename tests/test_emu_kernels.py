@@ -128,6 +128,52 @@ def test_fused_schedules_agree(emu):
         np.testing.assert_array_equal(out1, ref)
 
 
+def test_coresident_kernel(emu):
+    """column team + row team in one CTA, per-slice counters, normalisation by the team that finishes a slice's
+    last tile: same bits as the back-to-back kernels for the images, same statistics."""
+    k = synth.gaussian_kspace((2, 2, 2, 640, 368), 29)
+    m = synth.knee_mask()
+    ref, rms = recon(emu, k, m, (320, 320), cabi.SEQUENTIAL | cabi.NORM_INSTANCE)
+    out, ms = recon(emu, k, m, (320, 320), cabi.SCHED_CORESIDENT | cabi.NORM_INSTANCE)
+    np.testing.assert_allclose(out, ref, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(ms, rms, rtol=1e-6)
+    raw_ref, _ = recon(emu, k, m, (77, 200), cabi.SEQUENTIAL | cabi.FLIP_ROWS)
+    raw, _ = recon(emu, k, m, (77, 200), cabi.SCHED_CORESIDENT | cabi.FLIP_ROWS, chunk=1)
+    np.testing.assert_array_equal(raw, raw_ref)
+    # single average + a mask of the pair family: the row team is the pair row pass (rowpair.cuh)
+    k1 = synth.gaussian_kspace((2, 1, 3, 640, 368), 37)
+    ref1, rms1 = recon(emu, k1, m, (320, 320), cabi.SEQUENTIAL | cabi.NORM_INSTANCE)
+    out1, ms1 = recon(emu, k1, m, (320, 320), cabi.SCHED_CORESIDENT | cabi.NORM_INSTANCE)
+    assert O.rel_l2(out1, ref1) <= TOL
+    np.testing.assert_allclose(ms1, rms1, rtol=1e-5)
+
+
+def test_pipelined_schedule_and_fused_normalisation(emu):
+    """chunk-pipelined schedule (two T buffers, side stream) and the normalisation fused into the row pass (last tile
+    of a slice normalises it) against the separate normalise launch."""
+    import os
+    k = synth.gaussian_kspace((3, 1, 2, 640, 368), 31)
+    m = synth.knee_mask()
+    os.environ["MRIACL_FUSE_NORM"] = "1"       # opt-in knob, read per call
+    ref_raw, _ = recon(emu, k, m, (320, 320), cabi.SEQUENTIAL)
+    out, ms = recon(emu, k, m, (320, 320), cabi.SEQUENTIAL | cabi.NORM_INSTANCE)
+    for s in range(3):
+        nref, mean, std = O.normalize_instance(np.ascontiguousarray(ref_raw[s]))
+        assert O.rel_l2(out[s], nref) <= TOL
+        np.testing.assert_allclose(ms[s], [mean, std], rtol=1e-5)
+    pout, pms = recon(emu, k, m, (320, 320), cabi.SCHED_PIPELINED | cabi.NORM_INSTANCE, chunk=2)
+    np.testing.assert_array_equal(pout, out)
+    np.testing.assert_array_equal(pms, ms)
+    os.environ.pop("MRIACL_FUSE_NORM")
+    sep, sms_ = recon(emu, k, m, (320, 320), cabi.SEQUENTIAL | cabi.NORM_INSTANCE)
+    np.testing.assert_allclose(sep, out, rtol=0, atol=2e-6)
+    # co-resident schedule with a one-slot ring of T: the column teams wait for the row teams before reusing the slot
+    os.environ["MRIACL_KC_RING"] = "1"
+    rout, rms_ = recon(emu, k, m, (320, 320), cabi.SCHED_CORESIDENT | cabi.NORM_INSTANCE)
+    os.environ.pop("MRIACL_KC_RING")
+    assert O.rel_l2(rout, out) <= TOL
+
+
 def test_pair_row_pass(emu, golden):
     """the pair row pass (rowpair.cuh: per-output-pair transform, stager warp, rotated residue-major tile) against
     the oracle and the cooperative row pass, incl. an odd crop, a shifted mask offset and a mask outside its family."""

@@ -153,6 +153,56 @@ def test_experimental_schedules_many_groups(schedule):
         zero_filled_rss(k, m, synth.CROP, None, schedule="bogus")
 
 
+def test_coresident_schedule():
+    """the one-launch co-resident schedule (column team + row team in every CTA, fused normalisation) gives the same
+    images as the back-to-back kernels: bit-identical before normalisation, last-bit statistics differences after;
+    repeated calls and chunked workspaces reuse the counters correctly."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    k = torch.view_as_complex(torch.randn((13, 15, 640, 368, 2), device="cuda", generator=g))
+    m = synth.knee_mask()
+    ref, _, _ = zero_filled_rss(k, m, synth.CROP, None, schedule="sequential")
+    nref, rmean, rstd = zero_filled_rss(k, m, synth.CROP, "instance", schedule="sequential")
+    first = None
+    for chunk in (13, 5, 1):
+        out, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=chunk, schedule="coresident")
+        assert O.rel_l2(out.cpu().numpy(), ref.cpu().numpy()) <= 2e-6, chunk
+        first = out if first is None else first
+        assert torch.equal(out, first), chunk          # chunking never changes a slice
+        nout, mean, std = zero_filled_rss(k, m, synth.CROP, "instance", chunk_slices=chunk, schedule="coresident")
+        torch.testing.assert_close(nout, nref, rtol=0, atol=2e-5)
+        torch.testing.assert_close(mean, rmean, rtol=1e-5, atol=0)
+        torch.testing.assert_close(std, rstd, rtol=1e-5, atol=0)
+    for _ in range(4):
+        out, _, _ = zero_filled_rss(k, m, synth.CROP, None, schedule="coresident")
+    assert torch.equal(out, first)
+    # (single average + pair-family mask above runs the pair row team; MRIACL_KC_PAIR=0 selects the cooperative one)
+    # averages + flip + odd crop through the same kernel
+    k5 = torch.view_as_complex(torch.randn((3, 2, 4, 640, 368, 2), device="cuda", generator=g))
+    a, _, _ = zero_filled_rss(k5, m, (77, 200), None, average_axis=1, flip_rows=True, schedule="coresident")
+    b, _, _ = zero_filled_rss(k5, m, (77, 200), None, average_axis=1, flip_rows=True, schedule="sequential")
+    assert torch.equal(a, b)
+
+
+def test_pipelined_schedule():
+    """small chunks on two streams with T double-buffered in L2: same bits as one big chunk, incl. the fused normalisation;
+    ragged last chunk; repeated calls (event / buffer reuse)."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    k = torch.view_as_complex(torch.randn((21, 15, 640, 368, 2), device="cuda", generator=g))
+    m = synth.knee_mask()
+    ref, _, _ = zero_filled_rss(k, m, synth.CROP, None, schedule="sequential")
+    nref, rmean, rstd = zero_filled_rss(k, m, synth.CROP, "instance", schedule="sequential")
+    for chunk in (21, 16, 5):
+        out, _, _ = zero_filled_rss(k, m, synth.CROP, None, chunk_slices=chunk, schedule="pipelined")
+        assert torch.equal(out, ref), chunk
+        nout, mean, std = zero_filled_rss(k, m, synth.CROP, "instance", chunk_slices=chunk, schedule="pipelined")
+        assert torch.equal(nout, nref) and torch.equal(mean, rmean) and torch.equal(std, rstd)
+    for _ in range(3):
+        nout, _, _ = zero_filled_rss(k, m, synth.CROP, "instance", schedule="pipelined")
+    assert torch.equal(nout, nref)
+    want = O.knee_chain_numpy(k[20].cpu().numpy(), m, synth.CROP, "instance")
+    assert O.rel_l2(nout[20].cpu().numpy(), want[0]) <= TOL
+
+
 def test_pair_row_pass_schedule():
     """the pair row pass (rowpair.cuh) against the oracle (rel-L2 <= 1e-5) and the cooperative row pass; bit-stable
     under chunking; masked columns never read; a mask offset that needs the index rotation; fallback outside its family."""
