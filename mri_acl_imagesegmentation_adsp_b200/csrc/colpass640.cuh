@@ -322,6 +322,45 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
     full_wait(&full_bar[buf], (uses[buf] + (k >> 1)) & 1, CP_BAR_FULL + buf, CP_WS_T);
 
     const int ncols_c = (p.debug_skip & 2) ? 0 : ncols;
+    // Full item (8 columns): each thread owns columns sub, sub+2, sub+4, sub+6 and keeps all four butterflies of a
+    // pass in flight (4-way instruction-level parallelism between the team barriers); ragged items take the loop below.
+    if (ncols_c == CP_G && p.unit_mask) {
+      cf* col0 = cur + sub * CP_PITCH;
+      {
+        cf v[4][8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int n1 = 0; n1 < 8; ++n1) v[c][n1] = col0[2 * c * CP_PITCH + pos + n1 * CP_BLK];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) radix8<true>(v[c]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          cf* col = col0 + 2 * c * CP_PITCH + pos;
+          col[0] = v[c][0];
+#pragma unroll
+          for (int m1 = 1; m1 < 8; ++m1) col[m1 * CP_BLK] = cmul(v[c][m1], tw1[m1]);
+        }
+      }
+      named_bar_sync(CP_BAR_COMPUTE, CP_T);
+      {
+        cf v[4][8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int n2 = 0; n2 < 8; ++n2) v[c][n2] = col0[2 * c * CP_PITCH + base2 + n2 * 10];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) radix8<true>(v[c]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          cf* col = col0 + 2 * c * CP_PITCH + base2;
+          col[0] = v[c][0];
+#pragma unroll
+          for (int m2 = 1; m2 < 8; ++m2) col[m2 * 10] = cmul(v[c][m2], tw2[m2]);
+        }
+      }
+      named_bar_sync(CP_BAR_COMPUTE, CP_T);
+    } else {
     // ---- pass 1: radix-8 over n1 (stride 90), mask multiply, twiddle w640^{pos * m1}; two columns in flight ----
     for (int kc = sub; kc < ncols_c; kc += 4) {
       const bool two = kc + 2 < ncols;
@@ -369,6 +408,7 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
     }
     named_bar_sync(CP_BAR_COMPUTE, CP_T);
 
+    }
     // ---- pass 3: radix-10 over n3 (contiguous), crop/shift/flip on the way out ----
     int t_frame = fl;
     if (p.ring) {        // ring of T slots: wait until the slot's previous slice has been consumed by the row teams

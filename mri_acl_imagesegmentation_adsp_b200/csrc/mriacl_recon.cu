@@ -84,6 +84,7 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 8, 3>, SMEM_MAX / 3);
   bad |= rt_allow_smem((const void*)knee_coresident_kernel<FUSED_P, FUSED_Q>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_pair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 1>, SMEM_MAX / 2);
@@ -602,11 +603,11 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         auto kfn = rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>;
         MRIACL_LAUNCH(kfn, std::min(row_items, a.sms), RP_NW_SEQ * 32, rp_smem, row_st, rp);
       } else if (do_row) {
-        const bool w16 = rp16_cfg == 3;
+        const bool w16 = rp16_cfg == 3, w8 = rp16_cfg == 4;
         RowPass16Params q{};
         q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
-        q.sched = w16 ? pl->sched_p16 : pl->sched_p12;
-        q.sched_len = (int)(w16 ? pl->pairs16.size() : pl->pairs12.size());
+        q.sched = w16 ? pl->sched_p16 : w8 ? pl->sched_p8 : pl->sched_p12;
+        q.sched_len = (int)(w16 ? pl->pairs16.size() : w8 ? pl->pairs8.size() : pl->pairs12.size());
         q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size();
         q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
         q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
@@ -618,7 +619,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
           q.eps = a.eps; q.normalize = want_norm ? 1 : 0;
         }
         int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
-        const int limit = rp16_cfg == 1 ? SMEM_MAX / 2 : SMEM_MAX;
+        const int limit = rp16_cfg == 1 ? SMEM_MAX / 2 : rp16_cfg == 4 ? SMEM_MAX / 3 : SMEM_MAX;
         if (smem16 > limit) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
         if (smem16 > limit) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
         const int items16 = ns * g.n_tiles16;
@@ -626,6 +627,9 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         if (rp16_cfg == 1) {
           auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>;
           MRIACL_LAUNCH(kfn, std::min(items16, 2 * a.sms), 12 * 32, smem16, row_st, q);
+        } else if (rp16_cfg == 4) {
+          auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 8, 3>;
+          MRIACL_LAUNCH(kfn, std::min(items16, 3 * a.sms), 8 * 32, smem16, row_st, q);
         } else if (rp16_cfg == 2) {
           auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>;
           MRIACL_LAUNCH(kfn, std::min(items16, a.sms), 12 * 32, smem16, row_st, q);

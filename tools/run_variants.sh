@@ -2,10 +2,8 @@ run() { env "$@" timeout 100 python bench.py --steps 20 --warmup 3 --no-cpu-base
 import json,sys
 d=json.load(open('gpurun_out/b_var.json'))
 k=d['roofline']['kernels_ms']
-print('$*', round(d['ms_per_step'],4), round(d['value']), round(d['roofline']['frac'],4))
+print('$*', 'col', round(k['colpass640_alone'],4))
 " || tail -3 gpurun_out/b_var.err; }
-run MRIACL_SCHEDULE=coresident MRIACL_KC_RING=0
-run MRIACL_SCHEDULE=coresident MRIACL_KC_RING=12
-run MRIACL_SCHEDULE=coresident MRIACL_KC_RING=8
-run MRIACL_SCHEDULE=coresident MRIACL_KC_RING=16
-run MRIACL_SCHEDULE=coresident MRIACL_KC_RING=24
+run MRIACL_CP_DEBUG_SKIP=5
+run MRIACL_CP_DEBUG_SKIP=3
+run MRIACL_CP_DEBUG_SKIP=7
