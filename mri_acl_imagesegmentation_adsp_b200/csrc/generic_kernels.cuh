@@ -174,20 +174,37 @@ __global__ void __launch_bounds__(256) normalize_instance_kernel(NormParams p) {
   const int b = blockIdx.x / p.n_split, part = blockIdx.x - b * p.n_split;
   const float* x = p.in + (long long)b * p.n;
   if (p.partials) {
-    if (threadIdx.x == 0) {
+    // Chan's pairwise merge of the tiles' (count, mean, M2), in parallel: lane i of warp 0 starts from tiles i, i+32, ...
+    // and the lanes combine by a shuffle tree (double precision; a handful of operations instead of a serial loop)
+    if (threadIdx.x < 32) {
       double cnt = 0.0, mean = 0.0, m2 = 0.0;
-      for (int t = 0; t < p.n_part; ++t) {
-        const float* q = p.partials + ((long long)b * p.n_part + t) * 3;
-        const double nb = q[0], mb = q[1], sb = q[2];
+      auto merge = [&](double nb, double mb, double sb) {
         if (nb > 0.0) {
           const double d = mb - mean, tot = cnt + nb;
           mean += d * nb / tot;
           m2 += sb + d * d * cnt * nb / tot;
           cnt = tot;
         }
+      };
+      for (int t = threadIdx.x; t < p.n_part; t += 32) {
+        const float* q = p.partials + ((long long)b * p.n_part + t) * 3;
+        merge((double)q[0], (double)q[1], (double)q[2]);
       }
-      s_mean = (float)mean;
-      s_std = (float)sqrt(m2 / (double)(p.n - 1));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double nb = __shfl_xor_sync(0xffffffffu, cnt, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+                     sb = __shfl_xor_sync(0xffffffffu, m2, o);
+        // both partners must arrive at the same value: merge (lower lane's triple) <- (upper lane's triple)
+        const bool low = (threadIdx.x & o) == 0;
+        const double an = low ? cnt : nb, am = low ? mean : mb, as = low ? m2 : sb;
+        const double bn = low ? nb : cnt, bm = low ? mb : mean, bs = low ? sb : m2;
+        cnt = an; mean = am; m2 = as;
+        merge(bn, bm, bs);
+      }
+      if (threadIdx.x == 0) {
+        s_mean = (float)mean;
+        s_std = (float)sqrt(m2 / (double)(p.n - 1));
+      }
     }
     __syncthreads();
   } else {
@@ -205,13 +222,29 @@ __global__ void __launch_bounds__(256) normalize_instance_kernel(NormParams p) {
   if (p.normalize && p.out) {
     float* y = p.out + (long long)b * p.n;
     const float den = fstd + p.eps;
-    const long long per = (p.n + p.n_split - 1) / p.n_split;
-    const long long lo = part * per, hi = lo + per < p.n ? lo + per : p.n;
-    const bool vec = ((p.n | lo | hi) & 3) == 0 && ((((unsigned long long)x) | ((unsigned long long)y)) & 15) == 0;
+    const long long per = (((p.n + p.n_split - 1) / p.n_split) + 3) & ~3LL;      // shares start on 16-byte boundaries
+    const long long lo = part * per < p.n ? part * per : p.n, hi = lo + per < p.n ? lo + per : p.n;
+    const bool vec = ((lo | hi) & 3) == 0 && ((((unsigned long long)x) | ((unsigned long long)y)) & 15) == 0;
+    const float inv = 1.0f / den;
+    (void)inv;
     if (vec) {
       const float4* x4 = reinterpret_cast<const float4*>(x);
       float4* y4 = reinterpret_cast<float4*>(y);
-      for (long long i = lo / 4 + threadIdx.x; i < hi / 4; i += blockDim.x) {
+      const long long i0 = lo / 4, i1 = hi / 4;
+      long long i = i0 + threadIdx.x;
+      // four independent 128-bit loads in flight per thread
+      for (; i + 3LL * blockDim.x < i1; i += 4LL * blockDim.x) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = x4[i + (long long)u * blockDim.x];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u].x = (v[u].x - fmean) / den; v[u].y = (v[u].y - fmean) / den;
+          v[u].z = (v[u].z - fmean) / den; v[u].w = (v[u].w - fmean) / den;
+          y4[i + (long long)u * blockDim.x] = v[u];
+        }
+      }
+      for (; i < i1; i += blockDim.x) {
         float4 v = x4[i];
         v.x = (v.x - fmean) / den; v.y = (v.y - fmean) / den; v.z = (v.z - fmean) / den; v.w = (v.w - fmean) / den;
         y4[i] = v;

@@ -2,8 +2,6 @@ run() { env "$@" timeout 100 python bench.py --steps 20 --warmup 3 --no-cpu-base
 import json,sys
 d=json.load(open('gpurun_out/b_var.json'))
 k=d['roofline']['kernels_ms']
-print('$*', 'col', round(k['colpass640_alone'],4))
+print('$*', round(d['ms_per_step'],4), round(d['value']), round(d['roofline']['frac'],4), {a:round(b,4) for a,b in k.items()})
 " || tail -3 gpurun_out/b_var.err; }
-run MRIACL_CP_DEBUG_SKIP=5
-run MRIACL_CP_DEBUG_SKIP=3
-run MRIACL_CP_DEBUG_SKIP=7
+run MRIACL_X=1
