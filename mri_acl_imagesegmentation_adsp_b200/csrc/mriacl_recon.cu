@@ -19,6 +19,7 @@
 #include "rowpass.cuh"
 #include "rowpass16.cuh"
 #include "rowpair.cuh"
+#include "rowpass640.cuh"
 #include "fused640x368.cuh"
 #include "coresident640x368.cuh"
 
@@ -85,6 +86,7 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 8, 3>, SMEM_MAX / 3);
+  bad |= rt_allow_smem((const void*)rowpass640_kernel, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_kernel<FUSED_P, FUSED_Q>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_pair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 1>, SMEM_MAX / 2);
@@ -147,6 +149,9 @@ struct FusedPlanDev {
   cf* sptw16_dev = nullptr;
   int* sched_p12 = nullptr;
   int* sched_p16 = nullptr;
+  Row640PlanHost r640;             // 640-wide row pass (Wp == 640 plans)
+  int* r640_off = nullptr;
+  int* r640_ent = nullptr;
   RowPairPlanHost rpp;             // pair row pass (ok = the mask fits its template)
   int* rpp_slot = nullptr;
   int* rpp_zero = nullptr;
@@ -212,6 +217,14 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     void* s5 = nullptr;
     if (rt_malloc(&s5, sizeof(int) * pl->pairs8.size()) || rt_upload(s5, pl->pairs8.data(), sizeof(int) * pl->pairs8.size())) return nullptr;
     pl->sched_p8 = (int*)s5;
+    if (Wp == CP_N) {
+      build_row640_plan(pl->host, pl->r640);
+      void *o1 = nullptr, *o2 = nullptr;
+      if (rt_malloc(&o1, sizeof(int) * 81) || rt_malloc(&o2, sizeof(int) * (pl->r640.ent.size() + 1)) ||
+          rt_upload(o1, pl->r640.pos_off.data(), sizeof(int) * 81) ||
+          (!pl->r640.ent.empty() && rt_upload(o2, pl->r640.ent.data(), sizeof(int) * pl->r640.ent.size()))) return nullptr;
+      pl->r640_off = (int*)o1; pl->r640_ent = (int*)o2;
+    }
     build_rowpair_plan(pl->host, RPP_STEP, RPP_NE, pl->rpp);
     if (pl->rpp.ok) {
       void *q1 = nullptr, *q2 = nullptr, *q3 = nullptr;
@@ -234,12 +247,12 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
   return pl;
 }
 
-bool fused_shape(int H, int Wp) { return H == CP_N && Wp == FUSED_P * FUSED_Q; }
+bool fused_shape(int H, int Wp) { return H == CP_N && (Wp == FUSED_P * FUSED_Q || Wp == CP_N); }
 
 struct ReconGeom {
   bool fused;
   int n_act, n_tiles;   // n_tiles: 32-row tiles (T row pitch = 32 * n_tiles)
-  int n_tiles16;
+  int n_tiles16, n_tiles8;
   size_t per_slice;     // workspace bytes per slice in flight
   size_t t_bytes;       // intermediate bytes per slice
 };
@@ -249,13 +262,14 @@ int recon_geom(int A, int C, int H, int W, int pad_left, int Wp, int oh, int ow,
   g.fused = fused_shape(H, Wp) && !(flags & MRIACL_FORCE_GENERIC);
   g.n_tiles = (oh + RP_ROWS - 1) / RP_ROWS;
   g.n_tiles16 = (oh + RP16_ROWS - 1) / RP16_ROWS;
+  g.n_tiles8 = (oh + R640_ROWS - 1) / R640_ROWS;
   if (g.fused) {
     int n_act = 0;
     for (int w = 0; w < W; ++w) n_act += (!mask || mask[w] != 0.0f) ? 1 : 0;
     g.n_act = n_act;
     const size_t ohp = (size_t)g.n_tiles * RP_ROWS;
     g.t_bytes = align_up((size_t)A * C * (size_t)(n_act > 0 ? n_act : 1) * ohp * sizeof(cf), 256);
-    g.per_slice = g.t_bytes + align_up((size_t)g.n_tiles16 * 3 * sizeof(float), 256) + 256;   // + completion counter
+    g.per_slice = g.t_bytes + align_up((size_t)g.n_tiles8 * 3 * sizeof(float), 256) + 256;   // partials (finest tiling) + completion counter
   } else {
     g.n_act = W;
     g.t_bytes = align_up((size_t)A * C * H * Wp * sizeof(cf), 256);
@@ -339,6 +353,59 @@ struct FusedArgs {
   void* workspace; size_t workspace_bytes; rt_stream_t st; int dev, sms;
 };
 
+// The 640 x 640 plans (prostate-shape): column pass -> 640-wide row pass -> normalise, back to back.
+int run_fused640(const FusedArgs& a, const ReconGeom& g) {
+  std::shared_ptr<FusedPlanDev> pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
+  if (!pl || !pl->r640_off) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
+  const int n_act = (int)pl->host.act_w.size();
+  const int n_groups = (n_act + CP_G - 1) / CP_G;
+  const int ohp = g.n_tiles * RP_ROWS;
+  const int row0 = crop_start(a.H, a.oh), col0 = crop_start(a.Wp, a.ow);
+  const bool want_norm = (a.flags & MRIACL_NORM_INSTANCE) != 0;
+  const int flip = (a.flags & MRIACL_FLIP_ROWS) ? 1 : 0;
+  const int n_ent = (int)pl->r640.ent.size();
+  const int smem = row640_smem_bytes(std::max(1, n_act), n_ent, a.ow);
+  if (smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "640-wide row pass does not fit shared memory (n_act=%d ow=%d)", n_act, a.ow);
+  const int chunk = (int)std::min<size_t>((size_t)a.B, a.workspace_bytes / g.per_slice);
+  const size_t part_bytes = align_up((size_t)g.n_tiles8 * 3 * sizeof(float), 256);
+  for (int s0 = 0; s0 < a.B; s0 += chunk) {
+    const int ns = std::min(chunk, a.B - s0);
+    char* base = (char*)a.workspace;
+    cf* T = (cf*)base;
+    float* partials = (float*)(base + g.t_bytes * (size_t)chunk);
+    (void)part_bytes;
+    ColPassParams cp{};
+    cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = a.W;
+    cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
+    cp.tw = pl->twH; cp.T = T; cp.oh = a.oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
+    cp.frame0 = s0 * a.A * a.C; cp.n_frames = ns * a.A * a.C; cp.done = nullptr;
+    const long long col_items = (long long)cp.n_frames * n_groups;
+    if (col_items > 0) {
+      const int grid = (int)std::min<long long>(col_items, (long long)a.sms * 2);
+      MRIACL_LAUNCH(colpass640_ws_kernel, grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+    } else if (rt_memset_async(T, 0, g.t_bytes * (size_t)ns, a.st)) {
+      return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
+    }
+    Row640Params q{};
+    q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+    q.pos_off = pl->r640_off; q.ent = pl->r640_ent; q.n_ent = n_ent; q.tw = pl->twW;
+    q.out = a.out + (size_t)s0 * a.oh * a.ow; q.partials = partials; q.ow = a.ow; q.col0 = col0;
+    q.A = a.A; q.C = a.C; q.scale = (float)(1.0 / std::sqrt((double)a.H * (double)a.Wp));
+    q.n_slices = ns; q.n_tiles = g.n_tiles8;
+    const int per_sm = std::max(1, std::min(3, SMEM_MAX / smem));
+    MRIACL_LAUNCH(rowpass640_kernel, std::min(ns * g.n_tiles8, per_sm * a.sms), R640_T, smem, a.st, q);
+    if (want_norm || a.mean_std) {
+      NormParams np{};
+      np.in = q.out; np.out = q.out; np.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
+      np.partials = partials; np.n_part = g.n_tiles8; np.n = (long long)a.oh * a.ow; np.eps = a.eps;
+      np.normalize = want_norm ? 1 : 0;
+      np.n_split = want_norm ? std::max(1, std::min(16, (int)(np.n / 8192))) : 1;
+      MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
+    }
+  }
+  return 0;
+}
+
 // The fused 640x368 plan.  Two schedules:
 //  sequential  column pass (persistent, double-buffered gather) -> row pass (16 warps, one CTA per SM)
 //              -> normalise, back to back on the caller's stream, `chunk` slices per group;
@@ -418,7 +485,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
     n_bufs_ws = 1;
   }
   const size_t buf_bytes = g.per_slice * (size_t)chunk;
-  const size_t part_bytes = align_up((size_t)g.n_tiles16 * 3 * sizeof(float), 256);
+  const size_t part_bytes = align_up((size_t)g.n_tiles8 * 3 * sizeof(float), 256);
   // row-pass kernel: 0 = 32-row tiles (16 warps), 1 = 16-row tiles 12 warps x 2 CTAs/SM, 2 = 12 warps x 1, 3 = 16 warps x 1
   static const int rp16_cfg = env_int("MRIACL_RP16_CFG", 1);
 
@@ -751,7 +818,7 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
   if (g.fused) {
     FusedArgs fa{ksp, slice_stride, avg_stride, mask_w_host, out, mean_std, B, A, C, H, W, pad_left, Wp, oh, ow,
                  flags, eps, workspace, workspace_bytes, st, dev, sms};
-    if (int rc = run_fused(fa, g)) return rc;
+    if (int rc = (Wp == CP_N ? run_fused640(fa, g) : run_fused(fa, g))) return rc;
   } else {
     const float* mask_dev = nullptr;
     if (get_device_mask(dev, mask_w_host, W, &mask_dev)) return fail(MRIACL_ERR_CUDA, "mask upload failed: %s", rt_last_error_string());

@@ -334,6 +334,33 @@ inline void build_rowpair_plan(const FusedPlanHost& pl, int step, int ne, RowPai
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Plan of the 640-wide row pass (rowpass640.cuh): logical index n = 80 n1 + pos; for every butterfly position
+// pos the sampled inputs as entries n1 | (j << 3), sorted by n1.
+// ---------------------------------------------------------------------------------------
+struct Row640PlanHost {
+  std::vector<int> pos_off;   // [81]
+  std::vector<int> ent;
+};
+
+inline void build_row640_plan(const FusedPlanHost& pl, Row640PlanHost& rp) {
+  const int N = 640;
+  std::vector<std::vector<int>> per_pos(80);
+  for (int j = 0; j < (int)pl.act_w.size(); ++j) {
+    int n = pl.act_w[j] + pl.pad_left - N / 2;
+    if (n < 0) n += N;
+    per_pos[n % 80].push_back((n / 80) | (j << 3));
+  }
+  rp.pos_off.assign(81, 0);
+  rp.ent.clear();
+  for (int pos = 0; pos < 80; ++pos) {
+    std::sort(per_pos[pos].begin(), per_pos[pos].end(), [](int a, int b) { return (a & 7) < (b & 7); });
+    rp.pos_off[pos] = (int)rp.ent.size();
+    rp.ent.insert(rp.ent.end(), per_pos[pos].begin(), per_pos[pos].end());
+  }
+  rp.pos_off[80] = (int)rp.ent.size();
+}
+
 // FNV-1a over the plan-defining inputs: cache key for device-resident plans
 inline uint64_t plan_key(const int* dims, int n_dims, const float* mask, int mask_len) {
   uint64_t h = 1469598103934665603ull;
