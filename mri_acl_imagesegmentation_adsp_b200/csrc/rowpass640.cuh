@@ -7,10 +7,11 @@
 //   stage   the frame's [n_act][8 rows] block of the intermediate T (what the column pass wrote for the SAMPLED
 //           columns only) is copied with cp.async one frame ahead (two tiny buffers);
 //   pass 1  "expanding" radix-8: butterfly position pos = n mod 80 gathers its sampled inputs n = 80 n1 + pos from
-//           the staged block through the host plan -- all eight (a regular butterfly), none (the eight outputs are
-//           zero: nothing is loaded, zeros are stored) or a few (direct sum with w8 powers) -- so the zero padding
-//           and the unsampled columns cost stores but never loads or a memset;
-//   pass 2  radix-8 over n2, pass 3 radix-10 over n3 (as in the column pass);
+//           the staged block through the host plan -- all eight (a regular butterfly), a few (direct sum with w8
+//           powers) or none: then NOTHING is loaded or stored, because
+//   pass 2  (radix-8 over n2) knows from the same plan which of its eight inputs are empty positions and takes
+//           them as zero without touching shared memory -- the zero padding and the unsampled columns cost neither
+//           a memset nor loads nor stores; pass 3 is the radix-10 over n3 of the column pass;
 //   pass 3 does not store: each thread adds |X|^2 of its kept (fftshift + crop) columns to registers that live
 //           across the coil loop; at the end of an average sqrt(.) / sqrt(HW) is added to a [8][ow] tile in shared
 //           memory (mean over averages AFTER the RSS), and the tile leaves with coalesced stores plus its
@@ -91,6 +92,10 @@ __global__ void __launch_bounds__(R640_T, 3) rowpass640_kernel(Row640Params p) {
   }
   __syncthreads();
   const int e0 = plan[pos], e1 = plan[pos + 1], cnt = e1 - e0;
+  // pass 2 reads positions 10 n2 + (pos % 10), n2 = 0..7: bit n2 of present2 = that position has sampled inputs
+  int present2 = 0;
+#pragma unroll
+  for (int n2 = 0; n2 < 8; ++n2) present2 |= (plan[10 * n2 + pos % 10 + 1] > plan[10 * n2 + pos % 10]) ? (1 << n2) : 0;
   const int* ent = plan + 81;
   const int opitch = p.ow + 1;
   const int n_frames = p.A * p.C;
@@ -131,8 +136,7 @@ __global__ void __launch_bounds__(R640_T, 3) rowpass640_kernel(Row640Params p) {
       for (int kc = sub; kc < R640_ROWS; kc += 2) {
         cf* col = buf + kc * CP_PITCH + pos;
         if (cnt == 0) {
-#pragma unroll
-          for (int m1 = 0; m1 < 8; ++m1) col[m1 * CP_BLK] = cf_make(0.f, 0.f);
+          // empty position: pass 2 substitutes zeros (present2 below), nothing to do
         } else if (cnt == 8) {
           cf v[8];
 #pragma unroll
@@ -168,7 +172,11 @@ __global__ void __launch_bounds__(R640_T, 3) rowpass640_kernel(Row640Params p) {
         cf* colB = colA + 2 * CP_PITCH;
         cf va[8], vb[8];
 #pragma unroll
-        for (int n2 = 0; n2 < 8; ++n2) { va[n2] = colA[n2 * 10]; vb[n2] = colB[n2 * 10]; }
+        for (int n2 = 0; n2 < 8; ++n2) {
+          const bool has = (present2 >> n2) & 1;
+          va[n2] = has ? colA[n2 * 10] : cf_make(0.f, 0.f);
+          vb[n2] = has ? colB[n2 * 10] : cf_make(0.f, 0.f);
+        }
         radix8<true>(va);
         radix8<true>(vb);
         colA[0] = va[0];
