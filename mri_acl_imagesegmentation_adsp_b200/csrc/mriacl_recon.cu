@@ -20,6 +20,7 @@
 #include "rowpass16.cuh"
 #include "rowpair.cuh"
 #include "rowpass640.cuh"
+#include "rowpass_generic.cuh"
 #include "fused640x368.cuh"
 #include "coresident640x368.cuh"
 
@@ -87,6 +88,7 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 8, 3>, SMEM_MAX / 3);
   bad |= rt_allow_smem((const void*)rowpass640_kernel, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass_generic_kernel, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_kernel<FUSED_P, FUSED_Q>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_pair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 1>, SMEM_MAX / 2);
@@ -149,6 +151,8 @@ struct FusedPlanDev {
   cf* sptw16_dev = nullptr;
   int* sched_p12 = nullptr;
   int* sched_p16 = nullptr;
+  int* act_logical = nullptr;      // pruned generic row pass: logical index of active column j in the padded line
+  cf* twW_fwd = nullptr;           // forward-sign twiddles of the padded width (Stockham stages)
   Row640PlanHost r640;             // 640-wide row pass (Wp == 640 plans)
   int* r640_off = nullptr;
   int* r640_ent = nullptr;
@@ -217,6 +221,15 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     void* s5 = nullptr;
     if (rt_malloc(&s5, sizeof(int) * pl->pairs8.size()) || rt_upload(s5, pl->pairs8.data(), sizeof(int) * pl->pairs8.size())) return nullptr;
     pl->sched_p8 = (int*)s5;
+    if (Wp != CP_N && Wp != FUSED_P * FUSED_Q) {
+      std::vector<int> lg(std::max<size_t>(1, pl->host.act_w.size()), 0);
+      for (size_t j = 0; j < pl->host.act_w.size(); ++j) lg[j] = logical_of_phys(pl->host.act_w[j] + pad_left, Wp);
+      void* o = nullptr;
+      if (rt_malloc(&o, sizeof(int) * lg.size()) || rt_upload(o, lg.data(), sizeof(int) * lg.size())) return nullptr;
+      pl->act_logical = (int*)o;
+      pl->twW_fwd = get_twiddles(dev, Wp, -1);
+      if (!pl->twW_fwd) return nullptr;
+    }
     if (Wp == CP_N) {
       build_row640_plan(pl->host, pl->r640);
       void *o1 = nullptr, *o2 = nullptr;
@@ -248,6 +261,8 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
 }
 
 bool fused_shape(int H, int Wp) { return H == CP_N && (Wp == FUSED_P * FUSED_Q || Wp == CP_N); }
+// H = 640 with any other width: the fused column pass feeds the pruned generic row pass (rowpass_generic.cuh)
+bool pruned_shape(int H, int Wp) { return H == CP_N && !fused_shape(H, Wp) && Wp <= MRIACL_MAX_LINE; }
 
 struct ReconGeom {
   bool fused;
@@ -259,7 +274,7 @@ struct ReconGeom {
 
 int recon_geom(int A, int C, int H, int W, int pad_left, int Wp, int oh, int ow, const float* mask,
                unsigned flags, ReconGeom& g) {
-  g.fused = fused_shape(H, Wp) && !(flags & MRIACL_FORCE_GENERIC);
+  g.fused = (fused_shape(H, Wp) || pruned_shape(H, Wp)) && !(flags & MRIACL_FORCE_GENERIC);
   g.n_tiles = (oh + RP_ROWS - 1) / RP_ROWS;
   g.n_tiles16 = (oh + RP16_ROWS - 1) / RP16_ROWS;
   g.n_tiles8 = (oh + R640_ROWS - 1) / R640_ROWS;
@@ -269,7 +284,7 @@ int recon_geom(int A, int C, int H, int W, int pad_left, int Wp, int oh, int ow,
     g.n_act = n_act;
     const size_t ohp = (size_t)g.n_tiles * RP_ROWS;
     g.t_bytes = align_up((size_t)A * C * (size_t)(n_act > 0 ? n_act : 1) * ohp * sizeof(cf), 256);
-    g.per_slice = g.t_bytes + align_up((size_t)g.n_tiles8 * 3 * sizeof(float), 256) + 256;   // partials (finest tiling) + completion counter
+    g.per_slice = g.t_bytes + align_up((size_t)oh * 3 * sizeof(float), 256) + 256;   // partials (finest tiling: one row per tile) + completion counter
   } else {
     g.n_act = W;
     g.t_bytes = align_up((size_t)A * C * H * Wp * sizeof(cf), 256);
@@ -353,10 +368,12 @@ struct FusedArgs {
   void* workspace; size_t workspace_bytes; rt_stream_t st; int dev, sms;
 };
 
-// The 640 x 640 plans (prostate-shape): column pass -> 640-wide row pass -> normalise, back to back.
+// The 640 x 640 plans (prostate-shape) and every other width behind the H = 640 column pass:
+// column pass -> 640-wide row pass / pruned generic row pass -> normalise, back to back.
 int run_fused640(const FusedArgs& a, const ReconGeom& g) {
   std::shared_ptr<FusedPlanDev> pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
-  if (!pl || !pl->r640_off) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
+  const bool wide640 = a.Wp == CP_N;
+  if (!pl || (wide640 ? !pl->r640_off : !pl->act_logical)) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
   const int n_act = (int)pl->host.act_w.size();
   const int n_groups = (n_act + CP_G - 1) / CP_G;
   const int ohp = g.n_tiles * RP_ROWS;
@@ -364,10 +381,15 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
   const bool want_norm = (a.flags & MRIACL_NORM_INSTANCE) != 0;
   const int flip = (a.flags & MRIACL_FLIP_ROWS) ? 1 : 0;
   const int n_ent = (int)pl->r640.ent.size();
-  const int smem = row640_smem_bytes(std::max(1, n_act), n_ent, a.ow);
-  if (smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "640-wide row pass does not fit shared memory (n_act=%d ow=%d)", n_act, a.ow);
+  int rg_lines = 8;        // pruned generic row pass: lines per item, halved until the two line buffers + tiles fit
+  while (!wide640 && rg_lines > 1 && rowgen_smem_bytes(a.Wp, rg_lines, a.ow) > SMEM_MAX / 3) rg_lines /= 2;
+  const int smem = wide640 ? row640_smem_bytes(std::max(1, n_act), n_ent, a.ow) : rowgen_smem_bytes(a.Wp, rg_lines, a.ow);
+  if (smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "row pass does not fit shared memory (Wp=%d n_act=%d ow=%d)", a.Wp, n_act, a.ow);
+  const std::vector<int> rad = generic_radices(a.Wp);
+  if (!wide640 && (int)rad.size() > RG_MAX_STAGES) return fail(MRIACL_ERR_UNSUPPORTED, "too many FFT stages for N=%d", a.Wp);
+  const int n_tiles_row = wide640 ? g.n_tiles8 : (a.oh + rg_lines - 1) / rg_lines;
   const int chunk = (int)std::min<size_t>((size_t)a.B, a.workspace_bytes / g.per_slice);
-  const size_t part_bytes = align_up((size_t)g.n_tiles8 * 3 * sizeof(float), 256);
+  const size_t part_bytes = align_up((size_t)a.oh * 3 * sizeof(float), 256);
   for (int s0 = 0; s0 < a.B; s0 += chunk) {
     const int ns = std::min(chunk, a.B - s0);
     char* base = (char*)a.workspace;
@@ -386,18 +408,32 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
     } else if (rt_memset_async(T, 0, g.t_bytes * (size_t)ns, a.st)) {
       return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
     }
-    Row640Params q{};
-    q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
-    q.pos_off = pl->r640_off; q.ent = pl->r640_ent; q.n_ent = n_ent; q.tw = pl->twW;
-    q.out = a.out + (size_t)s0 * a.oh * a.ow; q.partials = partials; q.ow = a.ow; q.col0 = col0;
-    q.A = a.A; q.C = a.C; q.scale = (float)(1.0 / std::sqrt((double)a.H * (double)a.Wp));
-    q.n_slices = ns; q.n_tiles = g.n_tiles8;
+    float* out_s0 = a.out + (size_t)s0 * a.oh * a.ow;
+    const float scale = (float)(1.0 / std::sqrt((double)a.H * (double)a.Wp));
     const int per_sm = std::max(1, std::min(3, SMEM_MAX / smem));
-    MRIACL_LAUNCH(rowpass640_kernel, std::min(ns * g.n_tiles8, per_sm * a.sms), R640_T, smem, a.st, q);
+    if (wide640) {
+      Row640Params q{};
+      q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+      q.pos_off = pl->r640_off; q.ent = pl->r640_ent; q.n_ent = n_ent; q.tw = pl->twW;
+      q.out = out_s0; q.partials = partials; q.ow = a.ow; q.col0 = col0;
+      q.A = a.A; q.C = a.C; q.scale = scale;
+      q.n_slices = ns; q.n_tiles = n_tiles_row;
+      MRIACL_LAUNCH(rowpass640_kernel, std::min(ns * n_tiles_row, per_sm * a.sms), R640_T, smem, a.st, q);
+    } else {
+      RowGenParams q{};
+      q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+      q.act_logical = pl->act_logical; q.tw = pl->twW_fwd; q.N = a.Wp; q.L = rg_lines;
+      q.out = out_s0; q.partials = partials; q.ow = a.ow; q.col0 = col0;
+      q.A = a.A; q.C = a.C; q.scale = scale;
+      q.n_slices = ns; q.n_tiles = n_tiles_row;
+      q.n_stages = (int)rad.size();
+      for (int i = 0; i < q.n_stages; ++i) q.radix[i] = rad[i];
+      MRIACL_LAUNCH(rowpass_generic_kernel, std::min(ns * n_tiles_row, per_sm * a.sms), RG_T, smem, a.st, q);
+    }
     if (want_norm || a.mean_std) {
       NormParams np{};
-      np.in = q.out; np.out = q.out; np.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
-      np.partials = partials; np.n_part = g.n_tiles8; np.n = (long long)a.oh * a.ow; np.eps = a.eps;
+      np.in = out_s0; np.out = out_s0; np.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
+      np.partials = partials; np.n_part = n_tiles_row; np.n = (long long)a.oh * a.ow; np.eps = a.eps;
       np.normalize = want_norm ? 1 : 0;
       np.n_split = want_norm ? std::max(1, std::min(16, (int)(np.n / 8192))) : 1;
       MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
@@ -485,7 +521,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
     n_bufs_ws = 1;
   }
   const size_t buf_bytes = g.per_slice * (size_t)chunk;
-  const size_t part_bytes = align_up((size_t)g.n_tiles8 * 3 * sizeof(float), 256);
+  const size_t part_bytes = align_up((size_t)a.oh * 3 * sizeof(float), 256);
   // row-pass kernel: 0 = 32-row tiles (16 warps), 1 = 16-row tiles 12 warps x 2 CTAs/SM, 2 = 12 warps x 1, 3 = 16 warps x 1
   static const int rp16_cfg = env_int("MRIACL_RP16_CFG", 1);
 
@@ -818,7 +854,7 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
   if (g.fused) {
     FusedArgs fa{ksp, slice_stride, avg_stride, mask_w_host, out, mean_std, B, A, C, H, W, pad_left, Wp, oh, ow,
                  flags, eps, workspace, workspace_bytes, st, dev, sms};
-    if (int rc = (Wp == CP_N ? run_fused640(fa, g) : run_fused(fa, g))) return rc;
+    if (int rc = (Wp == FUSED_P * FUSED_Q ? run_fused(fa, g) : run_fused640(fa, g))) return rc;
   } else {
     const float* mask_dev = nullptr;
     if (get_device_mask(dev, mask_w_host, W, &mask_dev)) return fail(MRIACL_ERR_CUDA, "mask upload failed: %s", rt_last_error_string());
@@ -846,7 +882,7 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
 size_t mriacl_ifft2c_abs_workspace_bytes(int B, int H, int W) {
   if (B < 1) B = 1;
   if (H < 1 || W < 1) return 0;
-  if (fused_shape(H, W)) return mriacl_recon_rss_workspace_bytes(B, 1, 1, H, W, 0, W, H, W, nullptr, 0);
+  if (fused_shape(H, W) || pruned_shape(H, W)) return mriacl_recon_rss_workspace_bytes(B, 1, 1, H, W, 0, W, H, W, nullptr, 0);
   return align_up((size_t)B * H * W * sizeof(cf), 256);
 }
 

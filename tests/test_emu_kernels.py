@@ -195,6 +195,21 @@ def test_fused_640_wide_plan(emu):
     assert O.rel_l2(raw[0], ref) <= TOL
 
 
+def test_pruned_generic_row_pass(emu):
+    """H = 640 with a width that has no specialised row kernel (372): fused column pass + pruned generic row pass
+    (Stockham on the kept rows only, RSS / averages / crop fused) against the full generic path and the oracle."""
+    k = synth.gaussian_kspace((1, 2, 2, 640, 372), 43)
+    m = synth.equispaced_mask(372, 4, 0.08)
+    out, ms = recon(emu, k, m, (320, 320), cabi.NORM_INSTANCE)
+    gen, gms = recon(emu, k, m, (320, 320), cabi.NORM_INSTANCE | cabi.FORCE_GENERIC)
+    assert O.rel_l2(out, gen) <= TOL
+    np.testing.assert_allclose(ms, gms, rtol=1e-5)
+    raw, _ = recon(emu, k, None, (75, 372), cabi.FLIP_ROWS)          # ragged last tile, full width, fully sampled
+    ims = [np.flipud(np.sqrt((O.complex_abs(O.ifft2c(k[0, a])) ** 2).sum(0))) for a in range(2)]
+    ref = O.center_crop(np.mean(ims, axis=0), (75, 372)).astype(np.float32)
+    assert O.rel_l2(raw[0], ref) <= TOL
+
+
 def test_pair_row_pass(emu, golden):
     """the pair row pass (rowpair.cuh: per-output-pair transform, stager warp, rotated residue-major tile) against
     the oracle and the cooperative row pass, incl. an odd crop, a shifted mask offset and a mask outside its family."""

@@ -237,6 +237,23 @@ def test_pair_row_pass_schedule():
     assert torch.equal(a, b)
 
 
+def test_other_widths_behind_the_640_column_pass():
+    """640 x 372 / 640 x 320 knee files (no specialised row kernel): fused column pass + pruned generic row pass,
+    against the oracle's numpy chain and the full generic path; chunking never changes a slice."""
+    for W, seed in ((372, 61), (320, 62)):
+        k_np = synth.gaussian_kspace((3, 15, 640, W), seed)
+        k = torch.from_numpy(k_np).cuda()
+        m = synth.equispaced_mask(W, 4, 0.08)
+        out, mean, std = zero_filled_rss(k, m, (320, 320), "instance")
+        want, wmean, wstd = O.knee_chain_numpy(k_np[1], m, (320, 320), "instance")
+        assert O.rel_l2(out[1].cpu().numpy(), want) <= TOL
+        np.testing.assert_allclose([float(mean[1]), float(std[1])], [float(wmean), float(wstd)], rtol=1e-5)
+        gen, _, _ = zero_filled_rss(k, m, (320, 320), "instance", force_generic=True)
+        assert O.rel_l2(out.cpu().numpy(), gen.cpu().numpy()) <= 2e-6
+        c1, _, _ = zero_filled_rss(k, m, (320, 320), "instance", chunk_slices=1)
+        assert torch.equal(c1, out)
+
+
 def test_fused_variants_against_oracle():
     rng = np.random.default_rng(5)
     k = synth.gaussian_kspace((2, 2, 3, 640, 368), 7)       # (S, A, C, H, W)
