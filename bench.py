@@ -384,7 +384,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--chunk", type=int, default=0, help="slices in flight per launch group (0 = library default)")
-    ap.add_argument("--sub-batch", type=int, default=8, help="slices per host->device copy in the e2e pipeline")
+    ap.add_argument("--sub-batch", type=int, default=32, help="slices per host->device copy in the e2e pipeline")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
