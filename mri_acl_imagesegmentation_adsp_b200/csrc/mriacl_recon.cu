@@ -716,6 +716,8 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
         q.n_buf = 2;
         q.l2_hints = pipelined ? 1 : 0;
+        static const int rp_reverse = env_int("MRIACL_RP_REVERSE", 1);
+        q.reverse = (rp_reverse && do_col) ? 1 : 0;
         if (fuse_norm) {
           q.tiles_done = counters;
           q.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;

@@ -42,6 +42,8 @@ struct RowPass16Params {
   float eps;
   int normalize;         // 1: (x - mean) / (std + eps) in place
   int l2_hints;          // 1: T is read with an evict_last hint (chunk-pipelined schedule)
+  int reverse;           // 1: take the slices last-to-first: the column pass wrote them first-to-last, so the most
+                         //    recently written part of T is still in L2 when the row pass starts (sequential schedule)
 };
 
 inline int rowpass16_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_act, int n_buf, int ow, int A) {
@@ -138,7 +140,8 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
 
   {
 
-    const int s = item / p.n_tiles, tile = item - s * p.n_tiles;
+    const int s_fwd = item / p.n_tiles, tile = item - s_fwd * p.n_tiles;
+    const int s = p.reverse ? p.n_slices - 1 - s_fwd : s_fwd;
     const cf* Tit = p.T + (long long)s * n_frames * frame_elems + tile * RP16_ROWS;
 
     const cf* src0 = Tit + (long long)(tid >> 3) * p.ohp + 2 * (tid & 7);
@@ -344,7 +347,7 @@ __device__ __forceinline__ float4 rp16_ld_cg4(const float4* p) {
 template <int NW, int BAR>
 __device__ __forceinline__ void rowpass16_finish_slice(const RowPass16Params& r, int item, int t, float* s_stat, int* s_last) {
   constexpr int NT = NW * 32;
-  const int s = item / r.n_tiles;
+  const int s = r.reverse ? r.n_slices - 1 - item / r.n_tiles : item / r.n_tiles;
   __threadfence();
   rp16_sync<BAR, NT>();
   if (t == 0) {
