@@ -653,6 +653,8 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
     } else if (!overlap) {
       rt_stream_t row_st = pipelined ? ov->side : a.st;
+      static const int seq_hints = env_int("MRIACL_SEQ_L2_HINTS", 0);
+      if (seq_hints && !pipelined) cp.l2_hints = 1;
       if (pipelined) {
         cp.l2_hints = 1;
         // T buffer wb: its previous reader (row pass of group - 2) must be done
@@ -715,7 +717,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
         q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
         q.n_buf = 2;
-        q.l2_hints = pipelined ? 1 : 0;
+        q.l2_hints = (pipelined || seq_hints) ? 1 : 0;
         static const int rp_reverse = env_int("MRIACL_RP_REVERSE", 1);
         q.reverse = (rp_reverse && do_col) ? 1 : 0;
         if (fuse_norm) {
