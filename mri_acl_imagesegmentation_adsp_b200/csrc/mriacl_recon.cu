@@ -716,18 +716,20 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size();
         q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
         q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
-        q.n_buf = 2;
+        static const int rp_nbuf = std::min(3, std::max(1, env_int("MRIACL_RP_NBUF", 3)));
+        q.n_buf = rp_nbuf;
         q.l2_hints = (pipelined || seq_hints) ? 1 : 0;
         static const int rp_reverse = env_int("MRIACL_RP_REVERSE", 1);
         q.reverse = (rp_reverse && do_col) ? 1 : 0;
+        q.debug_skip = env_int("MRIACL_RP_DEBUG_SKIP", 0);
         if (fuse_norm) {
           q.tiles_done = counters;
           q.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
           q.eps = a.eps; q.normalize = want_norm ? 1 : 0;
         }
-        int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
+        int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, q.n_buf, a.ow, a.A);
         const int limit = rp16_cfg == 1 ? SMEM_MAX / 2 : rp16_cfg == 4 ? SMEM_MAX / 3 : SMEM_MAX;
-        if (smem16 > limit) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
+        while (smem16 > limit && q.n_buf > 1) { --q.n_buf; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, q.n_buf, a.ow, a.A); }
         if (smem16 > limit) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
         const int items16 = ns * g.n_tiles16;
         np.n_part = g.n_tiles16;

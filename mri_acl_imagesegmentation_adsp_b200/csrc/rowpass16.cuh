@@ -42,6 +42,7 @@ struct RowPass16Params {
   float eps;
   int normalize;         // 1: (x - mean) / (std + eps) in place
   int l2_hints;          // 1: T is read with an evict_last hint (chunk-pipelined schedule)
+  int debug_skip;        // profiling only (results are garbage): 1 = no stage 1, 2 = no stage 2, 4 = no T prefetch
   int reverse;           // 1: take the slices last-to-first: the column pass wrote them first-to-last, so the most
                          //    recently written part of T is still in L2 when the row pass starts (sequential schedule)
 };
@@ -152,7 +153,8 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
     auto prefetch = [&](int f, int buf) {
       const cf* src = src0 + (long long)f * frame_elems;
       cf* dst = dst0 + (size_t)buf * tile_elems;
-      if (p.l2_hints) {
+      if (p.debug_skip & 4) {
+      } else if (p.l2_hints) {
 #pragma unroll 1
         for (int i = 0; i < n_iter; ++i) {
           cp_async16_hint(dst, src, pol_t);
@@ -180,18 +182,24 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
     }
     if (p.A > 1) for (int i = tid; i < RP16_ROWS * opitch; i += NT) avsm[i] = 0.f;
     prefetch(0, 0);
+    if (p.n_buf == 3) { if (n_frames > 1) prefetch(1, 1); else cp_async_commit(); }
 
     float acc[KPW][Q];
     int coil = 0;
     for (int f = 0; f < n_frames; ++f) {
-      const int buf = p.n_buf == 2 ? (f & 1) : 0;
+      const int buf = p.n_buf == 3 ? f % 3 : p.n_buf == 2 ? (f & 1) : 0;
       if (coil == 0) {
 #pragma unroll
         for (int kk = 0; kk < KPW; ++kk)
 #pragma unroll
           for (int k2 = 0; k2 < Q; ++k2) acc[kk][k2] = 0.f;
       }
-      if (p.n_buf == 2) {
+      if (p.n_buf == 3) {
+        // two frames ahead: the block of frame f+2 goes where frame f-1 was (all its readers passed the stage-1 barrier);
+        // one (possibly empty) group is committed per frame, so "at most 2 pending" means frame f has landed
+        if (f + 2 < n_frames) prefetch(f + 2, (f + 2) % 3); else cp_async_commit();
+        cp_async_wait<2>();
+      } else if (p.n_buf == 2) {
         if (f + 1 < n_frames) { prefetch(f + 1, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
       } else {
         cp_async_wait<0>();
@@ -201,7 +209,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
       // ---------------- stage 1: two units per warp ----------------
       {
         const cf* tb = tbuf + (size_t)buf * tile_elems + r;
-        const int n_pairs = schsm[my_off];
+        const int n_pairs = (p.debug_skip & 1) ? 0 : schsm[my_off];
         int off = my_off + 1;
         for (int u = 0; u < n_pairs; ++u, off += 4) {
           const int type = schsm[off], nnz = schsm[off + 1];
@@ -245,7 +253,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
       for (int kk = 0; kk < KPW; ++kk) {
         const int pair = warp + NW * kk;
         const int k1 = 2 * pair + half;
-        if (pair < NPAIR) {
+        if (pair < NPAIR && !(p.debug_skip & 2)) {
           const int k1c = k1 < P ? k1 : P - 1;           // odd P: the last pair has one idle half
           cf v[Q];
           const cf* yrow = Y + k1c * YS + r;
@@ -276,6 +284,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
       }
     }
     rp16_sync<BAR, NT>();
+    if (p.debug_skip & 8) return;
     if (p.A == 1) {
 #pragma unroll
       for (int kk = 0; kk < KPW; ++kk) {
@@ -297,23 +306,34 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
     const int rows_here = min(RP16_ROWS, p.oh - tile * RP16_ROWS);
     const int n_here = rows_here * p.ow;
     float* dst = p.out + ((long long)s * p.oh + tile * RP16_ROWS) * p.ow;
+    // each thread keeps its share of the tile (elements tid, tid + NT, ...) in registers for the statistics pass;
+    // (row, column) advance incrementally: no integer division in the loops
+    constexpr int VMAX = (RP16_ROWS * N + NT - 1) / NT;
+    float vals[VMAX];
+    const int step_r = NT / p.ow, step_c = NT - step_r * p.ow;
+    int rr = tid / p.ow, cc = tid - rr * p.ow;
     float lsum = 0.f;
-    for (int e = tid; e < n_here; e += NT) {
-      const int rr = e / p.ow, cc = e - rr * p.ow;
-      float v = tile_sm[rr * opitch + cc];
-      if (p.A > 1) v *= inv_a;
-      dst[e] = v;
-      lsum += v;
+#pragma unroll
+    for (int i = 0; i < VMAX; ++i) {
+      const int e = tid + i * NT;
+      float v = 0.f;
+      if (e < n_here) {
+        v = tile_sm[rr * opitch + cc];
+        if (p.A > 1) v *= inv_a;
+        dst[e] = v;
+        lsum += v;
+      }
+      vals[i] = v;
+      rr += step_r; cc += step_c;
+      if (cc >= p.ow) { cc -= p.ow; ++rr; }
     }
     if (p.partials) {
       const float mean = rp16_team_sum<NW, BAR>(lsum, red, tid) / (float)n_here;
       float lq = 0.f;
-      for (int e = tid; e < n_here; e += NT) {
-        const int rr = e / p.ow, cc = e - rr * p.ow;
-        float v = tile_sm[rr * opitch + cc];
-        if (p.A > 1) v *= inv_a;
-        const float d = v - mean;
-        lq = fmaf(d, d, lq);
+#pragma unroll
+      for (int i = 0; i < VMAX; ++i) {
+        const float d = vals[i] - mean;
+        if (tid + i * NT < n_here) lq = fmaf(d, d, lq);
       }
       const float m2 = rp16_team_sum<NW, BAR>(lq, red, tid);
       if (tid == 0) {
