@@ -149,6 +149,9 @@ struct FusedPlanDev {
   int* sched_p8 = nullptr;
   std::vector<HostCf> sptw16;
   cf* sptw16_dev = nullptr;
+  std::vector<int> rp16_slot_of_j;     // residue-major staged tile of the 16-row row pass
+  int rp16_slots = 0;
+  int* rp16_slot_dev = nullptr;
   int* sched_p12 = nullptr;
   int* sched_p16 = nullptr;
   int* act_logical = nullptr;      // pruned generic row pass: logical index of active column j in the padded line
@@ -207,7 +210,13 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     if (rt_malloc(&s2, sizeof(int) * pl->host_ovl.sched.size()) ||
         rt_upload(s2, pl->host_ovl.sched.data(), sizeof(int) * pl->host_ovl.sched.size())) return nullptr;
     pl->sched_ovl = (int*)s2;
-    build_pair_schedule(pl->host, 12, pl->pairs12, pl->sptw16);
+    build_pair_schedule(pl->host, 12, pl->pairs12, pl->sptw16, &pl->rp16_slot_of_j, &pl->rp16_slots);
+    {
+      void* sj = nullptr;
+      const size_t nb = sizeof(int) * std::max<size_t>(1, pl->rp16_slot_of_j.size());
+      if (rt_malloc(&sj, nb) || (!pl->rp16_slot_of_j.empty() && rt_upload(sj, pl->rp16_slot_of_j.data(), sizeof(int) * pl->rp16_slot_of_j.size()))) return nullptr;
+      pl->rp16_slot_dev = (int*)sj;
+    }
     build_pair_schedule(pl->host, 16, pl->pairs16, pl->sptw16);
     void *s3 = nullptr, *s4 = nullptr, *t16 = nullptr;
     if (rt_malloc(&t16, sizeof(HostCf) * pl->sptw16.size()) ||
@@ -602,13 +611,13 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       RowPass16Params& q = kp.rp;
       q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
       q.sched = pl->sched_p12; q.sched_len = (int)pl->pairs12.size();
-      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size();
+      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size(); q.n_slots = pl->rp16_slots; q.slot_of_j = pl->rp16_slot_dev;
       q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
       q.n_slices = ns; q.n_tiles = g.n_tiles16;
       q.done = counters; q.done_target = a.A * a.C * n_groups; q.error_flag = ov->error_flag;
       q.n_buf = 2;
-      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
-      if (CP_SMEM_BYTES_DB + smem16 > SMEM_MAX) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
+      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 2, a.ow, a.A);
+      if (CP_SMEM_BYTES_DB + smem16 > SMEM_MAX) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 1, a.ow, a.A); }
       if (CP_SMEM_BYTES_DB + smem16 > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "co-resident tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
       if (want_norm || a.mean_std) {
         q.tiles_done = counters + ns;
@@ -633,12 +642,12 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       RowPass16Params& q = fp.rp;
       q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
       q.sched = pl->sched_p8; q.sched_len = (int)pl->pairs8.size();
-      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size();
+      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size(); q.n_slots = pl->rp16_slots; q.slot_of_j = pl->rp16_slot_dev;
       q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
       q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
       q.n_buf = 2;
-      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
-      if (smem16 > SMEM_MAX / 2) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
+      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 2, a.ow, a.A);
+      if (smem16 > SMEM_MAX / 2) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 1, a.ow, a.A); }
       const int fz_smem = std::max(smem16, CP_SMEM_BYTES_DB);
       if (fz_smem > SMEM_MAX / 2) return fail(MRIACL_ERR_UNSUPPORTED, "fused tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
       fp.state = counters + ns;            // two ints after the per-slice counters (the region is 64 ints per slice)
@@ -713,7 +722,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
         q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
         q.sched = w16 ? pl->sched_p16 : w8 ? pl->sched_p8 : pl->sched_p12;
         q.sched_len = (int)(w16 ? pl->pairs16.size() : w8 ? pl->pairs8.size() : pl->pairs12.size());
-        q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size();
+        q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size(); q.n_slots = pl->rp16_slots; q.slot_of_j = pl->rp16_slot_dev;
         q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
         q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
         static const int rp_nbuf = std::min(3, std::max(1, env_int("MRIACL_RP_NBUF", 3)));
@@ -727,9 +736,9 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
           q.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
           q.eps = a.eps; q.normalize = want_norm ? 1 : 0;
         }
-        int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, q.n_buf, a.ow, a.A);
+        int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, q.n_buf, a.ow, a.A);
         const int limit = rp16_cfg == 1 ? SMEM_MAX / 2 : rp16_cfg == 4 ? SMEM_MAX / 3 : SMEM_MAX;
-        while (smem16 > limit && q.n_buf > 1) { --q.n_buf; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, q.n_buf, a.ow, a.A); }
+        while (smem16 > limit && q.n_buf > 1) { --q.n_buf; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, q.n_buf, a.ow, a.A); }
         if (smem16 > limit) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
         const int items16 = ns * g.n_tiles16;
         np.n_part = g.n_tiles16;
@@ -762,13 +771,13 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       RowPass16Params q{};
       q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
       q.sched = pl->sched_p12; q.sched_len = (int)pl->pairs12.size();
-      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size();
+      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size(); q.n_slots = pl->rp16_slots; q.slot_of_j = pl->rp16_slot_dev;
       q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
       q.n_slices = ns; q.n_tiles = g.n_tiles16;
       q.done = counters; q.done_target = a.A * a.C * n_groups; q.error_flag = ov->error_flag;
       q.n_buf = 2;
-      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 2, a.ow, a.A);
-      if (smem16 > SMEM_MAX / 2) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, n_act, 1, a.ow, a.A); }
+      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 2, a.ow, a.A);
+      if (smem16 > SMEM_MAX / 2) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 1, a.ow, a.A); }
       if (smem16 > SMEM_MAX / 2) return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
       np.n_part = g.n_tiles16;
       const int items16 = ns * g.n_tiles16;

@@ -155,7 +155,12 @@ inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow,
 //   sptw16 = the sparse twiddle rows followed by one row w_N^{n2 k1} per dense residue
 //   an idle second half-warp (offB = -1) repeats unit A but stores into the spare residue column n2 = Q
 // Built from the 32-row schedule's units (same columns, same sptw rows), so both kernels do the same arithmetic.
-inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vector<int>& out, std::vector<HostCf>& sptw16) {
+// The staged tile of the 16-row kernel is RESIDUE-MAJOR: a dense residue owns P consecutive slots (slot = base + n1,
+// unsampled positions stay zero), the sparse residues' columns follow; `slot_of_j` maps active column j to its slot
+// (used by the cp.async prefetch), so every first-stage operand sits at an immediate offset from one base.
+//   dense payload: n2, twiddle-row offset, base slot        sparse payload: n2, twiddle-row offset, nnz slots
+inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vector<int>& out, std::vector<HostCf>& sptw16,
+                                std::vector<int>* slot_of_j = nullptr, int* n_slots_out = nullptr) {
   // recover the units from the 32-row schedule
   struct U { int n2, type, nnz; std::vector<int> payload; double cost; };
   std::vector<U> units;
@@ -230,6 +235,21 @@ inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vecto
       if (pr.b >= 0) { patch.push_back({(int)out.size(), pr.b}); out.push_back(0); } else out.push_back(-1);
     }
   }
+  // slot layout (identical for every n_warps: it only depends on the units)
+  std::vector<int> slots(pl.act_w.size(), -1), dense_base(pl.Q, -1);
+  int n_slots = 0;
+  for (int n2 = 0; n2 < pl.Q; ++n2)
+    for (auto& u : units)
+      if (u.type != 0 && u.n2 == n2 && dense_base[n2] < 0) {
+        dense_base[n2] = n_slots;
+        for (int n1 = 0; n1 < pl.P; ++n1) if (u.payload[n1] >= 0) slots[u.payload[n1]] = n_slots + n1;
+        n_slots += pl.P;
+      }
+  for (auto& u : units)
+    if (u.type == 0)
+      for (int e = 0; e < u.nnz; ++e) if (slots[u.payload[1 + e]] < 0) slots[u.payload[1 + e]] = n_slots++;
+  if (slot_of_j) *slot_of_j = slots;
+  if (n_slots_out) *n_slots_out = n_slots;
   std::vector<int> unit_off(units.size(), -1);
   for (auto& pu : patch) {
     if (unit_off[pu.second] < 0) {
@@ -237,10 +257,10 @@ inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vecto
       out.push_back(units[pu.second].n2);
       if (units[pu.second].type != 0) {
         out.push_back(dense_row[units[pu.second].n2]);
-        // unsampled positions of a dense residue read the all-zero column n_act of the staged block
-        for (int j : units[pu.second].payload) out.push_back(j >= 0 ? j : (int)pl.act_w.size());
+        out.push_back(dense_base[units[pu.second].n2]);
       } else {
-        out.insert(out.end(), units[pu.second].payload.begin(), units[pu.second].payload.end());
+        out.push_back(units[pu.second].payload[0]);
+        for (int e = 0; e < units[pu.second].nnz; ++e) out.push_back(slots[units[pu.second].payload[1 + e]]);
       }
     }
     out[pu.first] = unit_off[pu.second];

@@ -22,6 +22,8 @@ constexpr int RP16_ROWS = 16;
 struct RowPass16Params {
   const cf* T;           // [n_slices*A*C][n_act][ohp]
   int n_act, oh, ohp;
+  int n_slots;           // slots of the residue-major staged tile (>= n_act; slots without a column stay zero)
+  const int* slot_of_j;  // [n_act]
   const int* sched;      // pair schedule, see plan.h (build_pair_schedule)
   int sched_len;
   const cf* sptw;        // sparse twiddle rows followed by the dense residues' rows w_N^{n2 k1} (pitch 24)
@@ -41,15 +43,15 @@ struct RowPass16Params {
   float* mean_std;       // [n_slices][2] or nullptr
   float eps;
   int normalize;         // 1: (x - mean) / (std + eps) in place
-  int l2_hints;          // 1: T is read with an evict_last hint (chunk-pipelined schedule)
+  int l2_hints;          // unused by this kernel (kept for the launch code; the hint applies to the column pass only)
   int debug_skip;        // profiling only (results are garbage): 1 = no stage 1, 2 = no stage 2, 4 = no T prefetch
   int reverse;           // 1: take the slices last-to-first: the column pass wrote them first-to-last, so the most
                          //    recently written part of T is still in L2 when the row pass starts (sequential schedule)
 };
 
-inline int rowpass16_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_act, int n_buf, int ow, int A) {
-  return P * (Q + 1) * RP16_ROWS * 8 + rp_round16(sptw_len * 8) + rp_round16(sched_len * 4) +
-         n_buf * (n_act + 1) * RP16_ROWS * 8 + (A > 1 ? RP16_ROWS * (ow + 1) * 4 : 0);
+inline int rowpass16_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_slots, int n_buf, int ow, int A) {
+  return P * (Q + 1) * RP16_ROWS * 8 + rp_round16(sptw_len * 8) + rp_round16(sched_len * 4) + rp_round16(n_slots * 4) +
+         n_buf * (n_slots + 1) * RP16_ROWS * 8 + (A > 1 ? RP16_ROWS * (ow + 1) * 4 : 0);
 }
 
 // team barrier: BAR = 0 is the CTA barrier; BAR > 0 a named barrier over the NT threads of a sub-CTA team
@@ -93,14 +95,15 @@ __device__ __forceinline__ void rp16_sparse_unit(const int* pay, const cf* tb, c
 
 // shared-memory carve-up of one row-pass CTA
 template <int P, int Q> struct Rp16Smem {
-  cf* Y; cf* sptw; int* sch; cf* tbuf; float* av; float* osm;
+  cf* Y; cf* sptw; int* sch; int* slot; cf* tbuf; float* av; float* osm;
   __device__ __forceinline__ Rp16Smem(void* base, const RowPass16Params& p) {
     constexpr int YS = (Q + 1) * RP16_ROWS;
     Y = reinterpret_cast<cf*>(base);                                     // [P][Q + 1][16]
     sptw = Y + P * YS;
     sch = reinterpret_cast<int*>(reinterpret_cast<char*>(sptw) + rp_round16(p.sptw_len * 8));
-    tbuf = reinterpret_cast<cf*>(reinterpret_cast<char*>(sch) + rp_round16(p.sched_len * 4));   // [n_buf][n_act + 1][16], last column zero
-    av = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * (p.n_act + 1) * RP16_ROWS);
+    slot = reinterpret_cast<int*>(reinterpret_cast<char*>(sch) + rp_round16(p.sched_len * 4));  // [n_act] (room for n_slots)
+    tbuf = reinterpret_cast<cf*>(reinterpret_cast<char*>(slot) + rp_round16(p.n_slots * 4));    // [n_buf][n_slots + 1][16], residue-major
+    av = reinterpret_cast<float*>(tbuf + (size_t)p.n_buf * (p.n_slots + 1) * RP16_ROWS);
     osm = reinterpret_cast<float*>(Y);                                   // output tile [16][ow+1], aliases Y
   }
 };
@@ -109,8 +112,11 @@ template <int P, int Q> struct Rp16Smem {
 template <int NT> __device__ __forceinline__ void rp16_load_tables(const RowPass16Params& p, cf* sptwsm, int* schsm, cf* tbuf, int tid) {
   for (int i = tid; i < p.sched_len; i += NT) schsm[i] = p.sched[i];
   for (int i = tid; i < p.sptw_len; i += NT) sptwsm[i] = p.sptw[i];
-  if (tid < p.n_buf * RP16_ROWS)       // the zero column of every staging buffer
-    tbuf[((size_t)(tid / RP16_ROWS) * (p.n_act + 1) + p.n_act) * RP16_ROWS + tid % RP16_ROWS] = cf_make(0.f, 0.f);
+  int* slotsm = reinterpret_cast<int*>(reinterpret_cast<char*>(schsm) + rp_round16(p.sched_len * 4));
+  for (int i = tid; i < p.n_act; i += NT) slotsm[i] = p.slot_of_j[i];
+  // slots no column fills (unsampled positions of dense residues, the spare column) must read as zero: the
+  // prefetch never writes them, so clearing the staging buffers once is enough
+  for (int i = tid; i < p.n_buf * (p.n_slots + 1) * RP16_ROWS; i += NT) tbuf[i] = cf_make(0.f, 0.f);
 }
 
 // one work item = (slice, 16-row tile); called by all NW*32 threads of the (sub-)CTA; tables already loaded
@@ -136,7 +142,8 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
   const int my_off = schsm[warp];
   const int n_frames = p.A * p.C;
   const long long frame_elems = (long long)p.n_act * p.ohp;
-  const int tile_elems = (p.n_act + 1) * RP16_ROWS;
+  const int tile_elems = (p.n_slots + 1) * RP16_ROWS;
+  const int* slotsm = S.slot;
   const int n_copies = p.n_act * (RP16_ROWS / 2);    // 16-byte copies per block (8 per column)
 
   {
@@ -146,27 +153,21 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
     const cf* Tit = p.T + (long long)s * n_frames * frame_elems + tile * RP16_ROWS;
 
     const cf* src0 = Tit + (long long)(tid >> 3) * p.ohp + 2 * (tid & 7);
-    cf* dst0 = tbuf + (tid >> 3) * RP16_ROWS + 2 * (tid & 7);
+    cf* dst0 = tbuf + 2 * (tid & 7);
     const long long src_step = (long long)(NT / 8) * p.ohp;
     const int n_iter = tid < n_copies ? (n_copies - tid + NT - 1) / NT : 0;
-    const unsigned long long pol_t = l2_policy_evict_last();
     auto prefetch = [&](int f, int buf) {
       const cf* src = src0 + (long long)f * frame_elems;
       cf* dst = dst0 + (size_t)buf * tile_elems;
-      if (p.debug_skip & 4) {
-      } else if (p.l2_hints) {
+      int j = tid >> 3;
+      if (!(p.debug_skip & 4)) {
+        // (no L2 hint on these copies: ptxas 12.9 encodes a hinted LDGSTS with a uniform-register address offset
+        //  that sm_100a rejects as an illegal instruction, and the hints did not pay off anyway)
 #pragma unroll 1
         for (int i = 0; i < n_iter; ++i) {
-          cp_async16_hint(dst, src, pol_t);
+          cp_async16(dst + slotsm[j] * RP16_ROWS, src);
           src += src_step;
-          dst += (NT / 8) * RP16_ROWS;
-        }
-      } else {
-#pragma unroll 1
-        for (int i = 0; i < n_iter; ++i) {
-          cp_async16(dst, src);
-          src += src_step;
-          dst += (NT / 8) * RP16_ROWS;
+          j += NT / 8;
         }
       }
       cp_async_commit();
@@ -219,10 +220,9 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
           cf* ycol = Y + n2 * RP16_ROWS + r;                       // + k1 * YS
           if (type != 0) {
             cf x[P];
+            const cf* xb = tb + pay[2] * RP16_ROWS;
 #pragma unroll
-            for (int n1 = 0; n1 < P; ++n1) {
-              x[n1] = tb[pay[2 + n1] * RP16_ROWS];
-            }
+            for (int n1 = 0; n1 < P; ++n1) x[n1] = xb[n1 * RP16_ROWS];
             const cf* dtw = sptwsm + pay[1];
             auto emit = [&](auto kc, cf val) {
               constexpr int k1 = decltype(kc)::value;
