@@ -176,23 +176,25 @@ def test_pipelined_schedule_and_fused_normalisation(emu):
 
 def test_fused_640_wide_plan(emu):
     """prostate-shape plan (PE 451 zero-padded to 640, 8x mask + ACS, flipud, mean over averages after the RSS, crop):
-    column pass + 640-wide row pass (expanding first pass driven by the per-position plan) against the generic
-    kernels and the oracle; also fully sampled (regular butterflies everywhere) and an irregular mask (partial ones)."""
+    column pass + 640-wide row pass (expanding first pass driven by the per-position plan) against the oracle; also
+    fully sampled (regular butterflies everywhere) and an irregular mask (partial butterflies), normalisation included."""
     rng = np.random.default_rng(11)
     k = synth.gaussian_kspace((1, 2, 2, 640, 451), 41)           # (S, A, C, RO, PE)
+
+    def oracle(mask, crop):
+        ims = []
+        for a in range(2):
+            kk = np.pad(O.apply_mask(k[0, a], mask), ((0, 0), (0, 0), (94, 95)))
+            ims.append(np.flipud(np.sqrt((O.complex_abs(O.ifft2c(kk)) ** 2).sum(0))))
+        return O.center_crop(np.mean(ims, axis=0), crop).astype(np.float32)
+
     for m in (synth.prostate_mask(), None, (rng.uniform(size=451) < 0.3).astype(np.float32)):
         out, ms = recon(emu, k, m, (320, 320), cabi.FLIP_ROWS | cabi.NORM_INSTANCE, pad=(94, 95))
-        gen, gms = recon(emu, k, m, (320, 320), cabi.FLIP_ROWS | cabi.NORM_INSTANCE | cabi.FORCE_GENERIC, pad=(94, 95))
-        assert O.rel_l2(out, gen) <= TOL
-        np.testing.assert_allclose(ms, gms, rtol=1e-5)
-    m = synth.prostate_mask()
-    raw, _ = recon(emu, k, m, (77, 200), cabi.FLIP_ROWS, pad=(94, 95))
-    ims = []
-    for a in range(2):
-        kk = np.pad(O.apply_mask(k[0, a], m), ((0, 0), (0, 0), (94, 95)))
-        ims.append(np.flipud(np.sqrt((O.complex_abs(O.ifft2c(kk)) ** 2).sum(0))))
-    ref = O.center_crop(np.mean(ims, axis=0), (77, 200)).astype(np.float32)
-    assert O.rel_l2(raw[0], ref) <= TOL
+        nref, mean, std = O.normalize_instance(np.ascontiguousarray(oracle(m, (320, 320))))
+        assert O.rel_l2(out[0], nref) <= TOL
+        np.testing.assert_allclose(ms[0], [mean, std], rtol=1e-5)
+    raw, _ = recon(emu, k, synth.prostate_mask(), (77, 200), cabi.FLIP_ROWS, pad=(94, 95))
+    assert O.rel_l2(raw[0], oracle(synth.prostate_mask(), (77, 200))) <= TOL
 
 
 def test_pruned_generic_row_pass(emu):
