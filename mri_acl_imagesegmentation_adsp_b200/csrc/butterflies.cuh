@@ -127,42 +127,42 @@ template <bool INV> __device__ __forceinline__ void fft16(cf* v) {
 // are produced so the caller can twiddle and store without keeping all P outputs live.
 // The _part form computes only the output pairs k in [KLO, KHI) (and X[0] when WITH0), so one
 // transform can be shared between two warps.
-template <int P, bool INV, int KLO, int KHI, bool WITH0, class Emit>
-__device__ __forceinline__ void dft_odd_sym_part(const cf* x, Emit&& emit) {
+template <int P, bool INV, int KLO, int KHI, bool WITH0, class X, class Emit>
+__device__ __forceinline__ void dft_odd_sym_part(const X& x, Emit&& emit) {
   constexpr int Hh = (P - 1) / 2;
+  constexpr int NK = KHI - KLO;
   static_assert(KLO >= 1 && KHI <= Hh + 1 && KLO <= KHI, "pair range");
-  cf a[Hh], b[Hh];
+  // streaming order: each symmetric couple (x[n], x[P-n]) is combined once and fed to all NK output pairs, so only the
+  // 2 NK running sums (and X[0]'s) stay live -- not the Hh sums and differences
   const cf x0 = x[0];
+  cf A[NK > 0 ? NK : 1], B[NK > 0 ? NK : 1];
+  cf s0 = x0;
+  static_for<NK>([&](auto kk) { A[kk.value] = x0; });
   static_for<Hh>([&](auto nn) {
     constexpr int n = nn.value + 1;
-    a[n - 1] = cadd(x[n], x[P - n]);
-    b[n - 1] = csub(x[n], x[P - n]);
-  });
-  if constexpr (WITH0) {
-    cf s = x0;
-    static_for<Hh>([&](auto nn) { s = cadd(s, a[nn.value]); });
-    emit(std::integral_constant<int, 0>{}, s);
-  }
-  static_for<KHI - KLO>([&](auto kk) {
-    constexpr int k = kk.value + KLO;
-    cf A = x0, B = cf_make(0.f, 0.f);
-    static_for<Hh>([&](auto nn) {
-      constexpr int n = nn.value + 1;
+    const cf a = cadd(x[n], x[P - n]), b = csub(x[n], x[P - n]);
+    if constexpr (WITH0) s0 = cadd(s0, a);
+    static_for<NK>([&](auto kk) {
+      constexpr int k = kk.value + KLO;
       constexpr float c = DftConsts<P>::c((n * k) % P);
       constexpr float s = DftConsts<P>::s((n * k) % P);
-      A = pk_fma(a[n - 1], bc(c), A);
-      B = nn.value == 0 ? pk_mul(b[n - 1], bc(s)) : pk_fma(b[n - 1], bc(s), B);
+      A[kk.value] = pk_fma(a, bc(c), A[kk.value]);
+      if constexpr (n == 1) B[kk.value] = pk_mul(b, bc(s)); else B[kk.value] = pk_fma(b, bc(s), B[kk.value]);
     });
+  });
+  if constexpr (WITH0) emit(std::integral_constant<int, 0>{}, s0);
+  static_for<NK>([&](auto kk) {
+    constexpr int k = kk.value + KLO;
     // A + iB and A - iB
-    const cf iB = mul_i<true>(B);
-    const cf plus = cadd(A, iB), minus = csub(A, iB);
+    const cf iB = mul_i<true>(B[kk.value]);
+    const cf plus = cadd(A[kk.value], iB), minus = csub(A[kk.value], iB);
     emit(std::integral_constant<int, k>{}, INV ? plus : minus);
     emit(std::integral_constant<int, P - k>{}, INV ? minus : plus);
   });
 }
 
-template <int P, bool INV, class Emit>
-__device__ __forceinline__ void dft_odd_sym(const cf* x, Emit&& emit) {
+template <int P, bool INV, class X, class Emit>
+__device__ __forceinline__ void dft_odd_sym(const X& x, Emit&& emit) {
   dft_odd_sym_part<P, INV, 1, (P - 1) / 2 + 1, true>(x, emit);
 }
 

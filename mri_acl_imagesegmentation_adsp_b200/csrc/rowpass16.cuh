@@ -219,10 +219,8 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
           const int n2 = (half == 1 && offB < 0) ? Q : pay[0];     // idle half: spare column
           cf* ycol = Y + n2 * RP16_ROWS + r;                       // + k1 * YS
           if (type != 0) {
-            cf x[P];
-            const cf* xb = tb + pay[2] * RP16_ROWS;
-#pragma unroll
-            for (int n1 = 0; n1 < P; ++n1) x[n1] = xb[n1 * RP16_ROWS];
+            // operands are read where the streaming DFT consumes them (immediate offsets from the residue's base slot)
+            struct { const cf* p; __device__ __forceinline__ cf operator[](int n1) const { return p[n1 * RP16_ROWS]; } } x{tb + pay[2] * RP16_ROWS};
             const cf* dtw = sptwsm + pay[1];
             auto emit = [&](auto kc, cf val) {
               constexpr int k1 = decltype(kc)::value;
