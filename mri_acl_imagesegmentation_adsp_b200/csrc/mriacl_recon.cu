@@ -619,11 +619,13 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 2, a.ow, a.A);
       if (CP_SMEM_BYTES_DB + smem16 > SMEM_MAX) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 1, a.ow, a.A); }
       if (CP_SMEM_BYTES_DB + smem16 > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "co-resident tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
-      if (want_norm || a.mean_std) {
+      const bool kc_fuse_norm = env_int("MRIACL_KC_FUSE_NORM", 0) != 0;    // the finishing team normalises (measured slower)
+      if (kc_fuse_norm && (want_norm || a.mean_std)) {
         q.tiles_done = counters + ns;
         q.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
         q.eps = a.eps; q.normalize = want_norm ? 1 : 0;
       }
+      np.n_part = g.n_tiles16;
 #ifdef MRIACL_EMU   // the emulator runs the CTAs one after another: a single CTA does everything
       const int grid = 1;
 #else
@@ -634,6 +636,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       if (kc_only == 2) { kp.cp.n_frames = 0; kp.rp.done = nullptr; }
       auto kfn = knee_coresident_kernel<FUSED_P, FUSED_Q>;
       MRIACL_LAUNCH(kfn, grid, KC_T, CP_SMEM_BYTES_DB + smem16, a.st, kp);
+      if (run_norm && !kc_fuse_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
     } else if (fused_mode) {
       // one persistent launch: column items publish per-slice counters, row items are claimed when ready
       if (rt_memset_async(counters, 0, 256 * (size_t)ns, a.st)) return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
