@@ -159,6 +159,7 @@ struct FusedPlanDev {
   Row640PlanHost r640;             // 640-wide row pass (Wp == 640 plans)
   int* r640_off = nullptr;
   int* r640_ent = nullptr;
+  int* r640_perm = nullptr;
   RowPairPlanHost rpp;             // pair row pass (ok = the mask fits its template)
   int* rpp_slot = nullptr;
   int* rpp_zero = nullptr;
@@ -245,7 +246,9 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
       if (rt_malloc(&o1, sizeof(int) * 81) || rt_malloc(&o2, sizeof(int) * (pl->r640.ent.size() + 1)) ||
           rt_upload(o1, pl->r640.pos_off.data(), sizeof(int) * 81) ||
           (!pl->r640.ent.empty() && rt_upload(o2, pl->r640.ent.data(), sizeof(int) * pl->r640.ent.size()))) return nullptr;
-      pl->r640_off = (int*)o1; pl->r640_ent = (int*)o2;
+      void* o3 = nullptr;
+      if (rt_malloc(&o3, sizeof(int) * 160) || rt_upload(o3, pl->r640.perm.data(), sizeof(int) * 160)) return nullptr;
+      pl->r640_off = (int*)o1; pl->r640_ent = (int*)o2; pl->r640_perm = (int*)o3;
     }
     build_rowpair_plan(pl->host, RPP_STEP, RPP_NE, pl->rpp);
     if (pl->rpp.ok) {
@@ -423,7 +426,7 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
     if (wide640) {
       Row640Params q{};
       q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
-      q.pos_off = pl->r640_off; q.ent = pl->r640_ent; q.n_ent = n_ent; q.tw = pl->twW;
+      q.pos_off = pl->r640_off; q.ent = pl->r640_ent; q.n_ent = n_ent; q.perm = pl->r640_perm; q.tw = pl->twW;
       q.out = out_s0; q.partials = partials; q.ow = a.ow; q.col0 = col0;
       q.A = a.A; q.C = a.C; q.scale = scale;
       q.n_slices = ns; q.n_tiles = n_tiles_row;

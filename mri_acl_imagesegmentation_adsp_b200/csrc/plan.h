@@ -361,6 +361,7 @@ inline void build_rowpair_plan(const FusedPlanHost& pl, int step, int ne, RowPai
 struct Row640PlanHost {
   std::vector<int> pos_off;   // [81]
   std::vector<int> ent;
+  std::vector<int> perm;      // [160] first-pass position of thread tid: warps see one kind of butterfly where possible
 };
 
 inline void build_row640_plan(const FusedPlanHost& pl, Row640PlanHost& rp) {
@@ -379,6 +380,35 @@ inline void build_row640_plan(const FusedPlanHost& pl, Row640PlanHost& rp) {
     rp.ent.insert(rp.ent.end(), per_pos[pos].begin(), per_pos[pos].end());
   }
   rp.pos_off[80] = (int)rp.ent.size();
+  // First-pass thread -> position map.  Thread tid = 80 sub + slot works on lines sub, sub + 2, ...; its slot picks the
+  // position.  A warp runs every code path its lanes need, so positions are grouped by kind (all eight inputs sampled /
+  // a few / none) and the groups are started on warp boundaries where the empty positions leave room for that.
+  rp.perm.assign(160, 0);
+  std::vector<int> full, part, none;
+  for (int pos = 0; pos < 80; ++pos) {
+    const int c = rp.pos_off[pos + 1] - rp.pos_off[pos];
+    (c == 8 ? full : c == 0 ? none : part).push_back(pos);
+  }
+  for (int sub = 0; sub < 2; ++sub) {
+    std::vector<int> order(80, -1);
+    std::vector<int> pad = none;
+    int slot = 0;
+    auto place = [&](const std::vector<int>& v) { for (int x : v) order[slot++] = x; };
+    auto align = [&]() {     // advance to the next warp boundary of thread index 80 sub + slot, filling with empty positions
+      while (((80 * sub + slot) & 31) != 0 && slot < 80 && !pad.empty() &&
+             (int)pad.size() > 0 && slot + (int)part.size() < 80) { order[slot++] = pad.back(); pad.pop_back(); }
+    };
+    place(full);
+    if (!full.empty() && !part.empty()) align();
+    place(part);
+    for (int x : pad) if (slot < 80) order[slot++] = x;
+    // (if the padding ran out before a boundary the groups simply follow each other)
+    std::vector<char> seen(80, 0);
+    for (int i = 0; i < 80; ++i) if (order[i] >= 0) seen[order[i]] = 1;
+    int fill = 0;
+    for (int i = 0; i < 80; ++i) if (order[i] < 0) { while (seen[fill]) ++fill; order[i] = fill; seen[fill] = 1; }
+    for (int i = 0; i < 80; ++i) rp.perm[80 * sub + i] = order[i];
+  }
 }
 
 // FNV-1a over the plan-defining inputs: cache key for device-resident plans

@@ -32,6 +32,7 @@ struct Row640Params {
   const int* pos_off;          // [81] entries of butterfly position pos are ent[pos_off[pos] .. pos_off[pos + 1])
   const int* ent;              // per entry: n1 | (j << 3)
   int n_ent;
+  const int* perm;             // [160] first-pass position of thread tid (plan.h: kinds of butterfly grouped per warp)
   const cf* tw;                // w640^k = exp(+2 pi i k / 640)
   float* out;                  // [n_slices][oh][ow]
   float* partials;             // [n_slices][n_tiles][3] or nullptr
@@ -42,7 +43,7 @@ struct Row640Params {
 };
 
 __host__ __device__ inline int row640_smem_bytes(int n_act, int n_ent, int ow) {
-  return CP_BUF * 8 + 2 * n_act * R640_ROWS * 8 + R640_ROWS * (ow + 1) * 4 + ((81 + n_ent + 3) / 4) * 16 + 8 * 8;
+  return CP_BUF * 8 + 2 * n_act * R640_ROWS * 8 + R640_ROWS * (ow + 1) * 4 + ((81 + n_ent + 3) / 4) * 16 + 8 * 8;   // (perm is read once from global)
 }
 
 template <int NW> __device__ __forceinline__ float r640_block_sum(float v, float* red) {
@@ -72,12 +73,13 @@ __global__ void __launch_bounds__(R640_T, 3) rowpass640_kernel(Row640Params p) {
   for (int i = tid; i < p.n_ent; i += R640_T) plan[81 + i] = p.ent[i];
   if (tid < 8) w8sm[tid] = p.tw[80 * tid];
   cf tw1[8], tw2[8];
-  const int base2 = (pos / 10) * CP_BLK + (pos % 10);
+  const int pos1 = p.perm[tid];                                // first pass: my butterfly position (grouped by kind)
+  const int base2 = (pos / 10) * CP_BLK + (pos % 10);          // second pass: (m1, n3) = (pos / 10, pos % 10)
   {
     const int n3 = pos % 10;
 #pragma unroll
     for (int m = 1; m < 8; ++m) {
-      tw1[m] = p.tw[(pos * m) % CP_N];
+      tw1[m] = p.tw[(pos1 * m) % CP_N];
       tw2[m] = p.tw[(8 * n3 * m) % CP_N];
     }
   }
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(R640_T, 3) rowpass640_kernel(Row640Params p) {
     cc3[m3] = (cc >= 0 && cc < p.ow) ? cc : -1;
   }
   __syncthreads();
-  const int e0 = plan[pos], e1 = plan[pos + 1], cnt = e1 - e0;
+  const int e0 = plan[pos1], e1 = plan[pos1 + 1], cnt = e1 - e0;
   // pass 2 reads positions 10 n2 + (pos % 10), n2 = 0..7: bit n2 of present2 = that position has sampled inputs
   int present2 = 0;
 #pragma unroll
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(R640_T, 3) rowpass640_kernel(Row640Params p) {
 
       // ---- pass 1: expanding radix-8 over n1 (stride 90), twiddle w640^{pos * m1} ----
       for (int kc = sub; kc < R640_ROWS; kc += 2) {
-        cf* col = buf + kc * CP_PITCH + pos;
+        cf* col = buf + kc * CP_PITCH + pos1;
         if (cnt == 0) {
           // empty position: pass 2 substitutes zeros (present2 below), nothing to do
         } else if (cnt == 8) {
