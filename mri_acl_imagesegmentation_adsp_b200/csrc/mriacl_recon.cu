@@ -394,10 +394,10 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
   const int flip = (a.flags & MRIACL_FLIP_ROWS) ? 1 : 0;
   const int n_ent = (int)pl->r640.ent.size();
   int rg_lines = 8;        // pruned generic row pass: lines per item, halved until the two line buffers + tiles fit
-  while (!wide640 && rg_lines > 1 && rowgen_smem_bytes(a.Wp, rg_lines, a.ow) > SMEM_MAX / 3) rg_lines /= 2;
-  const int smem = wide640 ? row640_smem_bytes(std::max(1, n_act), n_ent, a.ow) : rowgen_smem_bytes(a.Wp, rg_lines, a.ow);
-  if (smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "row pass does not fit shared memory (Wp=%d n_act=%d ow=%d)", a.Wp, n_act, a.ow);
   const std::vector<int> rad = generic_radices(a.Wp);
+  while (!wide640 && rg_lines > 1 && rowgen_smem_bytes(a.Wp, rg_lines, a.ow, (int)rad.size()) > SMEM_MAX / 3) rg_lines /= 2;
+  const int smem = wide640 ? row640_smem_bytes(std::max(1, n_act), n_ent, a.ow) : rowgen_smem_bytes(a.Wp, rg_lines, a.ow, (int)rad.size());
+  if (smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "row pass does not fit shared memory (Wp=%d n_act=%d ow=%d)", a.Wp, n_act, a.ow);
   if (!wide640 && (int)rad.size() > RG_MAX_STAGES) return fail(MRIACL_ERR_UNSUPPORTED, "too many FFT stages for N=%d", a.Wp);
   const int n_tiles_row = wide640 ? g.n_tiles8 : (a.oh + rg_lines - 1) / rg_lines;
   const int chunk = (int)std::min<size_t>((size_t)a.B, a.workspace_bytes / g.per_slice);

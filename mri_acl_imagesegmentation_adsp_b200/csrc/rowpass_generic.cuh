@@ -34,8 +34,8 @@ struct RowGenParams {
   int radix[RG_MAX_STAGES];
 };
 
-__host__ __device__ inline int rowgen_smem_bytes(int N, int L, int ow) {
-  return 2 * L * N * 8 + 2 * L * (ow + 1) * 4;
+__host__ __device__ inline int rowgen_smem_bytes(int N, int L, int ow, int n_stages) {
+  return 2 * L * N * 8 + 2 * L * (ow + 1) * 4 + n_stages * N * 8 + N * 8;
 }
 
 __global__ void __launch_bounds__(RG_T, 3) rowpass_generic_kernel(RowGenParams p) {
@@ -43,12 +43,32 @@ __global__ void __launch_bounds__(RG_T, 3) rowpass_generic_kernel(RowGenParams p
   const int N = p.N, L = p.L;
   float* accsm = reinterpret_cast<float*>(sm + 2 * (size_t)L * N);      // [L][ow + 1] sum over coils of |X|^2
   float* avsm = accsm + L * (p.ow + 1);                                  // [L][ow + 1] sum over averages of the RSS
+  int2* stab = reinterpret_cast<int2*>(avsm + L * (p.ow + 1));          // [n_stages][N] (first input, twiddle step) per output
+  cf* twsm = reinterpret_cast<cf*>(stab + p.n_stages * N);               // [N] twiddles (shared memory: one load per MAC)
   __shared__ float red[RG_T / 32];
   const int tid = threadIdx.x;
   const int opitch = p.ow + 1;
+  for (int i = tid; i < N; i += RG_T) twsm[i] = p.tw[i];
   const int n_frames = p.A * p.C;
   const long long frame_elems = (long long)p.n_act * p.ohp;
   const int n_items = p.n_slices * p.n_tiles;
+  // Stockham index maps, once per CTA: output i of stage st reads inputs j, j + N/R, ... with twiddles idx = 0, step, 2 step ...
+  {
+    int Ns = 1;
+    for (int st = 0; st < p.n_stages; ++st) {
+      const int R = p.radix[st], NR = N / R, tstep = N / (Ns * R);
+      for (int i = tid; i < N; i += RG_T) {
+        const int k = i % Ns, t = i / Ns;
+        const int q = t % R, jh = t / R;
+        stab[st * N + i] = make_int2(jh * Ns + k, (int)(((long long)k * tstep + (long long)q * NR) % N));
+      }
+      Ns *= R;
+    }
+  }
+  __syncthreads();
+  // (line, index) of element e = tid + n RG_T advance without divisions
+  const int step_l = RG_T / N, step_i = RG_T - step_l * N;
+  const int l_first = tid / N, i_first = tid - l_first * N;
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int s = item / p.n_tiles, tile = item - s * p.n_tiles;
@@ -69,48 +89,52 @@ __global__ void __launch_bounds__(RG_T, 3) rowpass_generic_kernel(RowGenParams p
         buf0[l * N + p.act_logical[j]] = Tf[(long long)j * p.ohp + l];
       }
       __syncthreads();
-      int Ns = 1;
       for (int st = 0; st < p.n_stages; ++st) {
         const int R = p.radix[st];
         const int NR = N / R;
-        const int tstep = N / (Ns * R);
+        const int2* tab = stab + st * N;
+        int l = l_first, i = i_first;
         for (int e = tid; e < total; e += RG_T) {
-          const int l = e / N, i = e - l * N;
-          const int k = i % Ns, t = i / Ns;
-          const int q = t % R, jh = t / R;
-          const int j = jh * Ns + k;
-          const int step = (int)(((long long)k * tstep + (long long)q * NR) % N);
+          const int2 js = tab[i];
+          const int step = js.y;
           int idx = 0;
-          const cf* src = buf0 + l * N + j;
+          const cf* src = buf0 + l * N + js.x;
           cf acc = cf_make(0.f, 0.f);
           for (int r = 0; r < R; ++r) {
             const cf x = src[r * NR];
-            const cf w = p.tw[idx];                   // forward table: inverse transform uses conj(w)
+            const cf w = twsm[idx];                   // forward table: inverse transform uses conj(w)
             acc = pk_fma(mul_i<false>(x), bc(w.y), pk_fma(x, bc(w.x), acc));
             idx += step;
             if (idx >= N) idx -= N;
           }
           buf1[e] = acc;
+          l += step_l; i += step_i;
+          if (i >= N) { i -= N; ++l; }
         }
         __syncthreads();
         cf* tswap = buf0; buf0 = buf1; buf1 = tswap;
-        Ns *= R;
       }
       // |X|^2 of the kept columns (fftshift + crop) into the coil accumulators; element e always belongs to the same thread
-      for (int e = tid; e < total; e += RG_T) {
-        const int l = e / N, m = e - l * N;
-        const int cc = phys_of_logical(m, N) - p.col0;
-        if (cc >= 0 && cc < p.ow) accsm[l * opitch + cc] = cnorm2_acc(buf0[e], accsm[l * opitch + cc]);
+      {
+        int l = l_first, m = i_first;
+        for (int e = tid; e < total; e += RG_T) {
+          const int cc = phys_of_logical(m, N) - p.col0;
+          if (cc >= 0 && cc < p.ow) accsm[l * opitch + cc] = cnorm2_acc(buf0[e], accsm[l * opitch + cc]);
+          l += step_l; m += step_i;
+          if (m >= N) { m -= N; ++l; }
+        }
       }
       if (++coil == p.C) {
         coil = 0;
+        int l = l_first, m = i_first;
         for (int e = tid; e < total; e += RG_T) {
-          const int l = e / N, m = e - l * N;
           const int cc = phys_of_logical(m, N) - p.col0;
           if (cc >= 0 && cc < p.ow) {
             avsm[l * opitch + cc] += sqrtf(accsm[l * opitch + cc]) * p.scale;
             accsm[l * opitch + cc] = 0.f;
           }
+          l += step_l; m += step_i;
+          if (m >= N) { m -= N; ++l; }
         }
       }
       __syncthreads();

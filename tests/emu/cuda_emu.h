@@ -24,6 +24,7 @@ struct float4 { float x, y, z, w; };
 struct int2 { int x, y; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+static inline int2 make_int2(int a, int b) { return int2{a, b}; }
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 
 #define __global__
