@@ -120,6 +120,51 @@ template <bool INV> __device__ __forceinline__ void fft16(cf* v) {
   });
 }
 
+// 3-point DFT in place
+template <bool INV> __device__ __forceinline__ void radix3(cf& a0, cf& a1, cf& a2) {
+  constexpr float hs = 0.86602540378443864676f;   // sin(2 pi / 3)
+  const cf t = cadd(a1, a2);
+  const cf m = pk_fma(t, bc(-0.5f), a0);
+  const cf d = cscale(csub(a1, a2), hs);
+  const cf j = mul_i<INV>(d);
+  a0 = cadd(a0, t);
+  a1 = cadd(m, j);
+  a2 = csub(m, j);
+}
+
+// 12-point DFT, v[0..11] in place, natural order (n = 3a + b, k = c + 4d: four-point transforms over a, twiddles
+// w12^{bc}, three-point transforms over b)
+template <bool INV> __device__ __forceinline__ void fft12(cf* v) {
+  static_for<3>([&](auto bb) { constexpr int b = bb.value; radix4<INV>(v[b], v[3 + b], v[6 + b], v[9 + b]); });   // u[b][c] at v[3c + b]
+  constexpr float h3 = 0.86602540378443864676f;
+  constexpr float cw[7] = {1.f, h3, 0.5f, 0.f, -0.5f, -h3, -1.f};
+  constexpr float sw[7] = {0.f, 0.5f, h3, 1.f, h3, 0.5f, 0.f};
+  static_for<2>([&](auto bb) {
+    constexpr int b = bb.value + 1;
+    static_for<3>([&](auto cc) {
+      constexpr int c = cc.value + 1;
+      constexpr int e = b * c;      // 1, 2, 3, 2, 4, 6
+      constexpr float wc = cw[e], ws = INV ? sw[e] : -sw[e];
+      if constexpr (e == 6) v[3 * c + b] = cneg(v[3 * c + b]);
+      else if constexpr (e == 3) v[3 * c + b] = cscale(mul_i<true>(v[3 * c + b]), ws);
+      else v[3 * c + b] = cmul_k(v[3 * c + b], wc, ws);
+    });
+  });
+  static_for<4>([&](auto cc) { constexpr int c = cc.value; radix3<INV>(v[3 * c], v[3 * c + 1], v[3 * c + 2]); });   // X[c + 4d] at v[3c + d]
+  cf t[12];
+  static_for<12>([&](auto ii) { t[ii.value] = v[ii.value]; });
+  static_for<4>([&](auto cc) {
+    constexpr int c = cc.value;
+    static_for<3>([&](auto dd) { constexpr int d = dd.value; v[c + 4 * d] = t[3 * c + d]; });
+  });
+}
+
+// Q-point register FFT of the row pass's second stage
+template <int Q, bool INV> __device__ __forceinline__ void fft_q(cf* v) {
+  static_assert(Q == 16 || Q == 12, "second-stage lengths: 16 (368 = 23 x 16) and 12 (372 = 31 x 12)");
+  if constexpr (Q == 16) fft16<INV>(v); else fft12<INV>(v);
+}
+
 // P-point DFT for odd P by the symmetric direct method:
 //   a_n = x[n] + x[P-n], b_n = x[n] - x[P-n]  (n = 1..(P-1)/2)
 //   X[k], X[P-k] = x0 + sum a_n cos(2 pi n k/P)  +-  i sum b_n sin(2 pi n k/P)

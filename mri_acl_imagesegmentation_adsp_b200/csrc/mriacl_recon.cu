@@ -57,7 +57,9 @@ int device_sms(int dev) {
 
 int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
-constexpr int FUSED_P = 23, FUSED_Q = 16;
+constexpr int FUSED_P = 23, FUSED_Q = 16;      // 368-wide knee plans
+constexpr int W372_P = 31, W372_Q = 12;        // 372-wide knee plans: same row-pass kernel, 31-point first stage, 12-point second
+constexpr int W372_NW = 8;                     // 16 output pairs over 8 warps (two pairs each), 2 CTAs per SM
 constexpr int SMEM_MAX = 227 * 1024 - 512;     // dynamic shared memory a B200 CTA may opt in to (227 KB minus the kernels' static part)
 // Row-pass CTA shapes: 16 warps (one CTA owns the SM) for the sequential schedule, 8 warps for the
 // overlapped schedule, where one row-pass CTA shares each SM with column-pass CTAs.
@@ -87,6 +89,7 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 8, 3>, SMEM_MAX / 3);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<W372_P, W372_Q, W372_NW, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass640_kernel, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_generic_kernel, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_kernel<FUSED_P, FUSED_Q>, SMEM_MAX);
@@ -191,8 +194,9 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     }
   }
   auto pl = std::make_shared<FusedPlanDev>();
-  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, FUSED_P, FUSED_Q, RP_NW_SEQ, RP_MAX_SPARSE, /*split_dense=*/true, pl->host);
-  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, FUSED_P, FUSED_Q, RP_NW_OVL, RP_MAX_SPARSE, /*split_dense=*/true, pl->host_ovl);
+  const int planP = Wp == W372_P * W372_Q ? W372_P : FUSED_P, planQ = Wp == W372_P * W372_Q ? W372_Q : FUSED_Q;
+  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, planP, planQ, RP_NW_SEQ, RP_MAX_SPARSE, /*split_dense=*/true, pl->host);
+  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, planP, planQ, RP_NW_OVL, RP_MAX_SPARSE, /*split_dense=*/true, pl->host_ovl);
   pl->has_mask = mask != nullptr;
   if (mask) pl->mask_copy.assign(mask, mask + W);
   if (device_side) {
@@ -231,7 +235,7 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     void* s5 = nullptr;
     if (rt_malloc(&s5, sizeof(int) * pl->pairs8.size()) || rt_upload(s5, pl->pairs8.data(), sizeof(int) * pl->pairs8.size())) return nullptr;
     pl->sched_p8 = (int*)s5;
-    if (Wp != CP_N && Wp != FUSED_P * FUSED_Q) {
+    if (Wp != CP_N && Wp != FUSED_P * FUSED_Q) {      // (372 too: its dense plans fall back to the pruned generic row pass)
       std::vector<int> lg(std::max<size_t>(1, pl->host.act_w.size()), 0);
       for (size_t j = 0; j < pl->host.act_w.size(); ++j) lg[j] = logical_of_phys(pl->host.act_w[j] + pad_left, Wp);
       void* o = nullptr;
@@ -272,7 +276,7 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
   return pl;
 }
 
-bool fused_shape(int H, int Wp) { return H == CP_N && (Wp == FUSED_P * FUSED_Q || Wp == CP_N); }
+bool fused_shape(int H, int Wp) { return H == CP_N && (Wp == FUSED_P * FUSED_Q || Wp == W372_P * W372_Q || Wp == CP_N); }
 // H = 640 with any other width: the fused column pass feeds the pruned generic row pass (rowpass_generic.cuh)
 bool pruned_shape(int H, int Wp) { return H == CP_N && !fused_shape(H, Wp) && Wp <= MRIACL_MAX_LINE; }
 
@@ -379,6 +383,62 @@ struct FusedArgs {
   int B, A, C, H, W, pad_left, Wp, oh, ow; unsigned flags; float eps;
   void* workspace; size_t workspace_bytes; rt_stream_t st; int dev, sms;
 };
+
+int run_fused640(const FusedArgs& a, const ReconGeom& g);
+
+// The 640 x 372 knee plans: column pass -> 16-row row pass with a 31-point first stage and a 12-point second stage
+// (372 = 31 x 12; same kernel template and plan builder as the 368-wide plans) -> normalise, back to back.
+int run_fused372(const FusedArgs& a, const ReconGeom& g) {
+  std::shared_ptr<FusedPlanDev> pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
+  if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
+  const int n_act = (int)pl->host.act_w.size();
+  const int n_groups = (n_act + CP_G - 1) / CP_G;
+  const int ohp = g.n_tiles * RP_ROWS;
+  const int row0 = crop_start(a.H, a.oh), col0 = crop_start(a.Wp, a.ow);
+  const bool want_norm = (a.flags & MRIACL_NORM_INSTANCE) != 0;
+  const int flip = (a.flags & MRIACL_FLIP_ROWS) ? 1 : 0;
+  const int chunk = (int)std::min<size_t>((size_t)a.B, a.workspace_bytes / g.per_slice);
+  int n_buf372 = 2;
+  int smem16 = rowpass16_smem_bytes(W372_P, W372_Q, (int)pl->sptw16.size(), (int)pl->pairs8.size(), pl->rp16_slots, n_buf372, a.ow, a.A);
+  if (smem16 > SMEM_MAX / 2) { n_buf372 = 1; smem16 = rowpass16_smem_bytes(W372_P, W372_Q, (int)pl->sptw16.size(), (int)pl->pairs8.size(), pl->rp16_slots, 1, a.ow, a.A); }
+  if (smem16 > SMEM_MAX / 2) return run_fused640(a, g);     // (nearly) fully sampled: the staged tile is too large, take the pruned generic row pass
+  for (int s0 = 0; s0 < a.B; s0 += chunk) {
+    const int ns = std::min(chunk, a.B - s0);
+    char* base = (char*)a.workspace;
+    cf* T = (cf*)base;
+    float* partials = (float*)(base + g.t_bytes * (size_t)chunk);
+    ColPassParams cp{};
+    cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = a.W;
+    cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
+    cp.tw = pl->twH; cp.T = T; cp.oh = a.oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
+    cp.frame0 = s0 * a.A * a.C; cp.n_frames = ns * a.A * a.C; cp.done = nullptr;
+    const long long col_items = (long long)cp.n_frames * n_groups;
+    if (col_items > 0) {
+      const int grid = (int)std::min<long long>(col_items, (long long)a.sms * 2);
+      MRIACL_LAUNCH(colpass640_ws_kernel, grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+    }
+    RowPass16Params q{};
+    q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+    q.sched = pl->sched_p8; q.sched_len = (int)pl->pairs8.size();
+    q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size(); q.n_slots = pl->rp16_slots; q.slot_of_j = pl->rp16_slot_dev;
+    q.out = a.out + (size_t)s0 * a.oh * a.ow; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C;
+    q.scale = (float)(1.0 / std::sqrt((double)a.H * (double)a.Wp));
+    q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
+    q.n_buf = n_buf372;
+    q.reverse = 1;
+    auto kfn = rowpass16_kernel<W372_P, W372_Q, W372_NW, 2>;
+    MRIACL_LAUNCH(kfn, std::min(ns * g.n_tiles16, 2 * a.sms), W372_NW * 32, smem16, a.st, q);
+    if (want_norm || a.mean_std) {
+      NormParams np{};
+      np.in = q.out; np.out = q.out; np.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
+      np.partials = partials; np.n_part = g.n_tiles16; np.n = (long long)a.oh * a.ow; np.eps = a.eps;
+      np.normalize = want_norm ? 1 : 0;
+      np.n_split = want_norm ? std::max(1, std::min(16, (int)(np.n / 8192))) : 1;
+      MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
+    }
+  }
+  return 0;
+}
 
 // The 640 x 640 plans (prostate-shape) and every other width behind the H = 640 column pass:
 // column pass -> 640-wide row pass / pruned generic row pass -> normalise, back to back.
@@ -875,7 +935,7 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
   if (g.fused) {
     FusedArgs fa{ksp, slice_stride, avg_stride, mask_w_host, out, mean_std, B, A, C, H, W, pad_left, Wp, oh, ow,
                  flags, eps, workspace, workspace_bytes, st, dev, sms};
-    if (int rc = (Wp == FUSED_P * FUSED_Q ? run_fused(fa, g) : run_fused640(fa, g))) return rc;
+    if (int rc = (Wp == FUSED_P * FUSED_Q ? run_fused(fa, g) : Wp == W372_P * W372_Q ? run_fused372(fa, g) : run_fused640(fa, g))) return rc;
   } else {
     const float* mask_dev = nullptr;
     if (get_device_mask(dev, mask_w_host, W, &mask_dev)) return fail(MRIACL_ERR_CUDA, "mask upload failed: %s", rt_last_error_string());

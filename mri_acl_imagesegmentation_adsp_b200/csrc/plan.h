@@ -8,6 +8,11 @@
 #include <numeric>
 #include <vector>
 
+#if !defined(__CUDACC__) && !defined(__host__)
+#define __host__
+#define __device__
+#endif
+
 namespace mriacl {
 
 struct HostCf { float x, y; };
@@ -65,7 +70,9 @@ struct FusedPlanHost {
 //                      split_dense so that one dense residue is shared by two warps
 //     type 0 (sparse): payload = offset of the unit's first row in sptw, then nnz column indices j;
 //                      sptw row e holds w_N^{n_e k1}, k1 = 0..P-1 (n_e = Q n1 + n2 logical index)
-constexpr int SPTW_PITCH = 24;   // complex elements per sptw row (P = 23 padded to a 16-byte multiple)
+constexpr int SPTW_PITCH = 24;   // complex elements per sptw row for P = 23 (32-row kernel)
+// row pitch of the twiddle tables for a P-point first stage: P + 1 rounded up to even (16-byte rows): 23 -> 24, 31 -> 32
+__host__ __device__ constexpr int sptw_pitch(int P) { return (P + 2) & ~1; }
 inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow, const float* mask,
                              int P, int Q, int n_warps, int max_sparse, bool split_dense, FusedPlanHost& pl) {
   pl.H = H; pl.W = W; pl.pad_left = pad_left; pl.Wp = Wp; pl.oh = oh; pl.ow = ow;
@@ -115,7 +122,7 @@ inline void build_fused_plan(int H, int W, int pad_left, int Wp, int oh, int ow,
       for (int e = 0; e < nnz; ++e) {
         const int n = pairs[2 * e];
         u.payload.push_back(pairs[2 * e + 1]);
-        for (int k1 = 0; k1 < SPTW_PITCH; ++k1)
+        for (int k1 = 0; k1 < sptw_pitch(P); ++k1)
           pl.sptw.push_back(k1 < P ? twN[(size_t)(((long long)n * k1) % Wp)] : HostCf{0.f, 0.f});
       }
       units.push_back(u);
@@ -220,7 +227,7 @@ inline void build_pair_schedule(const FusedPlanHost& pl, int n_warps, std::vecto
   for (auto& u : units)
     if (u.type != 0 && dense_row[u.n2] < 0) {
       dense_row[u.n2] = (int)sptw16.size();
-      for (int k1 = 0; k1 < SPTW_PITCH; ++k1)
+      for (int k1 = 0; k1 < sptw_pitch(pl.P); ++k1)
         sptw16.push_back(k1 < pl.P ? twN[(size_t)(((long long)u.n2 * k1) % pl.Wp)] : HostCf{0.f, 0.f});
     }
   out.assign(n_warps, 0);

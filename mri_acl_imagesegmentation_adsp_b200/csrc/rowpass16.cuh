@@ -73,7 +73,7 @@ template <int NW, int BAR> __device__ __forceinline__ float rp16_team_sum(float 
 template <int P, int Q, int NNZ>
 __device__ __forceinline__ void rp16_sparse_unit(const int* pay, const cf* tb, const cf* sptw, cf* ycol) {
   constexpr int YS = (Q + 1) * RP16_ROWS;   // Y stride between k1
-  constexpr int PITCH = 24;
+  constexpr int PITCH = (P + 2) & ~1;       // plan.h sptw_pitch(P)
   cf xe[NNZ > 0 ? NNZ : 1];
   const float4* tw4 = reinterpret_cast<const float4*>(sptw + pay[1]);
 #pragma unroll
@@ -123,7 +123,6 @@ template <int NT> __device__ __forceinline__ void rp16_load_tables(const RowPass
 template <int P, int Q, int NW, int BAR = 0>
 __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* smem_base, int item, int tid,
                                                float* red, int* ready_flag) {
-  static_assert(Q == 16, "stage 2 is the register-level 16-point FFT");
   constexpr int N = P * Q;
   constexpr int NT = NW * 32;
   constexpr int NPAIR = (P + 1) / 2;                 // stage-2 pairs of k1
@@ -257,7 +256,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
           const cf* yrow = Y + k1c * YS + r;
 #pragma unroll
           for (int n2 = 0; n2 < Q; ++n2) v[n2] = yrow[n2 * RP16_ROWS];
-          fft16<true>(v);
+          fft_q<Q, true>(v);
 #pragma unroll
           for (int k2 = 0; k2 < Q; ++k2) acc[kk][k2] = cnorm2_acc(v[k2], acc[kk][k2]);
         }

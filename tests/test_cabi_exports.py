@@ -36,7 +36,8 @@ def test_queries_without_gpu(built):
     assert built._lib.mriacl_abi_version() == cabi.ABI_VERSION
     assert built.supported(640, 368) == cabi.PATH_FUSED
     assert built.supported(640, 640) == cabi.PATH_FUSED        # prostate-shape plan (rowpass640)
-    assert built.supported(640, 372) == cabi.PATH_GENERIC      # any-width path (pruned behind the 640 column pass)
+    assert built.supported(640, 372) == cabi.PATH_FUSED        # 372 = 31 x 12 knee plan
+    assert built.supported(640, 320) == cabi.PATH_GENERIC      # any-width path (pruned behind the 640 column pass)
     assert built.supported(372, 640) == cabi.PATH_GENERIC
     assert built.supported(640, 5000) == cabi.PATH_NONE
     n1 = built.recon_rss_workspace_bytes(1, 1, 15, 640, 368, 0, 368, 320, 320)

@@ -238,9 +238,9 @@ def test_pair_row_pass_schedule():
 
 
 def test_other_widths_behind_the_640_column_pass():
-    """640 x 372 / 640 x 320 knee files (no specialised row kernel): fused column pass + pruned generic row pass,
-    against the oracle's numpy chain and the full generic path; chunking never changes a slice."""
-    for W, seed in ((372, 61), (320, 62)):
+    """640 x 372 knee files (31 x 12 plan of the 16-row row pass) and 640 x 320 / 400 (no specialised row kernel: pruned
+    generic row pass), against the oracle's numpy chain and the full generic path; chunking never changes a slice."""
+    for W, seed in ((372, 61), (320, 62), (400, 63)):
         k_np = synth.gaussian_kspace((3, 15, 640, W), seed)
         k = torch.from_numpy(k_np).cuda()
         m = synth.equispaced_mask(W, 4, 0.08)
