@@ -160,7 +160,8 @@ __device__ __forceinline__ void full_wait(FullBarrier* b, int parity, int emu_id
 // a scheduling surprise cannot hang the device
 __device__ __forceinline__ bool wait_count_ge(const int* counter, int target) {
 #if defined(MRIACL_EMU)
-  for (int spin = 0; spin < 2000000; ++spin) {
+  const auto t0 = std::chrono::steady_clock::now();      // emulator: wall-clock bound (CUDA threads are OS threads here)
+  while (std::chrono::steady_clock::now() - t0 < std::chrono::seconds(300)) {
     if (reinterpret_cast<const std::atomic<int>*>(counter)->load() >= target) return true;
     std::this_thread::yield();
   }

@@ -58,7 +58,8 @@ inline int rowpass_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_a
 __device__ __forceinline__ bool rp_wait_count(const int* counter, int target, int* error_flag) {
 #if defined(MRIACL_EMU)
   // emulator: producers may be sibling threads of the same CTA (co-resident kernel), so poll for a while
-  for (int spin = 0; spin < 2000000; ++spin) {
+  const auto t0 = std::chrono::steady_clock::now();      // emulator: wall-clock bound (CUDA threads are OS threads here)
+  while (std::chrono::steady_clock::now() - t0 < std::chrono::seconds(300)) {
     if (reinterpret_cast<const std::atomic<int>*>(counter)->load() >= target) return true;
     std::this_thread::yield();
   }

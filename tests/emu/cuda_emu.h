@@ -7,6 +7,7 @@
 // the product path can reach it.
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
