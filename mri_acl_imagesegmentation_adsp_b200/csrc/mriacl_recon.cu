@@ -60,6 +60,8 @@ int env_int(const char* name, int dflt) { const char* e = getenv(name); return e
 constexpr int FUSED_P = 23, FUSED_Q = 16;      // 368-wide knee plans
 constexpr int W372_P = 31, W372_Q = 12;        // 372-wide knee plans: same row-pass kernel, 31-point first stage, 12-point second
 constexpr int W372_NW = 8;                     // 16 output pairs over 8 warps (two pairs each), 2 CTAs per SM
+constexpr int W400_P = 25, W400_Q = 16;        // 400-wide knee plans: 25-point first stage (symmetric direct DFT, any odd length)
+constexpr int W400_NW = 7;                     // 13 output pairs over 7 warps
 constexpr int SMEM_MAX = 227 * 1024 - 512;     // dynamic shared memory a B200 CTA may opt in to (227 KB minus the kernels' static part)
 // Row-pass CTA shapes: 16 warps (one CTA owns the SM) for the sequential schedule, 8 warps for the
 // overlapped schedule, where one row-pass CTA shares each SM with column-pass CTAs.
@@ -90,6 +92,7 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 8, 3>, SMEM_MAX / 3);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<W372_P, W372_Q, W372_NW, 2>, SMEM_MAX / 2);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<W400_P, W400_Q, W400_NW, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass640_kernel, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_generic_kernel, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_kernel<FUSED_P, FUSED_Q>, SMEM_MAX);
@@ -194,7 +197,8 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     }
   }
   auto pl = std::make_shared<FusedPlanDev>();
-  const int planP = Wp == W372_P * W372_Q ? W372_P : FUSED_P, planQ = Wp == W372_P * W372_Q ? W372_Q : FUSED_Q;
+  const int planP = Wp == W372_P * W372_Q ? W372_P : Wp == W400_P * W400_Q ? W400_P : FUSED_P;
+  const int planQ = Wp == W372_P * W372_Q ? W372_Q : Wp == W400_P * W400_Q ? W400_Q : FUSED_Q;
   build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, planP, planQ, RP_NW_SEQ, RP_MAX_SPARSE, /*split_dense=*/true, pl->host);
   build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, planP, planQ, RP_NW_OVL, RP_MAX_SPARSE, /*split_dense=*/true, pl->host_ovl);
   pl->has_mask = mask != nullptr;
@@ -231,7 +235,7 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
         rt_malloc(&s4, sizeof(int) * pl->pairs16.size()) || rt_upload(s4, pl->pairs16.data(), sizeof(int) * pl->pairs16.size()))
       return nullptr;
     pl->sched_p12 = (int*)s3; pl->sched_p16 = (int*)s4;
-    build_pair_schedule(pl->host, FZ_ROW_WARPS, pl->pairs8, pl->sptw16);
+    build_pair_schedule(pl->host, Wp == W400_P * W400_Q ? W400_NW : FZ_ROW_WARPS, pl->pairs8, pl->sptw16);   // (8 warps; 7 for the 400-wide plans)
     void* s5 = nullptr;
     if (rt_malloc(&s5, sizeof(int) * pl->pairs8.size()) || rt_upload(s5, pl->pairs8.data(), sizeof(int) * pl->pairs8.size())) return nullptr;
     pl->sched_p8 = (int*)s5;
@@ -276,7 +280,9 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
   return pl;
 }
 
-bool fused_shape(int H, int Wp) { return H == CP_N && (Wp == FUSED_P * FUSED_Q || Wp == W372_P * W372_Q || Wp == CP_N); }
+bool fused_shape(int H, int Wp) {
+  return H == CP_N && (Wp == FUSED_P * FUSED_Q || Wp == W372_P * W372_Q || Wp == W400_P * W400_Q || Wp == CP_N);
+}
 // H = 640 with any other width: the fused column pass feeds the pruned generic row pass (rowpass_generic.cuh)
 bool pruned_shape(int H, int Wp) { return H == CP_N && !fused_shape(H, Wp) && Wp <= MRIACL_MAX_LINE; }
 
@@ -386,9 +392,10 @@ struct FusedArgs {
 
 int run_fused640(const FusedArgs& a, const ReconGeom& g);
 
-// The 640 x 372 knee plans: column pass -> 16-row row pass with a 31-point first stage and a 12-point second stage
-// (372 = 31 x 12; same kernel template and plan builder as the 368-wide plans) -> normalise, back to back.
-int run_fused372(const FusedArgs& a, const ReconGeom& g) {
+// The 640 x 372 and 640 x 400 knee plans: column pass -> 16-row row pass with a P-point first stage and a Q-point second
+// stage (372 = 31 x 12, 400 = 25 x 16; same kernel template and plan builder as the 368-wide plans) -> normalise.
+template <int PP, int QQ, int NWW>
+int run_fused_pq(const FusedArgs& a, const ReconGeom& g) {
   std::shared_ptr<FusedPlanDev> pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
   if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
   const int n_act = (int)pl->host.act_w.size();
@@ -399,8 +406,8 @@ int run_fused372(const FusedArgs& a, const ReconGeom& g) {
   const int flip = (a.flags & MRIACL_FLIP_ROWS) ? 1 : 0;
   const int chunk = (int)std::min<size_t>((size_t)a.B, a.workspace_bytes / g.per_slice);
   int n_buf372 = 2;
-  int smem16 = rowpass16_smem_bytes(W372_P, W372_Q, (int)pl->sptw16.size(), (int)pl->pairs8.size(), pl->rp16_slots, n_buf372, a.ow, a.A);
-  if (smem16 > SMEM_MAX / 2) { n_buf372 = 1; smem16 = rowpass16_smem_bytes(W372_P, W372_Q, (int)pl->sptw16.size(), (int)pl->pairs8.size(), pl->rp16_slots, 1, a.ow, a.A); }
+  int smem16 = rowpass16_smem_bytes(PP, QQ, (int)pl->sptw16.size(), (int)pl->pairs8.size(), pl->rp16_slots, n_buf372, a.ow, a.A);
+  if (smem16 > SMEM_MAX / 2) { n_buf372 = 1; smem16 = rowpass16_smem_bytes(PP, QQ, (int)pl->sptw16.size(), (int)pl->pairs8.size(), pl->rp16_slots, 1, a.ow, a.A); }
   if (smem16 > SMEM_MAX / 2) return run_fused640(a, g);     // (nearly) fully sampled: the staged tile is too large, take the pruned generic row pass
   for (int s0 = 0; s0 < a.B; s0 += chunk) {
     const int ns = std::min(chunk, a.B - s0);
@@ -426,8 +433,8 @@ int run_fused372(const FusedArgs& a, const ReconGeom& g) {
     q.n_slices = ns; q.n_tiles = g.n_tiles16; q.done = nullptr; q.done_target = 0; q.error_flag = nullptr;
     q.n_buf = n_buf372;
     q.reverse = 1;
-    auto kfn = rowpass16_kernel<W372_P, W372_Q, W372_NW, 2>;
-    MRIACL_LAUNCH(kfn, std::min(ns * g.n_tiles16, 2 * a.sms), W372_NW * 32, smem16, a.st, q);
+    auto kfn = rowpass16_kernel<PP, QQ, NWW, 2>;
+    MRIACL_LAUNCH(kfn, std::min(ns * g.n_tiles16, 2 * a.sms), NWW * 32, smem16, a.st, q);
     if (want_norm || a.mean_std) {
       NormParams np{};
       np.in = q.out; np.out = q.out; np.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
@@ -935,7 +942,11 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
   if (g.fused) {
     FusedArgs fa{ksp, slice_stride, avg_stride, mask_w_host, out, mean_std, B, A, C, H, W, pad_left, Wp, oh, ow,
                  flags, eps, workspace, workspace_bytes, st, dev, sms};
-    if (int rc = (Wp == FUSED_P * FUSED_Q ? run_fused(fa, g) : Wp == W372_P * W372_Q ? run_fused372(fa, g) : run_fused640(fa, g))) return rc;
+    const int rc = Wp == FUSED_P * FUSED_Q   ? run_fused(fa, g)
+                   : Wp == W372_P * W372_Q ? run_fused_pq<W372_P, W372_Q, W372_NW>(fa, g)
+                   : Wp == W400_P * W400_Q ? run_fused_pq<W400_P, W400_Q, W400_NW>(fa, g)
+                                           : run_fused640(fa, g);
+    if (rc) return rc;
   } else {
     const float* mask_dev = nullptr;
     if (get_device_mask(dev, mask_w_host, W, &mask_dev)) return fail(MRIACL_ERR_CUDA, "mask upload failed: %s", rt_last_error_string());

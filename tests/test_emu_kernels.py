@@ -76,7 +76,7 @@ def test_generic_prostate_small(emu, golden):
 
 def test_fused_knee_slice(emu, golden):
     """configs[0]: the fused column pass + row pass + normalise on the 15-coil 640x368 slice."""
-    assert emu.supported(640, 368) == cabi.PATH_FUSED and emu.supported(640, 400) == cabi.PATH_GENERIC
+    assert emu.supported(640, 368) == cabi.PATH_FUSED and emu.supported(640, 320) == cabi.PATH_GENERIC
     k = synth.gaussian_kspace((1, 1) + synth.KNEE_SHAPE, 0)
     m = synth.knee_mask()
     out, ms = recon(emu, k, m, synth.CROP, cabi.NORM_INSTANCE)
@@ -197,18 +197,19 @@ def test_fused_640_wide_plan(emu):
     assert O.rel_l2(raw[0], oracle(synth.prostate_mask(), (77, 200))) <= TOL
 
 
-@pytest.mark.parametrize("W", [372, 400])
+@pytest.mark.parametrize("W", [372, 400, 320])
 def test_other_knee_widths(emu, W):
-    """H = 640 with the other knee widths: 372 = 31 x 12 runs the 16-row row pass with a 31-point first stage and a
-    12-point second stage; 400 has no specialised row kernel and takes the pruned generic row pass (Stockham on the
-    kept rows only, RSS / averages / crop fused).  Against the oracle, normalisation included; then fully sampled,
-    flipped, with a ragged last tile and the full width."""
-    assert emu.supported(640, W) == (cabi.PATH_FUSED if W == 372 else cabi.PATH_GENERIC)
+    """H = 640 with the other knee widths: 372 = 31 x 12 and 400 = 25 x 16 run the 16-row row pass with a 31- / 25-point
+    first stage and a 12- / 16-point second stage; 320 has no specialised row kernel and takes the pruned generic row
+    pass (Stockham on the kept rows only, RSS / averages / crop fused).  Against the oracle, normalisation included;
+    then fully sampled, flipped, with a ragged last tile and the full width."""
+    assert emu.supported(640, W) == (cabi.PATH_GENERIC if W == 320 else cabi.PATH_FUSED)
     k = synth.gaussian_kspace((1, 2, 2, 640, W), 43)
     m = synth.equispaced_mask(W, 4, 0.08)
-    out, ms = recon(emu, k, m, (320, 320), cabi.NORM_INSTANCE)
+    crop = (320, min(320, W))
+    out, ms = recon(emu, k, m, crop, cabi.NORM_INSTANCE)
     ims = [np.sqrt((O.complex_abs(O.ifft2c(O.apply_mask(k[0, a], m))) ** 2).sum(0)) for a in range(2)]
-    nref, mean, std = O.normalize_instance(np.ascontiguousarray(O.center_crop(np.mean(ims, axis=0), (320, 320)).astype(np.float32)))
+    nref, mean, std = O.normalize_instance(np.ascontiguousarray(O.center_crop(np.mean(ims, axis=0), crop).astype(np.float32)))
     assert O.rel_l2(out[0], nref) <= TOL
     np.testing.assert_allclose(ms[0], [mean, std], rtol=1e-5)
     raw, _ = recon(emu, k, None, (75, W), cabi.FLIP_ROWS)

@@ -4,7 +4,7 @@ import torch, numpy as np
 from mri_acl_imagesegmentation_adsp_b200 import synth
 from mri_acl_imagesegmentation_adsp_b200.recon.cartesian import zero_filled_rss
 g = torch.Generator(device="cuda").manual_seed(0)
-for W in (372, 368):
+for W in (400, 372, 368):
     k = torch.view_as_complex(torch.randn((16, 15, 640, W, 2), device="cuda", generator=g))
     m = synth.equispaced_mask(W, 4, 0.08)
     for _ in range(2): zero_filled_rss(k, m, (320, 320), "instance")
