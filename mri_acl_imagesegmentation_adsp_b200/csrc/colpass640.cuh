@@ -53,7 +53,7 @@ struct ColPassParams {
   int* done;                     // optional [n_slices]: += 1 per finished item of the slice (row pass waits on it)
   int persist;                   // single-buffer variant: 1 = grid-stride over items, 0 = one item per CTA
   int debug_skip;                // profiling only: 1 = no gather, 2 = no arithmetic, 4 = no stores (results are garbage)
-  int l2_hints;                  // 1: k-space loads evict_first, T stores evict_last (chunk-pipelined schedule)
+  int l2_hints;                  // bit 0: k-space loads evict_first, bit 1: T stores evict_last
   // co-resident schedule with a ring of T slots: slice s lives in slot s % ring, and its columns may only be written
   // once every row tile of slice s - ring has been consumed (rows_done[s - ring] == rows_target); ring = 0: no ring
   int ring;
@@ -260,7 +260,7 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
       if (j0 + k_ld < p.n_act && !(p.debug_skip & 1)) {
         const cf* src = p.ksp + b * p.sb + a * p.sa + ((long long)c * CP_N + hs) * p.W + p.act_w[j0 + k_ld];
         cf* dst = sm + buf * CP_BUF + k_ld * CP_PITCH + hs;
-        if (p.l2_hints) {
+        if (p.l2_hints & 1) {
 #pragma unroll 1
           for (int blk = 0; blk < 8; ++blk) {
             cf* d = dst + CP_BLK * ((blk + 4) & 7);
@@ -431,7 +431,7 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
         }
         radix10<true>(v);
         cf* dst = p.T + ((long long)t_frame * p.n_act + j0 + kc) * p.ohp;
-        if (p.l2_hints) {
+        if (p.l2_hints & 2) {
 #pragma unroll
           for (int m3 = 0; m3 < 10; ++m3)
             if (rr3[m3] >= 0) st_global_hint(dst + rr3[m3], v[m3], pol_t);

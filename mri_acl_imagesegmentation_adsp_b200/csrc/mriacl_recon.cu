@@ -655,7 +655,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       if (kc_ring > 0 && kc_ring < ns) {     // bounded lag between the column teams and the row teams: T stays in L2
         q.ring = kc_ring; q.rows_done = counters + ns;
         kp.cp.ring = kc_ring; kp.cp.rows_done = counters + ns; kp.cp.rows_target = g.n_tiles16;
-        kp.cp.l2_hints = 1;
+        kp.cp.l2_hints = 3;
       }
       int smem = L::smem_bytes(q.n_buf, n_act, q.n_zero);
       if (CP_SMEM_BYTES_DB + smem > SMEM_MAX) { q.n_buf = 2; smem = L::smem_bytes(2, n_act, q.n_zero); }
@@ -736,9 +736,9 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
     } else if (!overlap) {
       rt_stream_t row_st = pipelined ? ov->side : a.st;
       static const int seq_hints = env_int("MRIACL_SEQ_L2_HINTS", 0);
-      if (seq_hints && !pipelined) cp.l2_hints = 1;
+      if (seq_hints && !pipelined) cp.l2_hints = seq_hints;      // 1 = loads, 2 = stores, 3 = both
       if (pipelined) {
-        cp.l2_hints = 1;
+        cp.l2_hints = 3;
         // T buffer wb: its previous reader (row pass of group - 2) must be done
         if (group >= n_bufs_ws && rt_stream_wait_event(a.st, ov->ev_row[wb])) return fail(MRIACL_ERR_CUDA, "stream wait failed");
       }
