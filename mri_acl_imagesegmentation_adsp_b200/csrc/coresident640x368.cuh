@@ -113,4 +113,63 @@ __global__ void __launch_bounds__(KP_T, 1) knee_coresident_pair_kernel(CoresPair
   }
 }
 
+// ---- warp-group register split ------------------------------------------------------------------------------
+// Same two teams, 20 warps per CTA laid out on warp-group (4-warp) boundaries so that `setmaxnreg` can move
+// registers from the row team to the column team: the kernel is launched with 96 registers per thread (all an
+// 18-20-warp CTA can have), the three row warp groups shrink to 80 (what the row pass needs, spill-free) and the two
+// column warp groups grow to 120 (the column transform wants 115).
+//   threads   0-159  column transform warps      160-191 gather producer      192-255 idle (they only take part in
+//   the register hand-over)                      256-639 row team (12 warps, named barrier)
+constexpr int KS_T = 640, KS_ROW0 = 256;
+
+template <int REGS> __device__ __forceinline__ void kc_reg_inc() {
+#if !defined(MRIACL_EMU)
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+#endif
+}
+template <int REGS> __device__ __forceinline__ void kc_reg_dec() {
+#if !defined(MRIACL_EMU)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
+#endif
+}
+
+template <int P, int Q>
+__global__ void __launch_bounds__(KS_T, 1) knee_coresident_split_kernel(CoresParams p) {
+  MRIACL_DYN_SMEM(unsigned char, smem);
+  __shared__ FullBarrier full_bar[2];
+  __shared__ float red[KC_ROW_W];
+  __shared__ float s_stat[2];
+  __shared__ int s_ready, s_last;
+  const int tid = threadIdx.x;
+  if (tid == 0) { full_init(&full_bar[0], 32); full_init(&full_bar[1], 32); }
+  __syncthreads();
+
+  if (tid < KS_ROW0) {
+    kc_reg_inc<120>();
+    if (tid >= CP_WS_T) return;
+    const int n_items = p.cp.n_frames * p.cp.n_groups;
+    int uses[2] = {0, 0};
+    const int first = blockIdx.x;
+    if (first < n_items)
+      colpass_ws_run(p.cp, reinterpret_cast<cf*>(smem), full_bar, tid, first, gridDim.x,
+                     (n_items - first + gridDim.x - 1) / gridDim.x, uses);
+    return;
+  }
+  kc_reg_dec<80>();
+  const int t = tid - KS_ROW0;
+  unsigned char* rsm = smem + CP_SMEM_BYTES_DB;
+  const RowPass16Params& r = p.rp;
+  {
+    Rp16Smem<P, Q> S(rsm, r);
+    rp16_load_tables<KC_ROW_T>(r, S.sptw, S.sch, S.tbuf, t);
+  }
+  rp16_sync<KC_BAR_ROW, KC_ROW_T>();
+  const int n_items = r.n_slices * r.n_tiles;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    rowpass16_item<P, Q, KC_ROW_W, KC_BAR_ROW>(r, rsm, item, t, red, &s_ready);
+    if (r.done && !s_ready) return;
+    if (r.tiles_done) rowpass16_finish_slice<KC_ROW_W, KC_BAR_ROW>(r, item, t, s_stat, &s_last);
+  }
+}
+
 }  // namespace mriacl

@@ -96,6 +96,7 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)rowpass640_kernel, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_generic_kernel, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_kernel<FUSED_P, FUSED_Q>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)knee_coresident_split_kernel<FUSED_P, FUSED_Q>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_pair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 1>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 2>, SMEM_MAX / 2);
@@ -704,8 +705,14 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       static const int kc_only = env_int("MRIACL_KC_ONLY", 0);   // profiling: 1 = column teams only, 2 = row teams only (T from an earlier call)
       if (kc_only == 1) kp.rp.n_slices = 0;
       if (kc_only == 2) { kp.cp.n_frames = 0; kp.rp.done = nullptr; }
-      auto kfn = knee_coresident_kernel<FUSED_P, FUSED_Q>;
-      MRIACL_LAUNCH(kfn, grid, KC_T, CP_SMEM_BYTES_DB + smem16, a.st, kp);
+      static const int kc_split = env_int("MRIACL_KC_SPLIT", 1);   // 1: warp-group register split (setmaxnreg), 0: uniform 96 registers
+      if (kc_split) {
+        auto kfn = knee_coresident_split_kernel<FUSED_P, FUSED_Q>;
+        MRIACL_LAUNCH(kfn, grid, KS_T, CP_SMEM_BYTES_DB + smem16, a.st, kp);
+      } else {
+        auto kfn = knee_coresident_kernel<FUSED_P, FUSED_Q>;
+        MRIACL_LAUNCH(kfn, grid, KC_T, CP_SMEM_BYTES_DB + smem16, a.st, kp);
+      }
       if (run_norm && !kc_fuse_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
     } else if (fused_mode) {
       // one persistent launch: column items publish per-slice counters, row items are claimed when ready
