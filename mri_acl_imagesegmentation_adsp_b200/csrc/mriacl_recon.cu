@@ -178,10 +178,32 @@ struct FusedPlanDev {
   int* sched = nullptr;
   cf* sptw = nullptr;
   bool unit_mask = true;
-  cf* twH = nullptr;
+  cf* twH = nullptr;               // (shared twiddle cache: not owned)
   cf* twW = nullptr;
+  uint64_t stamp = 0;              // last use, for the cache bound below
+  // device tables owned by this plan; released when the plan is evicted from the cache (rt_free synchronises the
+  // device, so no kernel of an earlier call can still be reading them)
+  ~FusedPlanDev() {
+    void* owned[] = {sched_ovl, sched_p8, sptw16_dev, rp16_slot_dev, sched_p12, sched_p16, act_logical, r640_off, r640_ent,
+                     r640_perm, rpp_slot, rpp_zero, rpp_tab, act_w, act_m, sched, sptw};
+    for (void* q : owned) if (q) rt_free(q);
+  }
 };
 std::map<std::pair<int, uint64_t>, std::vector<std::shared_ptr<FusedPlanDev>>> g_fused;
+uint64_t g_plan_clock = 0;
+size_t g_plan_count = 0;
+constexpr size_t MAX_CACHED_PLANS = 64;   // per process: a data loader that draws a new random mask per volume must not leak plans
+
+// drop the least recently used plan (caller holds g_mu)
+void evict_one_plan() {
+  std::vector<std::shared_ptr<FusedPlanDev>>* best_bucket = nullptr;
+  size_t best_i = 0;
+  uint64_t best = ~0ull;
+  for (auto& kv : g_fused)
+    for (size_t i = 0; i < kv.second.size(); ++i)
+      if (kv.second[i]->stamp < best) { best = kv.second[i]->stamp; best_bucket = &kv.second; best_i = i; }
+  if (best_bucket) { best_bucket->erase(best_bucket->begin() + (long)best_i); --g_plan_count; }
+}
 
 std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left, int Wp, int oh, int ow,
                                              const float* mask, bool device_side) {
@@ -193,8 +215,10 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
       const FusedPlanHost& h = pl->host;
       if (h.H == H && h.W == W && h.pad_left == pad_left && h.Wp == Wp && h.oh == oh && h.ow == ow &&
           pl->has_mask == (mask != nullptr) &&
-          (!mask || !memcmp(pl->mask_copy.data(), mask, sizeof(float) * W)) && (pl->act_w || !device_side))
+          (!mask || !memcmp(pl->mask_copy.data(), mask, sizeof(float) * W)) && (pl->act_w || !device_side)) {
+        pl->stamp = ++g_plan_clock;
         return pl;
+      }
     }
   }
   auto pl = std::make_shared<FusedPlanDev>();
@@ -277,7 +301,9 @@ std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left
     if (!pl->twH || !pl->twW) return nullptr;
   }
   std::lock_guard<std::mutex> lk(g_mu);
+  pl->stamp = ++g_plan_clock;
   g_fused[{dev, key}].push_back(pl);
+  if (++g_plan_count > MAX_CACHED_PLANS) evict_one_plan();     // the caller's shared_ptr keeps its own plan alive for this call
   return pl;
 }
 

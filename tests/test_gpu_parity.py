@@ -254,6 +254,23 @@ def test_other_widths_behind_the_640_column_pass():
         assert torch.equal(c1, out)
 
 
+def test_plan_cache_is_bounded():
+    """a loader that draws a new random mask per volume: more distinct masks than the plan cache keeps (64); evicted plans
+    are rebuilt on demand and results never change."""
+    rng = np.random.default_rng(77)
+    k = torch.from_numpy(synth.gaussian_kspace((1, 2, 640, 368), 71)).cuda()
+    masks = [(rng.uniform(size=368) < 0.3).astype(np.float32) for _ in range(70)]
+    first, _, _ = zero_filled_rss(k, masks[0], synth.CROP, None)
+    ref0 = first.clone()
+    for m in masks[1:]:
+        zero_filled_rss(k, m, synth.CROP, None)
+    again, _, _ = zero_filled_rss(k, masks[0], synth.CROP, None)       # its plan was evicted in between
+    assert torch.equal(again, ref0)
+    want = O.center_crop(np.sqrt((O.complex_abs(O.ifft2c(O.apply_mask(k[0].cpu().numpy(), masks[69]))) ** 2).sum(0)), synth.CROP)
+    last, _, _ = zero_filled_rss(k, masks[69], synth.CROP, None)
+    assert O.rel_l2(last[0].cpu().numpy(), want.astype(np.float32)) <= TOL
+
+
 def test_fused_variants_against_oracle():
     rng = np.random.default_rng(5)
     k = synth.gaussian_kspace((2, 2, 3, 640, 368), 7)       # (S, A, C, H, W)
