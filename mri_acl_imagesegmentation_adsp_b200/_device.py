@@ -50,10 +50,15 @@ def workspace(nbytes: int) -> torch.Tensor:
 class Moved:
     """An input moved to the device together with how to hand results back."""
 
-    def __init__(self, tensor: torch.Tensor, kind: str, home: Optional[torch.device]):
-        self.tensor, self.kind, self.home = tensor, kind, home
+    def __init__(self, tensor: torch.Tensor, kind: str, home: Optional[torch.device], wide: bool = False):
+        self.tensor, self.kind, self.home, self.wide = tensor, kind, home, wide
 
-    def back(self, t: torch.Tensor) -> Any:
+    def back(self, t: torch.Tensor, widen: bool = False) -> Any:
+        """``widen``: the function is a twin of a reference function whose result dtype follows its input
+        (complex128 in -> complex128 / float64 out, ``src/utils/kspace.py:4-20``); the arithmetic itself is
+        single precision on the device."""
+        if widen and self.wide:
+            t = t.to(torch.complex128 if t.is_complex() else torch.float64)
         if self.kind == "numpy":
             return t.cpu().numpy()
         if self.home is not None and self.home.type == "cpu":
@@ -69,15 +74,16 @@ def to_device_complex(x: Any, *, name: str = "kspace") -> Moved:
         if not np.iscomplexobj(x):
             raise ValueError(f"{name} must be complex, got dtype {x.dtype}")
         t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.complex64)).to(dev, non_blocking=True)
-        return Moved(t, "numpy", None)
+        return Moved(t, "numpy", None, wide=x.dtype == np.complex128)
     if isinstance(x, torch.Tensor):
         home = x.device
+        wide = x.dtype == torch.complex128
         if not x.is_complex():
             if x.shape[-1] != 2:
                 raise ValueError("Tensor does not have separate complex dim.")
             x = torch.view_as_complex(x.to(torch.float32).contiguous())
         t = x.to(device=dev, dtype=torch.complex64, non_blocking=True).contiguous()
-        return Moved(t, "torch", home)
+        return Moved(t, "torch", home, wide=wide)
     raise ValueError(f"{name}: unsupported input type {type(x)!r}")
 
 

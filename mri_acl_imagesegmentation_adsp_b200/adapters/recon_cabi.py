@@ -25,7 +25,9 @@ ONLY_COLPASS, ONLY_ROWPASS, ONLY_NORM = 0x100, 0x200, 0x400   # profiling: singl
 PATH_NONE, PATH_GENERIC, PATH_FUSED = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIBRARY = os.path.join(os.path.dirname(_HERE), "csrc", "libmriacl_recon.so")
+#: the product library; MRIACL_RECON_LIBRARY selects another build of the same C ABI (A/B runs of the experimental
+#: schedules: `make -C csrc experimental` -> libmriacl_recon_exp.so).  Never a CPU library: there is none.
+DEFAULT_LIBRARY = os.environ.get("MRIACL_RECON_LIBRARY") or os.path.join(os.path.dirname(_HERE), "csrc", "libmriacl_recon.so")
 
 _vp, _i, _u, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_uint, C.c_float, C.c_longlong, C.c_size_t
 _fp = C.POINTER(C.c_float)

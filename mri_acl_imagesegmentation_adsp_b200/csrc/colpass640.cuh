@@ -20,8 +20,12 @@
 //
 // Shared-memory layout per column: slot(m1, m2, n3) = 90 m1 + 10 m2 + n3 (each block of 80 is
 // padded to 90) and column pitch 722 complex.  With it pass 1 (lanes over 10 n2 + n3), pass 2
-// (lanes over 10 m1 + n3), the gather store (lanes = 8 columns x 4 rows) and pass 3's 128-bit
-// loads (lanes over m1, then m2) are all free of bank conflicts; see DESIGN.md.
+// (lanes over 10 m1 + n3) and pass 3's 128-bit loads (lanes over m1, then m2) run at the ideal
+// wavefront count (ncu source view, profiles/r02_colpass_smem_wavefronts.md: LDS.64 / STS.64 / LDS.128 excess 0).
+// The gather itself is different: an LDGSTS writes shared memory once per 128-byte global line it
+// touched, and at 4x undersampling a line holds only four wanted elements, so the 8-byte copies
+// cost 3.4x their ideal wavefronts (reported by ncu as "bank conflicts": 19 % of the kernel's
+// shared-memory wavefronts).  That is a property of the access pattern, not of the layout.
 #pragma once
 #include "butterflies.cuh"
 
@@ -90,6 +94,7 @@ template <int N_PENDING> __device__ __forceinline__ void cp_async_wait_group() {
 #endif
 }
 
+#ifdef MRIACL_EXPERIMENTAL   // the compute warps issue their own gather: superseded by the warp-specialised kernel below
 // DB = true: persistent grid, next item's gather in flight during the arithmetic (2 CTAs/SM);
 // DB = false: one item per CTA, single buffer (4 CTAs/SM; leaves room for a row-pass CTA on the SM).
 template <bool DB>
@@ -226,6 +231,8 @@ __global__ void __launch_bounds__(CP_T, DB ? 2 : 4) colpass640_kernel(ColPassPar
 }
 
 
+#endif  // MRIACL_EXPERIMENTAL
+
 // ---------------------------------------------------------------------------------------------
 // Warp-specialised column pass: 5 compute warps + 1 producer warp per CTA, two item buffers.
 // An LDGSTS whose queue is full stalls the issuing warp, so when the compute warps issue their own
@@ -257,7 +264,7 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
       const int f = p.frame0 + fl;
       const int b = f / (p.A * p.C), a = (f / p.C) % p.A, c = f % p.C;
       const int j0 = g * CP_G;
-      if (j0 + k_ld < p.n_act && !(p.debug_skip & 1)) {
+      if (j0 + k_ld < p.n_act && !MRIACL_DBG_SKIP(p, 1)) {
         const cf* src = p.ksp + b * p.sb + a * p.sa + ((long long)c * CP_N + hs) * p.W + p.act_w[j0 + k_ld];
         cf* dst = sm + buf * CP_BUF + k_ld * CP_PITCH + hs;
         if (p.l2_hints & 1) {
@@ -321,7 +328,7 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
     cf* cur = sm + buf * CP_BUF;
     full_wait(&full_bar[buf], (uses[buf] + (k >> 1)) & 1, CP_BAR_FULL + buf, CP_WS_T);
 
-    const int ncols_c = (p.debug_skip & 2) ? 0 : ncols;
+    const int ncols_c = MRIACL_DBG_SKIP(p, 2) ? 0 : ncols;
     // Full item (8 columns): each thread owns columns sub, sub+2, sub+4, sub+6 and keeps all four butterflies of a
     // pass in flight (4-way instruction-level parallelism between the team barriers); ragged items take the loop below.
     if (ncols_c == CP_G && p.unit_mask) {
@@ -435,11 +442,11 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
 #pragma unroll
           for (int m3 = 0; m3 < 10; ++m3)
             if (rr3[m3] >= 0) st_global_hint(dst + rr3[m3], v[m3], pol_t);
-        } else if (!(p.debug_skip & 4)) {
+        } else if (!MRIACL_DBG_SKIP(p, 4)) {
 #pragma unroll
           for (int m3 = 0; m3 < 10; ++m3)
             if (rr3[m3] >= 0) dst[rr3[m3]] = v[m3];
-        } else if (v[0].x == 1.2345f) dst[0] = v[1];
+        }
       }
     }
     if (p.done) {

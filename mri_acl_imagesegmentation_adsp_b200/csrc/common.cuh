@@ -13,6 +13,13 @@
   type* name = reinterpret_cast<type*>(mriacl_dyn_smem_raw)
 #endif
 
+// profiling switches that skip parts of a kernel (results are garbage) exist in the experimental build only
+#ifdef MRIACL_EXPERIMENTAL
+#define MRIACL_DBG_SKIP(p, bits) ((p).debug_skip & (bits))
+#else
+#define MRIACL_DBG_SKIP(p, bits) 0
+#endif
+
 namespace mriacl {
 
 typedef float2 cf;  // complex64: x = re, y = im

@@ -18,11 +18,15 @@
 #include "colpass640.cuh"
 #include "rowpass.cuh"
 #include "rowpass16.cuh"
-#include "rowpair.cuh"
 #include "rowpass640.cuh"
 #include "rowpass_generic.cuh"
+#ifdef MRIACL_EXPERIMENTAL
+// schedules that were built, measured and found slower than `sequential`: kept as negative
+// results for the emulator tests and for A/B runs, not part of the product library
+#include "rowpair.cuh"
 #include "fused640x368.cuh"
 #include "coresident640x368.cuh"
+#endif
 
 using namespace mriacl;
 
@@ -55,7 +59,9 @@ int device_sms(int dev) {
   return d.sms;
 }
 
+#ifdef MRIACL_EXPERIMENTAL
 int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+#endif
 
 constexpr int FUSED_P = 23, FUSED_Q = 16;      // 368-wide knee plans
 constexpr int W372_P = 31, W372_Q = 12;        // 372-wide knee plans: same row-pass kernel, 31-point first stage, 12-point second
@@ -65,10 +71,15 @@ constexpr int W400_NW = 7;                     // 13 output pairs over 7 warps
 constexpr int SMEM_MAX = 227 * 1024 - 512;     // dynamic shared memory a B200 CTA may opt in to (227 KB minus the kernels' static part)
 // Row-pass CTA shapes: 16 warps (one CTA owns the SM) for the sequential schedule, 8 warps for the
 // overlapped schedule, where one row-pass CTA shares each SM with column-pass CTAs.
-constexpr int RP_NW_SEQ = 16, RP_NW_OVL = 8;
+constexpr int RP_NW_SEQ = 16;
+#ifdef MRIACL_EXPERIMENTAL
+constexpr int RP_NW_OVL = 8;
+#endif
 // Pair row pass (rowpair.cuh): dense residues every RPP_STEP-th, at most RPP_NE extra columns per other residue.
 // That is the 4x-equispaced + low-frequency-block mask family; other masks keep the cooperative row pass.
+#ifdef MRIACL_EXPERIMENTAL
 constexpr int RPP_STEP = 4, RPP_NE = 2;
+#endif
 
 
 
@@ -80,230 +91,223 @@ int ensure_smem_attrs(int dev) {
   if (d.smem_set) return 0;
   int bad = 0;
   bad |= rt_allow_smem((const void*)generic_fft_kernel, GEN_SMEM_BYTES);
-  const int cp_carve = env_int("MRIACL_CP_CARVEOUT", -1);
-  bad |= rt_allow_smem((const void*)colpass640_kernel<true>, CP_SMEM_BYTES_DB, cp_carve);
-  bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB, cp_carve);   // default carveout: 2 CTAs -> 196 KB, 60 KB of L1 left for the gather
-  bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, 100);   // co-resident with rowpass<8>: same carveout
-  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
-  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX, 100);
-  bad |= rt_allow_smem((const void*)fused640_kernel<FUSED_P, FUSED_Q>, SMEM_MAX / 2);
+  bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB);   // default carveout: 2 CTAs -> 196 KB, 60 KB of L1 left for the gather
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2);
-  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
-  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
-  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 8, 3>, SMEM_MAX / 3);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<W372_P, W372_Q, W372_NW, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<W400_P, W400_Q, W400_NW, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass640_kernel, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_generic_kernel, SMEM_MAX);
+#ifdef MRIACL_EXPERIMENTAL
+  const int cp_carve = env_int("MRIACL_CP_CARVEOUT", -1);
+  if (cp_carve >= 0) bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB, cp_carve);
+  bad |= rt_allow_smem((const void*)colpass640_kernel<true>, CP_SMEM_BYTES_DB, cp_carve);
+  bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, 100);   // co-resident with rowpass<8>: same carveout
+  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_OVL>, SMEM_MAX, 100);
+  bad |= rt_allow_smem((const void*)fused640_kernel<FUSED_P, FUSED_Q>, SMEM_MAX / 2);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 1>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 16, 1>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 8, 3>, SMEM_MAX / 3);
   bad |= rt_allow_smem((const void*)knee_coresident_kernel<FUSED_P, FUSED_Q>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_split_kernel<FUSED_P, FUSED_Q>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)knee_coresident_pair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 1>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpair_kernel<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE, 2>, SMEM_MAX / 2);
+#endif
   if (!bad) d.smem_set = true;
   return bad;
 }
 
-// ---- device-resident tables, built once and cached -------------------------------------
+// ---- device-resident tables, built once and cached (every cache is bounded: a data loader that draws a new random
+// mask or meets a new width per volume must not leak device memory) --------------------------------------------------
 struct DeviceBuf {
   void* p = nullptr;
-  ~DeviceBuf() { /* lives for the process; the driver reclaims at exit */ }
+  DeviceBuf() = default;
+  DeviceBuf(const DeviceBuf&) = delete;
+  DeviceBuf& operator=(const DeviceBuf&) = delete;
+  ~DeviceBuf() { if (p) rt_free(p); }      // rt_free synchronises the device: no kernel of an earlier call still reads it
 };
+typedef std::shared_ptr<DeviceBuf> DevPtr;
+
+// allocate + upload `n` elements; an empty vector gets a one-element allocation so that the pointer is never null
+template <class T> DevPtr dev_upload(const T* host, size_t n) {
+  auto b = std::make_shared<DeviceBuf>();
+  if (rt_malloc(&b->p, sizeof(T) * std::max<size_t>(1, n))) return nullptr;
+  if (n && rt_upload(b->p, host, sizeof(T) * n)) return nullptr;
+  return b;
+}
+template <class T> DevPtr dev_upload(const std::vector<T>& v) { return dev_upload(v.data(), v.size()); }
+
+uint64_t g_clock = 0;                      // LRU stamps (under g_mu)
+constexpr size_t MAX_CACHED_TWIDDLES = 64, MAX_CACHED_MASKS = 64, MAX_CACHED_PLANS = 64;
 
 // forward twiddles w_N^k = exp(-2 pi i k/N) for the generic kernel, and inverse-sign tables
 // for the fused kernels; key = (device, N, sign)
-std::map<std::tuple<int, int, int>, cf*> g_tw;
+struct TwEntry { DevPtr buf; uint64_t stamp; };
+std::map<std::tuple<int, int, int>, TwEntry> g_tw;
 
-cf* get_twiddles(int dev, int n, int sign) {
-  std::lock_guard<std::mutex> lk(g_mu);
+DevPtr get_twiddles(int dev, int n, int sign) {
   auto key = std::make_tuple(dev, n, sign);
-  auto it = g_tw.find(key);
-  if (it != g_tw.end()) return it->second;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) { it->second.stamp = ++g_clock; return it->second.buf; }
+  }
   std::vector<HostCf> t = make_twiddles(n, sign);
-  void* d = nullptr;
-  if (rt_malloc(&d, sizeof(HostCf) * n) || rt_upload(d, t.data(), sizeof(HostCf) * n)) return nullptr;
-  g_tw[key] = (cf*)d;
-  return (cf*)d;
+  DevPtr d = dev_upload(t);
+  if (!d) return nullptr;
+  DevPtr evicted;                          // released after the lock is dropped (cudaFree synchronises)
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) { it->second.stamp = ++g_clock; return it->second.buf; }   // another thread was faster
+    g_tw[key] = TwEntry{d, ++g_clock};
+    if (g_tw.size() > MAX_CACHED_TWIDDLES) {
+      auto victim = g_tw.end();
+      for (auto jt = g_tw.begin(); jt != g_tw.end(); ++jt)
+        if (jt->first != key && (victim == g_tw.end() || jt->second.stamp < victim->second.stamp)) victim = jt;
+      if (victim != g_tw.end()) { evicted = victim->second.buf; g_tw.erase(victim); }
+    }
+  }
+  return d;
 }
 
-struct MaskDev { std::vector<float> host; float* dev = nullptr; };
-std::map<std::pair<int, uint64_t>, std::vector<MaskDev>> g_masks;
+struct MaskDev { std::vector<float> host; DevPtr dev; int device; uint64_t stamp; };
+std::vector<MaskDev> g_masks;
 
-// device copy of a host mask (generic path); nullptr mask -> nullptr
-int get_device_mask(int dev, const float* mask, int w, const float** out) {
+// device copy of a host mask (generic path); nullptr mask -> nullptr.  `keep` holds the buffer for the caller.
+int get_device_mask(int dev, const float* mask, int w, const float** out, DevPtr& keep) {
   *out = nullptr;
   if (!mask) return 0;
-  std::lock_guard<std::mutex> lk(g_mu);
-  const int dims[1] = {w};
-  auto& bucket = g_masks[{dev, plan_key(dims, 1, mask, w)}];
-  for (auto& m : bucket)
-    if ((int)m.host.size() == w && !memcmp(m.host.data(), mask, sizeof(float) * w)) { *out = m.dev; return 0; }
-  MaskDev m;
-  m.host.assign(mask, mask + w);
-  void* d = nullptr;
-  if (rt_malloc(&d, sizeof(float) * w) || rt_upload(d, mask, sizeof(float) * w)) return 1;
-  m.dev = (float*)d;
-  bucket.push_back(m);
-  *out = m.dev;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& m : g_masks)
+      if (m.device == dev && (int)m.host.size() == w && !memcmp(m.host.data(), mask, sizeof(float) * w)) {
+        m.stamp = ++g_clock; keep = m.dev; *out = (const float*)keep->p; return 0;
+      }
+  }
+  DevPtr d = dev_upload(mask, (size_t)w);
+  if (!d) return 1;
+  DevPtr evicted;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_masks.push_back(MaskDev{std::vector<float>(mask, mask + w), d, dev, ++g_clock});
+    if (g_masks.size() > MAX_CACHED_MASKS) {
+      size_t victim = 0;
+      for (size_t i = 1; i + 1 < g_masks.size(); ++i) if (g_masks[i].stamp < g_masks[victim].stamp) victim = i;
+      evicted = g_masks[victim].dev;
+      g_masks.erase(g_masks.begin() + (long)victim);
+    }
+  }
+  keep = d; *out = (const float*)d->p;
   return 0;
 }
 
 struct FusedPlanDev {
-  FusedPlanHost host;            // schedule for RP_NW_SEQ warps
-  FusedPlanHost host_ovl;        // schedule for RP_NW_OVL warps (same columns, same sptw)
-  int* sched_ovl = nullptr;
-  std::vector<int> pairs12, pairs16, pairs8;   // 16-row kernel: pair schedules for 12, 16 and 8 warps
-  int* sched_p8 = nullptr;
+  FusedPlanHost host;            // column list + the 32-row schedule the pair schedules are derived from
+  std::vector<int> pairs12, pairs8;   // 16-row kernel: pair schedules for 12 and 8 (7 for 400-wide plans) warps
   std::vector<HostCf> sptw16;
-  cf* sptw16_dev = nullptr;
   std::vector<int> rp16_slot_of_j;     // residue-major staged tile of the 16-row row pass
   int rp16_slots = 0;
-  int* rp16_slot_dev = nullptr;
-  int* sched_p12 = nullptr;
-  int* sched_p16 = nullptr;
-  int* act_logical = nullptr;      // pruned generic row pass: logical index of active column j in the padded line
-  cf* twW_fwd = nullptr;           // forward-sign twiddles of the padded width (Stockham stages)
   Row640PlanHost r640;             // 640-wide row pass (Wp == 640 plans)
-  int* r640_off = nullptr;
-  int* r640_ent = nullptr;
-  int* r640_perm = nullptr;
-  RowPairPlanHost rpp;             // pair row pass (ok = the mask fits its template)
-  int* rpp_slot = nullptr;
-  int* rpp_zero = nullptr;
-  float* rpp_tab = nullptr;
   std::vector<float> mask_copy;
   bool has_mask = false;
-  int* act_w = nullptr;
-  float* act_m = nullptr;
-  int* sched = nullptr;
-  cf* sptw = nullptr;
   bool unit_mask = true;
-  cf* twH = nullptr;               // (shared twiddle cache: not owned)
-  cf* twW = nullptr;
-  uint64_t stamp = 0;              // last use, for the cache bound below
-  // device tables owned by this plan; released when the plan is evicted from the cache (rt_free synchronises the
-  // device, so no kernel of an earlier call can still be reading them)
-  ~FusedPlanDev() {
-    void* owned[] = {sched_ovl, sched_p8, sptw16_dev, rp16_slot_dev, sched_p12, sched_p16, act_logical, r640_off, r640_ent,
-                     r640_perm, rpp_slot, rpp_zero, rpp_tab, act_w, act_m, sched, sptw};
-    for (void* q : owned) if (q) rt_free(q);
+  // device tables: owned through the DevPtrs below, released when the plan is evicted from the cache and the last
+  // call using it has returned
+  std::vector<DevPtr> owned;
+  int* act_w = nullptr; float* act_m = nullptr;
+  int* sched_p8 = nullptr; int* sched_p12 = nullptr; cf* sptw16_dev = nullptr; int* rp16_slot_dev = nullptr;
+  int* act_logical = nullptr;      // pruned generic row pass: logical index of active column j in the padded line
+  int* r640_off = nullptr; int* r640_ent = nullptr; int* r640_perm = nullptr;
+  cf* twH = nullptr; cf* twW = nullptr; cf* twW_fwd = nullptr;     // (shared twiddle cache entries, kept alive by `owned`)
+#ifdef MRIACL_EXPERIMENTAL
+  FusedPlanHost host_ovl;        // schedule for RP_NW_OVL warps (same columns, same sptw)
+  std::vector<int> pairs16;
+  RowPairPlanHost rpp;           // pair row pass (ok = the mask fits its template)
+  int* sched = nullptr; cf* sptw = nullptr; int* sched_ovl = nullptr; int* sched_p16 = nullptr;
+  int* rpp_slot = nullptr; int* rpp_zero = nullptr; float* rpp_tab = nullptr;
+#endif
+  uint64_t stamp = 0;              // last use, for the cache bound
+  template <class T, class U> bool put(const std::vector<U>& v, T*& member) {
+    DevPtr d = dev_upload(v);
+    if (!d) return false;
+    owned.push_back(d);            // ownership first: an early return never leaks
+    member = (T*)d->p;
+    return true;
   }
+  bool hold(const DevPtr& d, cf*& member) { if (!d) return false; owned.push_back(d); member = (cf*)d->p; return true; }
 };
-std::map<std::pair<int, uint64_t>, std::vector<std::shared_ptr<FusedPlanDev>>> g_fused;
-uint64_t g_plan_clock = 0;
+typedef std::shared_ptr<FusedPlanDev> PlanPtr;
+std::map<std::pair<int, uint64_t>, std::vector<PlanPtr>> g_fused;
 size_t g_plan_count = 0;
-constexpr size_t MAX_CACHED_PLANS = 64;   // per process: a data loader that draws a new random mask per volume must not leak plans
 
-// drop the least recently used plan (caller holds g_mu)
-void evict_one_plan() {
-  std::vector<std::shared_ptr<FusedPlanDev>>* best_bucket = nullptr;
-  size_t best_i = 0;
-  uint64_t best = ~0ull;
-  for (auto& kv : g_fused)
-    for (size_t i = 0; i < kv.second.size(); ++i)
-      if (kv.second[i]->stamp < best) { best = kv.second[i]->stamp; best_bucket = &kv.second; best_i = i; }
-  if (best_bucket) { best_bucket->erase(best_bucket->begin() + (long)best_i); --g_plan_count; }
+bool plan_matches(const FusedPlanDev& pl, int H, int W, int pad_left, int Wp, int oh, int ow, const float* mask, bool device_side) {
+  const FusedPlanHost& h = pl.host;
+  return h.H == H && h.W == W && h.pad_left == pad_left && h.Wp == Wp && h.oh == oh && h.ow == ow &&
+         pl.has_mask == (mask != nullptr) && (!mask || !memcmp(pl.mask_copy.data(), mask, sizeof(float) * W)) &&
+         (pl.act_w || !device_side);
 }
 
-std::shared_ptr<FusedPlanDev> get_fused_plan(int dev, int H, int W, int pad_left, int Wp, int oh, int ow,
-                                             const float* mask, bool device_side) {
+PlanPtr get_fused_plan(int dev, int H, int W, int pad_left, int Wp, int oh, int ow, const float* mask, bool device_side) {
   const int dims[6] = {H, W, pad_left, Wp, oh, ow};
   const uint64_t key = plan_key(dims, 6, mask, W);
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    for (auto& pl : g_fused[{dev, key}]) {
-      const FusedPlanHost& h = pl->host;
-      if (h.H == H && h.W == W && h.pad_left == pad_left && h.Wp == Wp && h.oh == oh && h.ow == ow &&
-          pl->has_mask == (mask != nullptr) &&
-          (!mask || !memcmp(pl->mask_copy.data(), mask, sizeof(float) * W)) && (pl->act_w || !device_side)) {
-        pl->stamp = ++g_plan_clock;
-        return pl;
-      }
-    }
+    for (auto& pl : g_fused[{dev, key}])
+      if (plan_matches(*pl, H, W, pad_left, Wp, oh, ow, mask, device_side)) { pl->stamp = ++g_clock; return pl; }
   }
   auto pl = std::make_shared<FusedPlanDev>();
   const int planP = Wp == W372_P * W372_Q ? W372_P : Wp == W400_P * W400_Q ? W400_P : FUSED_P;
   const int planQ = Wp == W372_P * W372_Q ? W372_Q : Wp == W400_P * W400_Q ? W400_Q : FUSED_Q;
   build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, planP, planQ, RP_NW_SEQ, RP_MAX_SPARSE, /*split_dense=*/true, pl->host);
-  build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, planP, planQ, RP_NW_OVL, RP_MAX_SPARSE, /*split_dense=*/true, pl->host_ovl);
   pl->has_mask = mask != nullptr;
   if (mask) pl->mask_copy.assign(mask, mask + W);
   if (device_side) {
     const FusedPlanHost& h = pl->host;
-    void *a = nullptr, *m = nullptr, *s = nullptr;
-    const size_t na = h.act_w.size();
-    if (rt_malloc(&a, sizeof(int) * na) || rt_malloc(&m, sizeof(float) * na) || rt_malloc(&s, sizeof(int) * h.sched.size()))
-      return nullptr;
-    if (na && (rt_upload(a, h.act_w.data(), sizeof(int) * na) || rt_upload(m, h.act_m.data(), sizeof(float) * na)))
-      return nullptr;
-    if (rt_upload(s, h.sched.data(), sizeof(int) * h.sched.size())) return nullptr;
-    void* t = nullptr;
-    if (rt_malloc(&t, sizeof(HostCf) * h.sptw.size())) return nullptr;
-    if (!h.sptw.empty() && rt_upload(t, h.sptw.data(), sizeof(HostCf) * h.sptw.size())) return nullptr;
-    void* s2 = nullptr;
-    if (rt_malloc(&s2, sizeof(int) * pl->host_ovl.sched.size()) ||
-        rt_upload(s2, pl->host_ovl.sched.data(), sizeof(int) * pl->host_ovl.sched.size())) return nullptr;
-    pl->sched_ovl = (int*)s2;
+    if (!pl->put(h.act_w, pl->act_w) || !pl->put(h.act_m, pl->act_m)) return nullptr;
     build_pair_schedule(pl->host, 12, pl->pairs12, pl->sptw16, &pl->rp16_slot_of_j, &pl->rp16_slots);
-    {
-      void* sj = nullptr;
-      const size_t nb = sizeof(int) * std::max<size_t>(1, pl->rp16_slot_of_j.size());
-      if (rt_malloc(&sj, nb) || (!pl->rp16_slot_of_j.empty() && rt_upload(sj, pl->rp16_slot_of_j.data(), sizeof(int) * pl->rp16_slot_of_j.size()))) return nullptr;
-      pl->rp16_slot_dev = (int*)sj;
-    }
-    build_pair_schedule(pl->host, 16, pl->pairs16, pl->sptw16);
-    void *s3 = nullptr, *s4 = nullptr, *t16 = nullptr;
-    if (rt_malloc(&t16, sizeof(HostCf) * pl->sptw16.size()) ||
-        (!pl->sptw16.empty() && rt_upload(t16, pl->sptw16.data(), sizeof(HostCf) * pl->sptw16.size()))) return nullptr;
-    pl->sptw16_dev = (cf*)t16;
-    if (rt_malloc(&s3, sizeof(int) * pl->pairs12.size()) || rt_upload(s3, pl->pairs12.data(), sizeof(int) * pl->pairs12.size()) ||
-        rt_malloc(&s4, sizeof(int) * pl->pairs16.size()) || rt_upload(s4, pl->pairs16.data(), sizeof(int) * pl->pairs16.size()))
-      return nullptr;
-    pl->sched_p12 = (int*)s3; pl->sched_p16 = (int*)s4;
-    build_pair_schedule(pl->host, Wp == W400_P * W400_Q ? W400_NW : FZ_ROW_WARPS, pl->pairs8, pl->sptw16);   // (8 warps; 7 for the 400-wide plans)
-    void* s5 = nullptr;
-    if (rt_malloc(&s5, sizeof(int) * pl->pairs8.size()) || rt_upload(s5, pl->pairs8.data(), sizeof(int) * pl->pairs8.size())) return nullptr;
-    pl->sched_p8 = (int*)s5;
+    build_pair_schedule(pl->host, Wp == W400_P * W400_Q ? W400_NW : 8, pl->pairs8, pl->sptw16);   // (8 warps; 7 for the 400-wide plans)
+    if (!pl->put(pl->rp16_slot_of_j, pl->rp16_slot_dev) || !pl->put(pl->sptw16, pl->sptw16_dev) ||
+        !pl->put(pl->pairs12, pl->sched_p12) || !pl->put(pl->pairs8, pl->sched_p8)) return nullptr;
     if (Wp != CP_N && Wp != FUSED_P * FUSED_Q) {      // (372 too: its dense plans fall back to the pruned generic row pass)
-      std::vector<int> lg(std::max<size_t>(1, pl->host.act_w.size()), 0);
-      for (size_t j = 0; j < pl->host.act_w.size(); ++j) lg[j] = logical_of_phys(pl->host.act_w[j] + pad_left, Wp);
-      void* o = nullptr;
-      if (rt_malloc(&o, sizeof(int) * lg.size()) || rt_upload(o, lg.data(), sizeof(int) * lg.size())) return nullptr;
-      pl->act_logical = (int*)o;
-      pl->twW_fwd = get_twiddles(dev, Wp, -1);
-      if (!pl->twW_fwd) return nullptr;
+      std::vector<int> lg(std::max<size_t>(1, h.act_w.size()), 0);
+      for (size_t j = 0; j < h.act_w.size(); ++j) lg[j] = logical_of_phys(h.act_w[j] + pad_left, Wp);
+      if (!pl->put(lg, pl->act_logical) || !pl->hold(get_twiddles(dev, Wp, -1), pl->twW_fwd)) return nullptr;
     }
     if (Wp == CP_N) {
       build_row640_plan(pl->host, pl->r640);
-      void *o1 = nullptr, *o2 = nullptr;
-      if (rt_malloc(&o1, sizeof(int) * 81) || rt_malloc(&o2, sizeof(int) * (pl->r640.ent.size() + 1)) ||
-          rt_upload(o1, pl->r640.pos_off.data(), sizeof(int) * 81) ||
-          (!pl->r640.ent.empty() && rt_upload(o2, pl->r640.ent.data(), sizeof(int) * pl->r640.ent.size()))) return nullptr;
-      void* o3 = nullptr;
-      if (rt_malloc(&o3, sizeof(int) * 160) || rt_upload(o3, pl->r640.perm.data(), sizeof(int) * 160)) return nullptr;
-      pl->r640_off = (int*)o1; pl->r640_ent = (int*)o2; pl->r640_perm = (int*)o3;
+      if (!pl->put(pl->r640.pos_off, pl->r640_off) || !pl->put(pl->r640.ent, pl->r640_ent) ||
+          !pl->put(pl->r640.perm, pl->r640_perm)) return nullptr;
     }
+#ifdef MRIACL_EXPERIMENTAL
+    build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, planP, planQ, RP_NW_OVL, RP_MAX_SPARSE, /*split_dense=*/true, pl->host_ovl);
+    build_pair_schedule(pl->host, 16, pl->pairs16, pl->sptw16);
+    if (!pl->put(h.sched, pl->sched) || !pl->put(h.sptw, pl->sptw) || !pl->put(pl->host_ovl.sched, pl->sched_ovl) ||
+        !pl->put(pl->pairs16, pl->sched_p16)) return nullptr;
     build_rowpair_plan(pl->host, RPP_STEP, RPP_NE, pl->rpp);
-    if (pl->rpp.ok) {
-      void *q1 = nullptr, *q2 = nullptr, *q3 = nullptr;
-      const RowPairPlanHost& r = pl->rpp;
-      if (rt_malloc(&q1, sizeof(int) * r.slot_of_j.size()) || rt_malloc(&q2, sizeof(int) * (r.zero_slots.size() + 1)) ||
-          rt_malloc(&q3, sizeof(float) * r.tables.size())) return nullptr;
-      if ((!r.slot_of_j.empty() && rt_upload(q1, r.slot_of_j.data(), sizeof(int) * r.slot_of_j.size())) ||
-          (!r.zero_slots.empty() && rt_upload(q2, r.zero_slots.data(), sizeof(int) * r.zero_slots.size())) ||
-          rt_upload(q3, r.tables.data(), sizeof(float) * r.tables.size())) return nullptr;
-      pl->rpp_slot = (int*)q1; pl->rpp_zero = (int*)q2; pl->rpp_tab = (float*)q3;
-    }
-    pl->act_w = (int*)a; pl->act_m = (float*)m; pl->sched = (int*)s; pl->sptw = (cf*)t;
+    if (pl->rpp.ok && (!pl->put(pl->rpp.slot_of_j, pl->rpp_slot) || !pl->put(pl->rpp.zero_slots, pl->rpp_zero) ||
+                       !pl->put(pl->rpp.tables, pl->rpp_tab))) return nullptr;
+#endif
     for (float v : h.act_m) if (v != 1.0f) pl->unit_mask = false;
-    pl->twH = get_twiddles(dev, H, +1);
-    pl->twW = get_twiddles(dev, Wp, +1);
-    if (!pl->twH || !pl->twW) return nullptr;
+    if (!pl->hold(get_twiddles(dev, H, +1), pl->twH) || !pl->hold(get_twiddles(dev, Wp, +1), pl->twW)) return nullptr;
   }
+  PlanPtr evicted;                           // destroyed (cudaFree, device synchronisation) after the lock is dropped
   std::lock_guard<std::mutex> lk(g_mu);
-  pl->stamp = ++g_plan_clock;
-  g_fused[{dev, key}].push_back(pl);
-  if (++g_plan_count > MAX_CACHED_PLANS) evict_one_plan();     // the caller's shared_ptr keeps its own plan alive for this call
+  auto& bucket = g_fused[{dev, key}];
+  for (auto& other : bucket)                 // two threads missed on the same key: keep the first plan
+    if (plan_matches(*other, H, W, pad_left, Wp, oh, ow, mask, device_side)) { other->stamp = ++g_clock; evicted = pl; return other; }
+  pl->stamp = ++g_clock;
+  bucket.push_back(pl);
+  if (++g_plan_count > MAX_CACHED_PLANS) {   // drop the least recently used plan (the caller's PlanPtr keeps its own alive)
+    std::vector<PlanPtr>* best_bucket = nullptr;
+    size_t best_i = 0;
+    uint64_t best = ~0ull;
+    for (auto& kv : g_fused)
+      for (size_t i = 0; i < kv.second.size(); ++i)
+        if (kv.second[i] != pl && kv.second[i]->stamp < best) { best = kv.second[i]->stamp; best_bucket = &kv.second; best_i = i; }
+    if (best_bucket) { evicted = (*best_bucket)[best_i]; best_bucket->erase(best_bucket->begin() + (long)best_i); --g_plan_count; }
+  }
   return pl;
 }
 
@@ -356,8 +360,9 @@ int launch_generic_pass(GenFftParams gp, int dev, rt_stream_t st) {
   if ((int)rad.size() > MRIACL_GEN_MAX_STAGES) return fail(MRIACL_ERR_UNSUPPORTED, "too many FFT stages for N=%d", gp.N);
   gp.n_stages = (int)rad.size();
   for (int i = 0; i < gp.n_stages; ++i) gp.radix[i] = rad[i];
-  gp.tw = get_twiddles(dev, gp.N, -1);
-  if (!gp.tw) return fail(MRIACL_ERR_CUDA, "twiddle table allocation failed: %s", rt_last_error_string());
+  const DevPtr tw = get_twiddles(dev, gp.N, -1);     // (an evicted table is freed with a device synchronisation, after this launch)
+  if (!tw) return fail(MRIACL_ERR_CUDA, "twiddle table allocation failed: %s", rt_last_error_string());
+  gp.tw = (const cf*)tw->p;
   int L = MRIACL_GEN_SMEM_ELEMS / gp.N;
   L = L < 1 ? 1 : (L > 8 ? 8 : L);
   if (L > gp.lines_per_frame) L = gp.lines_per_frame;
@@ -390,27 +395,6 @@ int generic_fft2c(const cf* in, long long sb, long long sa, int A, int C, cf* ou
   return launch_generic_pass(c, dev, st);
 }
 
-// ---- side stream + events of the overlapped schedule, one set per (device, caller stream) ----
-struct OverlapRes { rt_stream_t side = nullptr; rt_event_t ev_start[2], ev_row[2]; int* error_flag = nullptr; bool ok = false; };
-std::map<std::pair<int, void*>, OverlapRes> g_ovl;
-
-OverlapRes* get_overlap_res(int dev, rt_stream_t st) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  OverlapRes& r = g_ovl[{dev, (void*)st}];
-  if (!r.ok) {
-    int bad = rt_stream_create_high_priority(&r.side);
-    for (int i = 0; i < 2; ++i) { bad |= rt_event_create(&r.ev_start[i]); bad |= rt_event_create(&r.ev_row[i]); }
-    void* ef = nullptr;
-    const int zero = 0;
-    bad |= rt_malloc(&ef, sizeof(int));
-    if (!bad) bad |= rt_upload(ef, &zero, sizeof(int));
-    if (bad) return nullptr;
-    r.error_flag = (int*)ef;
-    r.ok = true;
-  }
-  return &r;
-}
-
 struct FusedArgs {
   const cf* ksp; long long slice_stride, avg_stride; const float* mask; float* out; float* mean_std;
   int B, A, C, H, W, pad_left, Wp, oh, ow; unsigned flags; float eps;
@@ -418,12 +402,15 @@ struct FusedArgs {
 };
 
 int run_fused640(const FusedArgs& a, const ReconGeom& g);
+#ifdef MRIACL_EXPERIMENTAL
+int run_fused_experimental(const FusedArgs& a, const ReconGeom& g);
+#endif
 
 // The 640 x 372 and 640 x 400 knee plans: column pass -> 16-row row pass with a P-point first stage and a Q-point second
 // stage (372 = 31 x 12, 400 = 25 x 16; same kernel template and plan builder as the 368-wide plans) -> normalise.
 template <int PP, int QQ, int NWW>
 int run_fused_pq(const FusedArgs& a, const ReconGeom& g) {
-  std::shared_ptr<FusedPlanDev> pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
+  PlanPtr pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
   if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
   const int n_act = (int)pl->host.act_w.size();
   const int n_groups = (n_act + CP_G - 1) / CP_G;
@@ -477,7 +464,7 @@ int run_fused_pq(const FusedArgs& a, const ReconGeom& g) {
 // The 640 x 640 plans (prostate-shape) and every other width behind the H = 640 column pass:
 // column pass -> 640-wide row pass / pruned generic row pass -> normalise, back to back.
 int run_fused640(const FusedArgs& a, const ReconGeom& g) {
-  std::shared_ptr<FusedPlanDev> pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
+  PlanPtr pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
   const bool wide640 = a.Wp == CP_N;
   if (!pl || (wide640 ? !pl->r640_off : !pl->act_logical)) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
   const int n_act = (int)pl->host.act_w.size();
@@ -548,6 +535,28 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
   return 0;
 }
 
+#ifdef MRIACL_EXPERIMENTAL
+// ---- side stream + events of the overlapped schedule, one set per (device, caller stream) ----
+struct OverlapRes { rt_stream_t side = nullptr; rt_event_t ev_start[2], ev_row[2]; int* error_flag = nullptr; bool ok = false; };
+std::map<std::pair<int, void*>, OverlapRes> g_ovl;
+
+OverlapRes* get_overlap_res(int dev, rt_stream_t st) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  OverlapRes& r = g_ovl[{dev, (void*)st}];
+  if (!r.ok) {
+    int bad = rt_stream_create_high_priority(&r.side);
+    for (int i = 0; i < 2; ++i) { bad |= rt_event_create(&r.ev_start[i]); bad |= rt_event_create(&r.ev_row[i]); }
+    void* ef = nullptr;
+    const int zero = 0;
+    bad |= rt_malloc(&ef, sizeof(int));
+    if (!bad) bad |= rt_upload(ef, &zero, sizeof(int));
+    if (bad) return nullptr;
+    r.error_flag = (int*)ef;
+    r.ok = true;
+  }
+  return &r;
+}
+
 // The fused 640x368 plan.  Two schedules:
 //  sequential  column pass (persistent, double-buffered gather) -> row pass (16 warps, one CTA per SM)
 //              -> normalise, back to back on the caller's stream, `chunk` slices per group;
@@ -556,8 +565,8 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
 //              concurrently running column pass (caller's stream) publishes them through per-slice counters,
 //              so the HBM-bound gather and the issue-bound row transform share the SMs and the intermediate
 //              is read back while still in L2.  The side stream is joined to the caller's stream at the end.
-int run_fused(const FusedArgs& a, const ReconGeom& g) {
-  std::shared_ptr<FusedPlanDev> pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
+int run_fused_experimental(const FusedArgs& a, const ReconGeom& g) {
+  PlanPtr pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
   if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
   const int n_act = (int)pl->host.act_w.size();
   const int n_groups = (n_act + CP_G - 1) / CP_G;
@@ -712,8 +721,8 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
       q.n_slices = ns; q.n_tiles = g.n_tiles16;
       q.done = counters; q.done_target = a.A * a.C * n_groups; q.error_flag = ov->error_flag;
-      q.n_buf = 2;
-      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 2, a.ow, a.A);
+      q.n_buf = std::max(1, std::min(2, env_int("MRIACL_KC_NBUF", 2)));   // 1: the CTA stays under 164 KB, which leaves the gather 92 KB of L1
+      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, q.n_buf, a.ow, a.A);
       if (CP_SMEM_BYTES_DB + smem16 > SMEM_MAX) { q.n_buf = 1; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 1, a.ow, a.A); }
       if (CP_SMEM_BYTES_DB + smem16 > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "co-resident tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
       const bool kc_fuse_norm = env_int("MRIACL_KC_FUSE_NORM", 0) != 0;    // the finishing team normalises (measured slower)
@@ -914,6 +923,80 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
   return 0;
 }
 
+#endif  // MRIACL_EXPERIMENTAL
+
+// The fused 640 x 368 knee plan (product schedule): column pass (persistent, warp-specialised gather) -> 16-row row
+// pass -> normalise, back to back on the caller's stream, `chunk` slices per group.  The MRIACL_ONLY_* flags run
+// single phases of the same plan (bench.py's per-kernel timings).
+int run_fused(const FusedArgs& a, const ReconGeom& g) {
+  constexpr unsigned experimental = MRIACL_SCHED_FUSED | MRIACL_SCHED_OVERLAP | MRIACL_SCHED_PAIR | MRIACL_SCHED_CORESIDENT |
+                                    MRIACL_SCHED_PIPELINED;
+#ifdef MRIACL_EXPERIMENTAL
+  if ((a.flags & experimental) || getenv("MRIACL_SCHEDULE") || getenv("MRIACL_RP16_CFG") || getenv("MRIACL_CP_DEBUG_SKIP") ||
+      getenv("MRIACL_RP_DEBUG_SKIP") || getenv("MRIACL_CP_PER_SM") || getenv("MRIACL_FUSE_NORM"))
+    return run_fused_experimental(a, g);
+#else
+  if ((a.flags & experimental) && !(a.flags & MRIACL_SEQUENTIAL))
+    return fail(MRIACL_ERR_UNSUPPORTED, "schedule not built: this library was compiled without MRIACL_EXPERIMENTAL");
+#endif
+  PlanPtr pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
+  if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
+  const int n_act = (int)pl->host.act_w.size();
+  const int n_groups = (n_act + CP_G - 1) / CP_G;
+  const int ohp = g.n_tiles * RP_ROWS;
+  const int row0 = crop_start(a.H, a.oh), col0 = crop_start(a.Wp, a.ow);
+  const bool want_norm = (a.flags & MRIACL_NORM_INSTANCE) != 0;
+  const int flip = (a.flags & MRIACL_FLIP_ROWS) ? 1 : 0;
+  const unsigned only = a.flags & (MRIACL_ONLY_COLPASS | MRIACL_ONLY_ROWPASS | MRIACL_ONLY_NORM);
+  const bool do_col = !only || (only & MRIACL_ONLY_COLPASS);
+  const bool do_row = !only || (only & MRIACL_ONLY_ROWPASS);
+  const bool do_norm = !only || (only & MRIACL_ONLY_NORM);
+  const int chunk = (int)std::min<size_t>((size_t)a.B, a.workspace_bytes / g.per_slice);
+  const int sptw_len = (int)pl->sptw16.size(), sched_len = (int)pl->pairs12.size();
+  int n_buf = 3;
+  int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, sptw_len, sched_len, pl->rp16_slots, n_buf, a.ow, a.A);
+  while (smem16 > SMEM_MAX / 2 && n_buf > 1) { --n_buf; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, sptw_len, sched_len, pl->rp16_slots, n_buf, a.ow, a.A); }
+  if (smem16 > SMEM_MAX / 2)
+    return fail(MRIACL_ERR_UNSUPPORTED, "row-pass tile does not fit shared memory (n_act=%d ow=%d A=%d)", n_act, a.ow, a.A);
+  for (int s0 = 0; s0 < a.B; s0 += chunk) {
+    const int ns = std::min(chunk, a.B - s0);
+    char* base = (char*)a.workspace;
+    cf* T = (cf*)base;
+    float* partials = (float*)(base + g.t_bytes * (size_t)chunk);
+    float* out_s0 = a.out + (size_t)s0 * a.oh * a.ow;
+    if (n_groups > 0 && do_col) {
+      ColPassParams cp{};
+      cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = a.W;
+      cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
+      cp.tw = pl->twH; cp.T = T; cp.oh = a.oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
+      cp.frame0 = s0 * a.A * a.C; cp.n_frames = ns * a.A * a.C; cp.done = nullptr;
+      const long long col_items = (long long)cp.n_frames * n_groups;
+      MRIACL_LAUNCH(colpass640_ws_kernel, (int)std::min<long long>(col_items, 2LL * a.sms), CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+    }
+    if (do_row) {
+      RowPass16Params q{};
+      q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+      q.sched = pl->sched_p12; q.sched_len = sched_len;
+      q.sptw = pl->sptw16_dev; q.sptw_len = sptw_len; q.n_slots = pl->rp16_slots; q.slot_of_j = pl->rp16_slot_dev;
+      q.out = out_s0; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C;
+      q.scale = (float)(1.0 / std::sqrt((double)a.H * (double)a.Wp));
+      q.n_slices = ns; q.n_tiles = g.n_tiles16; q.n_buf = n_buf;
+      q.reverse = (n_groups > 0 && do_col) ? 1 : 0;     // the most recently written slices of T are still in L2
+      auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>;
+      MRIACL_LAUNCH(kfn, std::min(ns * g.n_tiles16, 2 * a.sms), 12 * 32, smem16, a.st, q);
+    }
+    if ((want_norm || a.mean_std) && do_norm) {
+      NormParams np{};
+      np.in = out_s0; np.out = out_s0; np.mean_std = a.mean_std ? a.mean_std + 2 * (size_t)s0 : nullptr;
+      np.partials = partials; np.n_part = g.n_tiles16; np.n = (long long)a.oh * a.ow; np.eps = a.eps;
+      np.normalize = want_norm ? 1 : 0;
+      np.n_split = want_norm ? std::max(1, std::min(16, (int)(np.n / 8192))) : 1;
+      MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
+    }
+  }
+  return 0;
+}
+
 int grid_for(long long work_items, int per_block) {
   long long g = (work_items + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -982,7 +1065,8 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
     if (rc) return rc;
   } else {
     const float* mask_dev = nullptr;
-    if (get_device_mask(dev, mask_w_host, W, &mask_dev)) return fail(MRIACL_ERR_CUDA, "mask upload failed: %s", rt_last_error_string());
+    DevPtr mask_keep;
+    if (get_device_mask(dev, mask_w_host, W, &mask_dev, mask_keep)) return fail(MRIACL_ERR_CUDA, "mask upload failed: %s", rt_last_error_string());
     for (int s0 = 0; s0 < B; s0 += chunk) {
       const int ns = std::min(chunk, B - s0);
       cf* img = (cf*)workspace;

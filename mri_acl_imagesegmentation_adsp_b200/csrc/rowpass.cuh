@@ -115,6 +115,7 @@ template <int NW> __device__ __forceinline__ float rp_block_sum(float v, float* 
   return t;
 }
 
+#ifdef MRIACL_EXPERIMENTAL   // the 32-row kernel: superseded by the 16-row kernel (rowpass16.cuh), kept as a measured alternative
 // sparse residue with exactly NNZ sampled columns: Y'[k1] = sum_e x_e w_N^{n_e k1}; the twiddle
 // rows were tabulated by the host plan, so every operand is a shared-memory load at an immediate offset
 template <int P, int Q, int NNZ>
@@ -337,5 +338,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) rowpass_kernel(RowPa
     __syncthreads();   // tile fully consumed before the next item's prefetch / stage 1 reuse the buffers
   }
 }
+
+#endif  // MRIACL_EXPERIMENTAL
 
 }  // namespace mriacl

@@ -159,7 +159,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
       const cf* src = src0 + (long long)f * frame_elems;
       cf* dst = dst0 + (size_t)buf * tile_elems;
       int j = tid >> 3;
-      if (!(p.debug_skip & 4)) {
+      if (!MRIACL_DBG_SKIP(p, 4)) {
         // (no L2 hint on these copies: ptxas 12.9 encodes a hinted LDGSTS with a uniform-register address offset
         //  that sm_100a rejects as an illegal instruction, and the hints did not pay off anyway)
 #pragma unroll 1
@@ -209,7 +209,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
       // ---------------- stage 1: two units per warp ----------------
       {
         const cf* tb = tbuf + (size_t)buf * tile_elems + r;
-        const int n_pairs = (p.debug_skip & 1) ? 0 : schsm[my_off];
+        const int n_pairs = MRIACL_DBG_SKIP(p, 1) ? 0 : schsm[my_off];
         int off = my_off + 1;
         for (int u = 0; u < n_pairs; ++u, off += 4) {
           const int type = schsm[off], nnz = schsm[off + 1];
@@ -250,7 +250,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
       for (int kk = 0; kk < KPW; ++kk) {
         const int pair = warp + NW * kk;
         const int k1 = 2 * pair + half;
-        if (pair < NPAIR && !(p.debug_skip & 2)) {
+        if (pair < NPAIR && !MRIACL_DBG_SKIP(p, 2)) {
           const int k1c = k1 < P ? k1 : P - 1;           // odd P: the last pair has one idle half
           cf v[Q];
           const cf* yrow = Y + k1c * YS + r;
@@ -281,7 +281,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
       }
     }
     rp16_sync<BAR, NT>();
-    if (p.debug_skip & 8) return;
+    if (MRIACL_DBG_SKIP(p, 8)) return;
     if (p.A == 1) {
 #pragma unroll
       for (int kk = 0; kk < KPW; ++kk) {

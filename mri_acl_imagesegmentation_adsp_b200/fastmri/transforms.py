@@ -1,5 +1,5 @@
-"""Twins of ``ZIP!/DL_reconstruction/data/transforms.py``: to_tensor, center_crop, normalize,
-normalize_instance."""
+"""Twins of ``ZIP!/DL_reconstruction/data/transforms.py``: to_tensor, center_crop, complex_center_crop,
+center_crop_to_smallest, normalize, normalize_instance."""
 from __future__ import annotations
 
 from typing import Tuple, Union
@@ -25,6 +25,23 @@ def center_crop(data: torch.Tensor, shape: Tuple[int, int]) -> torch.Tensor:
     w_from = (data.shape[-2] - shape[0]) // 2
     h_from = (data.shape[-1] - shape[1]) // 2
     return data[..., w_from:w_from + shape[0], h_from:h_from + shape[1]]
+
+
+def complex_center_crop(data: torch.Tensor, shape: Tuple[int, int]) -> torch.Tensor:
+    """Centre crop of dims -3 and -2 of a real-view complex tensor ``(..., H, W, 2)`` (``transforms.py:70-92``);
+    a view, ValueError("Invalid shapes.") when the crop exceeds the data."""
+    if not (0 < shape[0] <= data.shape[-3] and 0 < shape[1] <= data.shape[-2]):
+        raise ValueError("Invalid shapes.")
+    w_from = (data.shape[-3] - shape[0]) // 2
+    h_from = (data.shape[-2] - shape[1]) // 2
+    return data[..., w_from:w_from + shape[0], h_from:h_from + shape[1], :]
+
+
+def center_crop_to_smallest(x: torch.Tensor, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Crop both images to the smaller extent of each of the last two dims (``transforms.py:95-117``)."""
+    smallest_width = min(x.shape[-1], y.shape[-1])
+    smallest_height = min(x.shape[-2], y.shape[-2])
+    return center_crop(x, (smallest_height, smallest_width)), center_crop(y, (smallest_height, smallest_width))
 
 
 def normalize(data, mean, stddev, eps=0.0):

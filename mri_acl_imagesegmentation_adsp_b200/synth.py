@@ -73,3 +73,22 @@ def knee_mask() -> np.ndarray:
 def prostate_mask() -> np.ndarray:
     """configs[2]: PE=451, 8x equispaced + round(451*0.04)=18 ACS columns."""
     return equispaced_mask(451, 8, 0.04)
+
+
+def prostate_volume_block(a: int, s: int, seed: int = 0) -> np.ndarray:
+    """``(C, RO, PE)`` block (average ``a``, slice ``s``) of the configs[2] volume ``PROSTATE_SHAPE``.
+
+    The full-size parity tests and the golden script build the 3.3 GB volume block by block from these
+    seeds, so neither needs the whole volume in host memory at once."""
+    _, n_sl, c, ro, pe = PROSTATE_SHAPE
+    return gaussian_kspace((c, ro, pe), 100000 + 1000 * seed + a * n_sl + s)
+
+
+#: (width, acceleration, center_fraction, offset) of every sampling mask the tests and the bench use; their index
+#: lists are frozen in tests/golden/manifest.json ("masks") -- the generator is builder-defined (SURVEY.md 8c)
+FROZEN_MASKS = ((368, 4, 0.08, 0), (368, 8, 0.04, 0), (368, 4, 0.08, 1), (368, 4, 0.08, 3), (640, 8, 0.04, 0),
+                (451, 8, 0.04, 0), (372, 4, 0.08, 0))
+
+
+def mask_name(width: int, acceleration: int, center_fraction: float, offset: int = 0) -> str:
+    return f"equispaced({width},{acceleration},{center_fraction:g},{offset})"

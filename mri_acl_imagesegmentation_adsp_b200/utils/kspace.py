@@ -3,6 +3,10 @@ shapes), computed by ``libmriacl_recon.so`` on the current CUDA device.
 
 numpy in -> numpy out exactly like the reference; torch tensors (CPU or CUDA) are accepted too
 and come back as torch tensors on their original device.  Leading dimensions are batch.
+
+dtype follows the input exactly as in the reference: complex64 -> complex64 / float32, complex128 ->
+complex128 / float64.  The device arithmetic is single precision either way (the path's parity bar is
+rel-L2 <= 1e-5), so a complex128 result carries float32 accuracy.
 """
 from __future__ import annotations
 
@@ -24,7 +28,7 @@ def _fft2c(x: Any, inverse: bool) -> Any:
     out = torch.empty_like(t)
     if t.numel():
         D.lib().fft2c(t.data_ptr(), out.data_ptr(), b, h, w, inverse, D.stream_ptr())
-    return mv.back(out)
+    return mv.back(out, widen=True)      # complex128 in -> complex128 out, as numpy.fft (kspace.py:7,14)
 
 
 def fft2c(x: Any) -> Any:
@@ -44,7 +48,7 @@ def complex_abs(x: Any) -> Any:
     out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
     if t.numel():
         D.lib().complex_abs(t.data_ptr(), out.data_ptr(), t.numel(), False, D.stream_ptr())
-    return mv.back(out)
+    return mv.back(out, widen=True)
 
 
 def center_crop_or_pad(img: Any, out_h: int, out_w: int) -> Any:

@@ -144,6 +144,34 @@ def main() -> None:
     man["cases"]["prostate_one_slice"] = {"generator": "gaussian_kspace", "shape": list(shape), "seed": 0,
                                           "mask": "equispaced(451,8,0.04)", "pad": [94, 95], "sha256": _sha(fin)}
 
+    # ---- 5b. configs[2] at full size: two slices of the (3,30,16,640,451) volume, built block by block ----
+    for s_idx in (0, 29):
+        kk = np.stack([synth.prostate_volume_block(a, s_idx) for a in range(3)])[:, None] * pm.reshape(1, 1, 1, 1, -1)
+        ims = np.zeros((3, 1, 640, 640))
+        for av in range(3):
+            ims[av] = pr.t2.create_coil_combined_im(pr.mri_data.zero_pad_kspace_hdr(hdr, kk[av]))
+        fin = pr.utils.center_crop_im(np.mean(ims, axis=0), [320, 320])
+        vec[f"prostate/volume_slice{s_idx}_sub2"] = fin[0, ::2, ::2].astype(np.float32)
+        man["cases"][f"prostate_volume_slice{s_idx}"] = {"generator": "prostate_volume_block", "slice": s_idx, "seed": 0,
+                                                        "mask": "equispaced(451,8,0.04)", "pad": [94, 95],
+                                                        "sha256": _sha(fin), "stored": "[0, ::2, ::2] as float32"}
+
+    # ---- 5c. configs[0] slice under the 8x knee mask and under 4x masks with a non-zero offset ----
+    k = synth.gaussian_kspace(synth.KNEE_SHAPE, 0)
+    for tag, mm in (("8x", synth.equispaced_mask(368, 8, 0.04)), ("4x_off1", synth.equispaced_mask(368, 4, 0.08, 1)),
+                    ("4x_off3", synth.equispaced_mask(368, 4, 0.08, 3))):
+        a = ref_numpy_chain(k, mm, synth.CROP)
+        o, mu, sd = ref_fastmri_chain(k, mm, synth.CROP)
+        vec[f"knee_gauss/numpy_chain_{tag}_sub2"] = a[::2, ::2].astype(np.float32)
+        vec[f"knee_gauss/fastmri_mean_std_{tag}"] = np.array([mu, sd], dtype=np.float32)
+        man["cases"][f"knee_gauss_{tag}"] = {"generator": "gaussian_kspace", "shape": list(synth.KNEE_SHAPE), "seed": 0,
+                                             "columns_kept": int(np.count_nonzero(mm)), "numpy_chain_sha256": _sha(a),
+                                             "stored": "[::2, ::2]"}
+
+    # ---- 5d. frozen sampling-mask index lists (the generator is builder-defined: SURVEY.md section 8c) ----
+    man["masks"] = {synth.mask_name(*spec): [int(i) for i in np.flatnonzero(synth.equispaced_mask(*spec))]
+                    for spec in synth.FROZEN_MASKS}
+
     # ---- 6. normalize_instance on its own -------------------------------------------
     x = np.abs(synth.gaussian_kspace((320, 320), seed=3)).astype(np.float32) + 2.0
     o, mu, sd = dl.transforms.normalize_instance(torch.from_numpy(x), eps=1e-11)

@@ -254,6 +254,30 @@ def ifftnd(kspace: np.ndarray, axes: Optional[Sequence[int]] = (-1,)) -> np.ndar
     return img
 
 
+def flip_im(vol: np.ndarray, slice_axis: int) -> np.ndarray:
+    """ZIP!/fastmri_prostate/reconstruction/utils.py:32-51, including its quirk: the loop runs
+    ``vol.shape[slice_axis]`` times but always indexes the FIRST axis; in place, returns ``vol``."""
+    for i in range(vol.shape[slice_axis]):
+        vol[i] = np.flipud(vol[i])
+    return vol
+
+
+def complex_center_crop_ri(data: np.ndarray, shape: Tuple[int, int]) -> np.ndarray:
+    """Centre crop of dims -3, -2 of a real-view array (..., H, W, 2) (transforms.py:70-92)."""
+    if not (0 < shape[0] <= data.shape[-3] and 0 < shape[1] <= data.shape[-2]):
+        raise ValueError("Invalid shapes.")
+    r0 = crop_start(data.shape[-3], shape[0])
+    c0 = crop_start(data.shape[-2], shape[1])
+    return data[..., r0:r0 + shape[0], c0:c0 + shape[1], :]
+
+
+def center_crop_to_smallest(x: np.ndarray, y: np.ndarray):
+    """Crop both to the smaller extent of each of the last two dims (transforms.py:95-117)."""
+    w = min(x.shape[-1], y.shape[-1])
+    h = min(x.shape[-2], y.shape[-2])
+    return center_crop(x, (h, w)), center_crop(y, (h, w))
+
+
 def create_coil_combined_im(k: np.ndarray) -> np.ndarray:
     """(S, C, RO, PE) complex -> (S, RO, PE) float64: per slice ifftnd over
     (RO, PE), RSS over coils, ``np.flipud`` (prostate_t2_recon.py:80-102)."""

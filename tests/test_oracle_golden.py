@@ -145,6 +145,37 @@ def test_mask_rule_frozen():
     assert int(O.equispaced_mask(451, 8, 0.04).sum()) == len(np.flatnonzero(synth.prostate_mask()))
 
 
+def test_frozen_mask_index_lists(manifest):
+    """the mask generator is builder-defined, so its index lists are frozen (manifest "masks")."""
+    assert set(manifest["masks"]) == {synth.mask_name(*spec) for spec in synth.FROZEN_MASKS}
+    for spec in synth.FROZEN_MASKS:
+        want = manifest["masks"][synth.mask_name(*spec)]
+        for gen in (synth.equispaced_mask, O.equispaced_mask):
+            m = gen(*spec)
+            assert m.dtype == np.float32 and set(np.unique(m).tolist()) <= {0.0, 1.0}
+            assert np.flatnonzero(m).tolist() == want, spec
+    assert len(manifest["masks"]["equispaced(368,4,0.08,0)"]) == 114
+    assert len(manifest["masks"]["equispaced(368,8,0.04,0)"]) == 60
+
+
+@pytest.mark.parametrize("tag,spec", [("8x", (368, 8, 0.04, 0)), ("4x_off1", (368, 4, 0.08, 1)), ("4x_off3", (368, 4, 0.08, 3))])
+def test_knee_other_masks(golden, tag, spec):
+    k = synth.gaussian_kspace(synth.KNEE_SHAPE, 0)
+    m = synth.equispaced_mask(*spec)
+    img, _, _ = O.knee_chain_numpy(k, m, synth.CROP, normalize_mode=None)
+    assert O.rel_l2(img[::2, ::2], golden[f"knee_gauss/numpy_chain_{tag}_sub2"]) <= TOL
+    _, mean, std = O.knee_chain_fastmri(k, m, synth.CROP)
+    np.testing.assert_allclose([mean, std], golden[f"knee_gauss/fastmri_mean_std_{tag}"], rtol=2e-6)
+
+
+@pytest.mark.parametrize("s_idx", [0, 29])
+def test_prostate_volume_slices(golden, s_idx):
+    """two slices of the full configs[2] volume, built block by block (synth.prostate_volume_block)"""
+    k = np.stack([synth.prostate_volume_block(a, s_idx) for a in range(3)])[:, None]
+    fin = O.prostate_chain(k, synth.prostate_mask(), synth.PROSTATE_PAD)
+    assert O.rel_l2(fin[0, ::2, ::2], golden[f"prostate/volume_slice{s_idx}_sub2"]) <= TOL
+
+
 def test_analytic_cases():
     # delta at the k-space centre <-> constant image 1/sqrt(HW); Parseval for the ortho pair
     h, w = 640, 368

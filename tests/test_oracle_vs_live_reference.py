@@ -73,3 +73,32 @@ def test_prostate_twins():
         lr = O.padding_lr(enc_x, max_pe)
         assert lr[0] + lr[1] == enc_x - (max_pe + 1)
         assert lr == ((int(np.floor(p)), int(np.ceil(p))) if p % 2 != 0 else (int(p), int(p)))
+
+
+def test_reference_signature_twins():
+    """ifftnd (default axes=[-1], single axes, None), flip_im (with its first-axis quirk), center_crop_im, numpy rss,
+    complex_center_crop, center_crop_to_smallest: the oracle restatements against the live functions."""
+    pr = ref_shim.prostate()
+    dl = ref_shim.fastmri_dl()
+    x = synth.gaussian_kspace((3, 10, 7), 24)
+    np.testing.assert_array_equal(O.ifftnd(x.copy()), pr.utils.ifftnd(x.copy()))
+    for axes in ([0], [1], [0, 2], [1, 2], None):
+        np.testing.assert_array_equal(O.ifftnd(x.copy(), axes), pr.utils.ifftnd(x.copy(), axes))
+    x128 = x.astype(np.complex128)
+    assert pr.utils.ifftnd(x128.copy(), [1, 2]).dtype == np.complex128 == O.ifftnd(x128.copy(), [1, 2]).dtype
+    vol = np.abs(x).astype(np.float64)
+    for ax in (0, 1):
+        np.testing.assert_array_equal(O.flip_im(vol[:, :3].copy(), ax), pr.utils.flip_im(vol[:, :3].copy(), ax))
+    np.testing.assert_array_equal(O.center_crop_im(vol, [4, 6]), pr.utils.center_crop_im(vol, [4, 6]))
+    for ax in (-1, 0, 1):
+        np.testing.assert_array_equal(O.rss_np(x, ax), pr.t2.rss(x, ax))
+    assert pr.t2.rss(x, 0).dtype == np.float32 and pr.t2.rss(x128, 0).dtype == np.float64
+    t = dl.transforms.to_tensor(x)
+    np.testing.assert_array_equal(O.complex_center_crop_ri(t.numpy(), (6, 3)), dl.transforms.complex_center_crop(t, (6, 3)).numpy())
+    with pytest.raises(ValueError):
+        dl.transforms.complex_center_crop(t, (11, 3))
+    a, b = torch.from_numpy(vol[:, :8, :]), torch.from_numpy(vol[:, :, :5])
+    ra, rb = dl.transforms.center_crop_to_smallest(a, b)
+    oa, ob = O.center_crop_to_smallest(a.numpy(), b.numpy())
+    np.testing.assert_array_equal(ra.numpy(), oa)
+    np.testing.assert_array_equal(rb.numpy(), ob)
