@@ -45,8 +45,9 @@ extern "C" {
 #define MRIACL_FLIP_ROWS      0x1u  /* np.flipud of each combined image (ZIP!/fastmri_prostate/reconstruction/t2/prostate_t2_recon.py:101) */
 #define MRIACL_NORM_INSTANCE  0x2u  /* (x-mean)/(std+eps), unbiased std (ZIP!/DL_reconstruction/data/transforms.py:143-162) */
 #define MRIACL_FORCE_GENERIC  0x4u  /* testing: use the generic (any-size) kernels even where a fused plan exists */
-/* kernel schedule of the fused 640x368 plan (default: MRIACL_SEQUENTIAL unless the environment variable
- * MRIACL_SCHEDULE=fused|overlapped says otherwise; all three produce identical images) */
+/* kernel schedule of the fused 640x368 plan.  The product library holds ONE schedule, MRIACL_SEQUENTIAL (the default);
+ * the MRIACL_SCHED_* schedules below were measured slower, exist only in builds with
+ * -DMRIACL_EXPERIMENTAL (libmriacl_recon_exp.so) and return MRIACL_ERR_UNSUPPORTED from the product library. */
 #define MRIACL_SEQUENTIAL     0x8u   /* column pass -> row pass -> normalise, back to back on the caller's stream */
 #define MRIACL_SCHED_FUSED    0x10u  /* experimental: one persistent kernel, CTAs switch between column and row items */
 #define MRIACL_SCHED_CORESIDENT 0x80u /* one persistent kernel, one CTA per SM: column team + row team co-resident, normalisation fused */
@@ -58,6 +59,10 @@ extern "C" {
 #define MRIACL_ONLY_COLPASS   0x100u
 #define MRIACL_ONLY_ROWPASS   0x200u
 #define MRIACL_ONLY_NORM      0x400u
+/* kspace holds only the SAMPLED columns (mask value != 0), densely: element (b,a,c,h,j) of sampled column j lives at
+ * b*slice_stride + a*avg_stride + (c*H + h)*n_act + j, as written by mriacl_pack_columns_host.  W, pad_left and mask
+ * still describe the full line.  Plans with the 640-row column pass only (MRIACL_ERR_UNSUPPORTED otherwise). */
+#define MRIACL_PACKED_COLUMNS 0x1000u
 
 /* path selector reported by mriacl_supported */
 #define MRIACL_PATH_NONE    0
@@ -110,6 +115,15 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
                          int B, int A, int C, int H, int W, int pad_left, int W_padded,
                          int out_h, int out_w, unsigned flags, float eps,
                          void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* HOST helper of the end-to-end path: copy the sampled columns (mask value != 0; NULL mask = all) of n_rows rows of
+ * W complex64 values from kspace_c64_host to packed_c64_host [n_rows][n_act], on n_threads host threads (<= 0: one per
+ * core this process may run on).  Unsampled columns are multiplied by zero by the mask apply (fastMRI convention,
+ * SURVEY.md section 0 fact 4), so they need not cross PCIe: the caller copies the packed buffer to the device and
+ * passes MRIACL_PACKED_COLUMNS.  Both pointers are HOST pointers (pageable or pinned); no CUDA call is made.
+ * Returns n_act (>= 0) or a negative MRIACL_ERR_* code. */
+int mriacl_pack_columns_host(const void* kspace_c64_host, void* packed_c64_host, long long n_rows, int W,
+                             const float* mask_w_host, int n_threads);
 
 /* |ifft2c(k)| as float32 for B single-coil (H, W) slices.
  * Replaces MRIKneePreprocessor.ifft2c_single, REF/src/preprocess/mri_preprocess.py:149-160.

@@ -22,6 +22,7 @@ SCHED_CORESIDENT = 0x80                    # one persistent kernel: column team 
 SCHED_PIPELINED = 0x800                    # small chunks on two streams, T kept in L2
 SCHED_PAIR = 0x40                          # column pass -> pair row pass (rowpair.cuh) -> normalise
 ONLY_COLPASS, ONLY_ROWPASS, ONLY_NORM = 0x100, 0x200, 0x400   # profiling: single phases of the fused plan
+PACKED_COLUMNS = 0x1000                    # k-space holds the sampled columns only (mriacl_pack_columns_host)
 PATH_NONE, PATH_GENERIC, PATH_FUSED = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -41,6 +42,7 @@ SIGNATURES = {
     "mriacl_recon_rss_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _u]),
     "mriacl_recon_rss_f32": (_i, [_vp, _ll, _ll, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _u, _f,
                                    _vp, _sz, _vp]),
+    "mriacl_pack_columns_host": (_i, [_vp, _vp, _ll, _i, _fp, _i]),
     "mriacl_ifft2c_abs_workspace_bytes": (_sz, [_i, _i, _i]),
     "mriacl_ifft2c_abs_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "mriacl_fft2c_c64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -121,6 +123,15 @@ class ReconLibrary:
         self._check(self._lib.mriacl_recon_rss_f32(kspace_ptr, slice_stride, avg_stride, mp, out_ptr, mean_std_ptr or None,
                                                     b, a, c, h, w, pad_left, w_padded, out_h, out_w, flags, eps,
                                                     workspace_ptr, workspace_bytes, stream or None))
+
+    def pack_columns_host(self, src_host_ptr, dst_host_ptr, n_rows, w, mask, n_threads=0) -> int:
+        """Host gather of the sampled columns (both pointers are HOST addresses); returns n_act.  ctypes drops the
+        GIL for the duration of the call."""
+        keep, mp = self._mask_ptr(mask)
+        n = int(self._lib.mriacl_pack_columns_host(src_host_ptr, dst_host_ptr, n_rows, w, mp, n_threads))
+        if n < 0:
+            self._check(n)
+        return n
 
     def ifft2c_abs(self, k_ptr, out_ptr, b, h, w, workspace_ptr, workspace_bytes, stream=0) -> None:
         self._check(self._lib.mriacl_ifft2c_abs_f32(k_ptr, out_ptr, b, h, w, workspace_ptr, workspace_bytes, stream or None))

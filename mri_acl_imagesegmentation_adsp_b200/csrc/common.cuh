@@ -164,7 +164,7 @@ __device__ __forceinline__ void full_wait(FullBarrier* b, int parity, int emu_id
 }
 
 // one thread spins until *counter >= target (another team of this persistent kernel publishes it); bounded so that
-// a scheduling surprise cannot hang the device
+// a scheduling surprise cannot hang the device: on a timeout the kernel traps (sticky CUDA error, reported by the call)
 __device__ __forceinline__ bool wait_count_ge(const int* counter, int target) {
 #if defined(MRIACL_EMU)
   const auto t0 = std::chrono::steady_clock::now();      // emulator: wall-clock bound (CUDA threads are OS threads here)
@@ -179,6 +179,7 @@ __device__ __forceinline__ bool wait_count_ge(const int* counter, int target) {
     if (*c >= target) { __threadfence(); return true; }
     __nanosleep(100);
   }
+  __trap();          // never proceed past an unmet dependency (the caller would overwrite data still in use)
   return false;
 #endif
 }

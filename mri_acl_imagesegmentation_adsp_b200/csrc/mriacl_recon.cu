@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "rt.h"
 #include "plan.h"
+#include "hostpack.h"
 #include "generic_kernels.cuh"
 #include "colpass640.cuh"
 #include "rowpass.cuh"
@@ -217,6 +218,7 @@ struct FusedPlanDev {
   // call using it has returned
   std::vector<DevPtr> owned;
   int* act_w = nullptr; float* act_m = nullptr;
+  int* act_ident = nullptr;        // 0 .. n_act-1: the column list of packed k-space (MRIACL_PACKED_COLUMNS)
   int* sched_p8 = nullptr; int* sched_p12 = nullptr; cf* sptw16_dev = nullptr; int* rp16_slot_dev = nullptr;
   int* act_logical = nullptr;      // pruned generic row pass: logical index of active column j in the padded line
   int* r640_off = nullptr; int* r640_ent = nullptr; int* r640_perm = nullptr;
@@ -266,6 +268,11 @@ PlanPtr get_fused_plan(int dev, int H, int W, int pad_left, int Wp, int oh, int 
   if (device_side) {
     const FusedPlanHost& h = pl->host;
     if (!pl->put(h.act_w, pl->act_w) || !pl->put(h.act_m, pl->act_m)) return nullptr;
+    {
+      std::vector<int> ident(h.act_w.size());
+      for (size_t j = 0; j < ident.size(); ++j) ident[j] = (int)j;
+      if (!pl->put(ident, pl->act_ident)) return nullptr;
+    }
     build_pair_schedule(pl->host, 12, pl->pairs12, pl->sptw16, &pl->rp16_slot_of_j, &pl->rp16_slots);
     build_pair_schedule(pl->host, Wp == W400_P * W400_Q ? W400_NW : 8, pl->pairs8, pl->sptw16);   // (8 warps; 7 for the 400-wide plans)
     if (!pl->put(pl->rp16_slot_of_j, pl->rp16_slot_dev) || !pl->put(pl->sptw16, pl->sptw16_dev) ||
@@ -316,6 +323,12 @@ bool fused_shape(int H, int Wp) {
 }
 // H = 640 with any other width: the fused column pass feeds the pruned generic row pass (rowpass_generic.cuh)
 bool pruned_shape(int H, int Wp) { return H == CP_N && !fused_shape(H, Wp) && Wp <= MRIACL_MAX_LINE; }
+// ... provided one line of it fits shared memory: two line buffers + the per-stage index tables + the output tiles
+// (Wp = 3072 or 4096 do not: those shapes take the generic kernels, which hold lines up to MRIACL_MAX_LINE)
+bool pruned_fits(int Wp, int ow) {
+  const int stages = (int)generic_radices(Wp).size();
+  return stages <= RG_MAX_STAGES && rowgen_smem_bytes(Wp, 1, ow, stages) <= SMEM_MAX;
+}
 
 struct ReconGeom {
   bool fused;
@@ -327,7 +340,7 @@ struct ReconGeom {
 
 int recon_geom(int A, int C, int H, int W, int pad_left, int Wp, int oh, int ow, const float* mask,
                unsigned flags, ReconGeom& g) {
-  g.fused = (fused_shape(H, Wp) || pruned_shape(H, Wp)) && !(flags & MRIACL_FORCE_GENERIC);
+  g.fused = (fused_shape(H, Wp) || (pruned_shape(H, Wp) && pruned_fits(Wp, ow))) && !(flags & MRIACL_FORCE_GENERIC);
   g.n_tiles = (oh + RP_ROWS - 1) / RP_ROWS;
   g.n_tiles16 = (oh + RP16_ROWS - 1) / RP16_ROWS;
   g.n_tiles8 = (oh + R640_ROWS - 1) / R640_ROWS;
@@ -429,8 +442,8 @@ int run_fused_pq(const FusedArgs& a, const ReconGeom& g) {
     cf* T = (cf*)base;
     float* partials = (float*)(base + g.t_bytes * (size_t)chunk);
     ColPassParams cp{};
-    cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = a.W;
-    cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
+    cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = (a.flags & MRIACL_PACKED_COLUMNS) ? n_act : a.W;
+    cp.act_w = (a.flags & MRIACL_PACKED_COLUMNS) ? pl->act_ident : pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
     cp.tw = pl->twH; cp.T = T; cp.oh = a.oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
     cp.frame0 = s0 * a.A * a.C; cp.n_frames = ns * a.A * a.C; cp.done = nullptr;
     const long long col_items = (long long)cp.n_frames * n_groups;
@@ -490,8 +503,8 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
     float* partials = (float*)(base + g.t_bytes * (size_t)chunk);
     (void)part_bytes;
     ColPassParams cp{};
-    cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = a.W;
-    cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
+    cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = (a.flags & MRIACL_PACKED_COLUMNS) ? n_act : a.W;
+    cp.act_w = (a.flags & MRIACL_PACKED_COLUMNS) ? pl->act_ident : pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
     cp.tw = pl->twH; cp.T = T; cp.oh = a.oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
     cp.frame0 = s0 * a.A * a.C; cp.n_frames = ns * a.A * a.C; cp.done = nullptr;
     const long long col_items = (long long)cp.n_frames * n_groups;
@@ -650,8 +663,8 @@ int run_fused_experimental(const FusedArgs& a, const ReconGeom& g) {
     int* counters = (int*)(base + (g.t_bytes + part_bytes) * (size_t)chunk);
 
     ColPassParams cp{};
-    cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = a.W;
-    cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
+    cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = (a.flags & MRIACL_PACKED_COLUMNS) ? n_act : a.W;
+    cp.act_w = (a.flags & MRIACL_PACKED_COLUMNS) ? pl->act_ident : pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
     cp.tw = pl->twH; cp.T = T; cp.oh = a.oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
     cp.frame0 = s0 * a.A * a.C; cp.n_frames = ns * a.A * a.C; cp.done = nullptr;
     cp.debug_skip = env_int("MRIACL_CP_DEBUG_SKIP", 0);
@@ -966,8 +979,8 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
     float* out_s0 = a.out + (size_t)s0 * a.oh * a.ow;
     if (n_groups > 0 && do_col) {
       ColPassParams cp{};
-      cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = a.W;
-      cp.act_w = pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
+      cp.ksp = a.ksp; cp.sb = a.slice_stride; cp.sa = a.avg_stride; cp.A = a.A; cp.C = a.C; cp.W = (a.flags & MRIACL_PACKED_COLUMNS) ? n_act : a.W;
+      cp.act_w = (a.flags & MRIACL_PACKED_COLUMNS) ? pl->act_ident : pl->act_w; cp.act_m = pl->act_m; cp.unit_mask = pl->unit_mask ? 1 : 0; cp.n_act = n_act; cp.n_groups = n_groups;
       cp.tw = pl->twH; cp.T = T; cp.oh = a.oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
       cp.frame0 = s0 * a.A * a.C; cp.n_frames = ns * a.A * a.C; cp.done = nullptr;
       const long long col_items = (long long)cp.n_frames * n_groups;
@@ -1064,6 +1077,8 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
                                            : run_fused640(fa, g);
     if (rc) return rc;
   } else {
+    if (flags & MRIACL_PACKED_COLUMNS)
+      return fail(MRIACL_ERR_UNSUPPORTED, "packed k-space columns need a plan with the 640-row column pass (H=%d Wp=%d has none)", H, Wp);
     const float* mask_dev = nullptr;
     DevPtr mask_keep;
     if (get_device_mask(dev, mask_w_host, W, &mask_dev, mask_keep)) return fail(MRIACL_ERR_CUDA, "mask upload failed: %s", rt_last_error_string());
@@ -1091,7 +1106,7 @@ int mriacl_recon_rss_f32(const void* kspace_c64, long long slice_stride, long lo
 size_t mriacl_ifft2c_abs_workspace_bytes(int B, int H, int W) {
   if (B < 1) B = 1;
   if (H < 1 || W < 1) return 0;
-  if (fused_shape(H, W) || pruned_shape(H, W)) return mriacl_recon_rss_workspace_bytes(B, 1, 1, H, W, 0, W, H, W, nullptr, 0);
+  if (fused_shape(H, W) || (pruned_shape(H, W) && pruned_fits(W, W))) return mriacl_recon_rss_workspace_bytes(B, 1, 1, H, W, 0, W, H, W, nullptr, 0);
   return align_up((size_t)B * H * W * sizeof(cf), 256);
 }
 
@@ -1102,6 +1117,17 @@ int mriacl_ifft2c_abs_f32(const void* kspace_c64, float* out, int B, int H, int 
   // RSS over a single coil is the magnitude: reuse the fused stage without crop or normalisation
   return mriacl_recon_rss_f32(kspace_c64, (long long)H * W, 0, nullptr, out, nullptr, B, 1, 1, H, W, 0, W, H, W,
                               0u, 0.f, workspace, workspace_bytes, cuda_stream);
+}
+
+int mriacl_pack_columns_host(const void* kspace_c64_host, void* packed_c64_host, long long n_rows, int W,
+                             const float* mask_w_host, int n_threads) {
+  if (n_rows < 0 || W < 1) return fail(MRIACL_ERR_INVALID, "bad dims n_rows=%lld W=%d", n_rows, W);
+  std::vector<int> idx;
+  for (int w = 0; w < W; ++w) if (!mask_w_host || mask_w_host[w] != 0.0f) idx.push_back(w);
+  if (n_rows == 0 || idx.empty()) return (int)idx.size();
+  if (!kspace_c64_host || !packed_c64_host) return fail(MRIACL_ERR_INVALID, "null pointer");
+  pack_columns(kspace_c64_host, packed_c64_host, n_rows, W, idx, n_threads);
+  return (int)idx.size();
 }
 
 int mriacl_fft2c_c64(const void* in_c64, void* out_c64, int B, int H, int W, int inverse, void* cuda_stream) {

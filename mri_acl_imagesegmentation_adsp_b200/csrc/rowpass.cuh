@@ -53,8 +53,9 @@ inline int rowpass_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_a
          n_buf * n_act * RP_ROWS * 8 + (A > 1 ? RP_ROWS * (ow + 1) * 4 : 0);
 }
 
-// spin (one thread) until a concurrently running producer has published `target`.  Bounded (~50 ms) and
-// abortable through a device-wide flag, so that a scheduling surprise ends in an error flag, not a hung device.
+// spin (one thread) until a concurrently running producer has published `target`.  Bounded (~50 ms): a scheduling
+// surprise ends in a trapped kernel (sticky CUDA error -> MRIACL_ERR_CUDA from this and every later call), never in a
+// hung device and never in a silently unwritten tile.
 __device__ __forceinline__ bool rp_wait_count(const int* counter, int target, int* error_flag) {
 #if defined(MRIACL_EMU)
   // emulator: producers may be sibling threads of the same CTA (co-resident kernel), so poll for a while
@@ -69,9 +70,12 @@ __device__ __forceinline__ bool rp_wait_count(const int* counter, int target, in
   const volatile int* err = error_flag;
   for (int spin = 0; spin < (1 << 18); ++spin) {
     if (*c >= target) { __threadfence(); return true; }
-    if (err && (spin & 63) == 63 && *err) return false;
+    if (err && (spin & 63) == 63 && *err) break;
     __nanosleep(200);
   }
+  // the producer never published (it was not co-resident, or died): a silent return would leave this tile unwritten
+  // and the call would still report success, so the kernel aborts -- every later call on the context fails loudly
+  __trap();
   return false;
 #endif
 }

@@ -12,8 +12,6 @@ Weights are seeded random (``data: synthetic`` in every number that involves it)
 """
 from __future__ import annotations
 
-from typing import List
-
 import torch
 from torch import nn
 import torch.nn.functional as F
@@ -54,39 +52,67 @@ class _DecoderBlock(nn.Module):
         return self.conv2(self.conv1(x))
 
 
+class _ResNet34Encoder(nn.Module):
+    """Module names of smp's ``ResNetEncoder`` (torchvision ``ResNet`` without ``fc`` / ``avgpool``):
+    ``conv1, bn1, relu, maxpool, layer1..layer4``."""
+
+    def __init__(self, in_ch: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_ch, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.layer1 = _stage(64, 64, 3, 1)
+        self.layer2 = _stage(64, 128, 4, 2)
+        self.layer3 = _stage(128, 256, 6, 2)
+        self.layer4 = _stage(256, 512, 3, 2)
+
+    def forward(self, x):
+        f0 = self.relu(self.bn1(self.conv1(x)))
+        f1 = self.layer1(self.maxpool(f0))
+        f2 = self.layer2(f1)
+        f3 = self.layer3(f2)
+        f4 = self.layer4(f3)
+        return f0, f1, f2, f3, f4
+
+
+class _UnetDecoder(nn.Module):
+    """smp's ``UnetDecoder``: ``blocks`` = five ``DecoderBlock`` s (``conv1`` / ``conv2`` = conv-BN-ReLU sequentials)."""
+
+    def __init__(self, enc, dec):
+        super().__init__()
+        skips = [enc[3], enc[2], enc[1], enc[0], 0]
+        cins = [enc[4]] + list(dec[:-1])
+        self.blocks = nn.ModuleList([_DecoderBlock(ci, cs, co) for ci, cs, co in zip(cins, skips, dec)])
+
+    def forward(self, feats):
+        f0, f1, f2, f3, f4 = feats
+        y = f4
+        for blk, sk in zip(self.blocks, (f3, f2, f1, f0, None)):
+            y = blk(y, sk)
+        return y
+
+
 class ResNet34UNet(nn.Module):
     """``smp.Unet("resnet34")`` topology: encoder features at strides 2, 4, 8, 16, 32 with 64, 64, 128, 256, 512
-    channels; decoder 256-128-64-32-16; logits at the input resolution."""
+    channels; decoder 256-128-64-32-16; logits at the input resolution.  The module hierarchy carries smp's names
+    (``encoder.conv1 / bn1 / layer1..4``, ``decoder.blocks.N.conv1.0 / .1``, ``segmentation_head.0``), so a raw
+    ``state_dict`` the reference saves (``REF/src/train/engine.py:264,279``, ``REF/src/train/train_unet.py:227``:
+    ``best.pt`` / ``epoch_XXX.pt``) loads with ``load_state_dict`` unchanged."""
     encoder_channels = (64, 64, 128, 256, 512)
     decoder_channels = (256, 128, 64, 32, 16)
 
     def __init__(self, in_ch: int = 1, classes: int = 1):
         super().__init__()
-        self.stem = nn.Sequential(nn.Conv2d(in_ch, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
-        self.pool = nn.MaxPool2d(3, 2, 1)
-        self.layer1 = _stage(64, 64, 3, 1)
-        self.layer2 = _stage(64, 128, 4, 2)
-        self.layer3 = _stage(128, 256, 6, 2)
-        self.layer4 = _stage(256, 512, 3, 2)
-        enc, dec = self.encoder_channels, self.decoder_channels
-        skips = [enc[3], enc[2], enc[1], enc[0], 0]
-        cins = [enc[4]] + list(dec[:-1])
-        self.decoder = nn.ModuleList([_DecoderBlock(ci, cs, co) for ci, cs, co in zip(cins, skips, dec)])
-        self.head = nn.Conv2d(dec[-1], classes, 3, 1, 1)
+        self.encoder = _ResNet34Encoder(in_ch)
+        self.decoder = _UnetDecoder(self.encoder_channels, self.decoder_channels)
+        # smp's SegmentationHead: Sequential(conv3x3, upsampling = Identity, activation = Identity)
+        self.segmentation_head = nn.Sequential(nn.Conv2d(self.decoder_channels[-1], classes, 3, 1, 1), nn.Identity(), nn.Identity())
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.shape[-1] % 32 or x.shape[-2] % 32:
             raise ValueError(f"input height and width must be divisible by 32, got {tuple(x.shape[-2:])}")
-        f0 = self.stem(x)
-        f1 = self.layer1(self.pool(f0))
-        f2 = self.layer2(f1)
-        f3 = self.layer3(f2)
-        f4 = self.layer4(f3)
-        skips: List = [f3, f2, f1, f0, None]
-        y = f4
-        for blk, sk in zip(self.decoder, skips):
-            y = blk(y, sk)
-        return self.head(y)
+        return self.segmentation_head(self.decoder(self.encoder(x)))
 
 
 def build_unet(model: str = "unet", encoder: str = "resnet34", encoder_weights: str = "none", in_ch: int = 1,

@@ -31,7 +31,7 @@ def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int
                     normalize: Optional[str] = "instance", eps: float = 0.0, flip_rows: bool = False,
                     average_axis: Optional[int] = None, pad: Optional[Tuple[int, int]] = None,
                     *, chunk_slices: Optional[int] = None, force_generic: bool = False, sequential: bool = False,
-                    schedule: Optional[str] = None):
+                    schedule: Optional[str] = None, packed: bool = False, stats_2col: bool = False):
     """k-space -> cropped (normalised) RSS magnitude images.
 
     kspace   complex64 ``(C,H,W)``, ``(S,C,H,W)`` or, with ``average_axis`` 0 or 1,
@@ -47,6 +47,12 @@ def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int
     pad      ``(left, right)`` zero-padding of the W axis before the transform.
     chunk_slices / schedule / force_generic  tuning and testing knobs: slices the workspace holds, kernel
              schedule of the fused plan ("sequential" default, "fused", "overlapped"), generic kernels.
+    packed   the last axis of ``kspace`` holds only the sampled columns (``mask != 0``), densely, as written by
+             ``mriacl_pack_columns_host`` (``recon.pipeline.HostPipeline`` ships host k-space this way); ``mask`` is
+             still the full-width mask.  Shapes with the 640-row column pass only.
+
+    stats_2col  return ``(image, mean_std)`` with the library's own contiguous ``(S, 2)`` statistics tensor instead of two
+             strided views of it (``HostPipeline`` copies it to the host in one asynchronous transfer).
 
     Returns ``(image, mean, std)``: image float32 ``(S,oh,ow)`` (``(oh,ow)`` for a single slice),
     mean/std float32 ``(S,)`` (0-d for a single slice) of the un-normalised crop.  Types follow
@@ -74,6 +80,22 @@ def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int
         else:
             S, A, C, H, W = k.shape
             slice_stride, avg_stride = A * C * H * W, C * H * W
+    if packed:
+        if mask is None:
+            raise ValueError("packed k-space needs the sampling mask that selected its columns")
+        m_arr = mask.detach().cpu().numpy() if isinstance(mask, torch.Tensor) else np.asarray(mask)
+        m_full = D.host_mask(m_arr, int(m_arr.size))
+        n_act = int(np.count_nonzero(m_full))
+        if W != n_act:
+            raise ValueError(f"packed k-space has {W} columns, the mask samples {n_act}")
+        # strides are in elements of the packed buffer; W becomes the full line length again
+        Wk, W = W, int(m_full.shape[0])
+        if average_axis is None:
+            slice_stride = C * H * Wk
+        elif average_axis == 0:
+            slice_stride, avg_stride = C * H * Wk, S * C * H * Wk
+        else:
+            slice_stride, avg_stride = A * C * H * Wk, C * H * Wk
     pad_left, pad_right = (0, 0) if pad is None else (int(pad[0]), int(pad[1]))
     if pad_left < 0 or pad_right < 0:
         raise ValueError("pad must be non-negative")
@@ -83,7 +105,8 @@ def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int
         raise ValueError("Invalid shapes.")
     m = D.host_mask(mask, W)
     flags = (cabi.NORM_INSTANCE if normalize == "instance" else 0) | (cabi.FLIP_ROWS if flip_rows else 0) \
-        | (cabi.FORCE_GENERIC if force_generic else 0) | (cabi.SEQUENTIAL if sequential else 0)
+        | (cabi.FORCE_GENERIC if force_generic else 0) | (cabi.SEQUENTIAL if sequential else 0) \
+        | (cabi.PACKED_COLUMNS if packed else 0)
     if schedule is not None:
         try:
             flags |= {"sequential": cabi.SEQUENTIAL, "fused": cabi.SCHED_FUSED, "overlapped": cabi.SCHED_OVERLAP,
@@ -101,6 +124,8 @@ def zero_filled_rss(kspace: Any, mask: Any = None, crop: Optional[Tuple[int, int
         ws = D.workspace(nbytes)
         lib.recon_rss(k.data_ptr(), slice_stride, avg_stride, m, out.data_ptr(), mean_std.data_ptr(),
                       S, A, C, H, W, pad_left, Wp, oh, ow, flags, float(eps), ws.data_ptr(), ws.numel(), D.stream_ptr())
+    if stats_2col:
+        return mv.back(out), mv.back(mean_std)
     mean, std = mean_std[:, 0], mean_std[:, 1]
     if single:
         out, mean, std = out[0], mean[0], std[0]

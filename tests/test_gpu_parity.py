@@ -275,6 +275,19 @@ def test_other_widths_behind_the_640_column_pass():
         assert torch.equal(c1, out)
 
 
+def test_wide_lines_fall_back_to_generic_kernels():
+    """640 x 4096 / 640 x 3072: one line of the pruned generic row pass would need 292 / 245 KB of shared memory, so the
+    call must take the generic kernels (which hold lines up to 8192) instead of failing -- and `supported` says GENERIC."""
+    from mri_acl_imagesegmentation_adsp_b200.adapters import recon_cabi
+    for W, seed in ((4096, 81), (3072, 82)):
+        assert recon_cabi.library().supported(640, W) == recon_cabi.PATH_GENERIC
+        k_np = synth.gaussian_kspace((1, 2, 640, W), seed)
+        m = synth.equispaced_mask(W, 4, 0.08)
+        out, _, _ = zero_filled_rss(torch.from_numpy(k_np).cuda(), m, (320, 320), None)
+        want, _, _ = O.knee_chain_numpy(k_np[0], m, (320, 320), None)
+        assert O.rel_l2(out[0].cpu().numpy(), want) <= TOL
+
+
 def test_plan_cache_is_bounded():
     """a loader that draws a new random mask per volume: more distinct masks than the plan cache keeps (64); evicted plans
     are rebuilt on demand and results never change."""

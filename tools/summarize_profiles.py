@@ -70,7 +70,10 @@ if summary:
         rd += r; wr += w
     slices = 64
     alg = 28673472 * slices
-    t = {"source": f"profiles/{tag}_ncu_summary.json (ncu --set full, one launch of each kernel of a {slices}-slice step)",
+    sys.path.insert(0, os.path.dirname(out_dir))
+    from bench import csrc_sha
+    t = {"csrc_sha": csrc_sha(),
+         "source": f"profiles/{tag}_ncu_summary.json (ncu --set full, one launch of each kernel of a {slices}-slice step)",
          "slices_per_step": slices, "step_dram_bytes": rd + wr, "step_dram_read_bytes": rd, "step_dram_write_bytes": wr,
          "algorithmic_bytes_per_step": alg, "ratio_to_algorithmic": (rd + wr) / alg, "per_kernel": per,
          "note": "the 4.4 MB/slice intermediate T (280 MB per 64-slice step) is written by the column pass and read back by the "
