@@ -52,6 +52,15 @@ def workload_config(batch: int, chunk: int, world: int) -> dict:
             "chunk_slices": chunk, "parallelism": f"slice-sharded x{world}, no collective"}
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def hbm_peak() -> tuple:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -175,7 +184,7 @@ def reference_arm(args) -> None:
                                        "requested steps were run (bounded to ~90 s)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "steps_run": steps_run, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -468,7 +477,10 @@ def ours(args) -> None:
     if not args.no_extra:
         start, stop = sharding.slice_shard(SWEEP_SLICES, world, rank)
         n_mine = stop - start
+        for _ in range(3):
+            step()
         barrier()
+        sampler.window_open()
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0.record()
         calls = 0
@@ -478,6 +490,7 @@ def ours(args) -> None:
             calls += 1
         w1.record()
         barrier()
+        sweep_clk = sampler.window_close()
         mine_ms = w0.elapsed_time(w1)
         sweep_ms = max_over_ranks(mine_ms)
         sweep_min = -max_over_ranks(-mine_ms)
@@ -486,7 +499,7 @@ def ours(args) -> None:
                  "scaling": "strong", "slices": SWEEP_SLICES, "slices_rank0": n_mine, "calls_rank0": calls,
                  "last_call_slices_rank0": (n_mine - 1) % B + 1 if n_mine else 0,
                  "ms_to_last_rank": sweep_ms, "ms_fastest_rank": sweep_min,
-                 "value": SWEEP_SLICES / (sweep_ms * 1e-3), "unit": UNIT,
+                 "value": SWEEP_SLICES / (sweep_ms * 1e-3), "unit": UNIT, "clocks": sweep_clk,
                  "hbm_frac_per_gpu": SWEEP_SLICES * BYTES_PER_SLICE / (sweep_ms * 1e-3) / 1e9 / peak / world}
 
     # ---- configs[2] and configs[3] (rank 0 at N=1) ----
@@ -522,7 +535,7 @@ def ours(args) -> None:
                 "host_pack_ms_last_step": pipe.pack_s * 1e3, "host_wait_ms_last_step": pipe.wait_s * 1e3}
 
     pipe = HostPipeline((C, H, W), CROP, "instance", 0.0, sub_batch=args.sub_batch, n_streams=args.e2e_streams, pack=pack_arg,
-                        pack_threads=args.pack_threads)
+                        pack_threads=args.pack_threads, collective_calibration=world > 1)
     head = e2e_run(pipe, e2e_steps)
     if world > 1 and pack_arg == "auto":
         # every rank decided on its own; report whether they agree (they share the host memory system)
@@ -629,7 +642,7 @@ def ours(args) -> None:
         line["gather"] = gather
     if extra:
         line["extra_configs"] = extra
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def extra_configs_leg(torch, dev, k, mask, peak) -> dict:
@@ -726,6 +739,13 @@ def main() -> None:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533")] + sys.argv
         raise SystemExit(subprocess.call(cmd))
+    # stdout carries ONE JSON line: everything else any library prints there (NCCL's version banner, torchrun notes)
+    # is sent to stderr by pointing fd 1 at fd 2 for the run; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(saved, "w")
     if args.impl == "reference":
         reference_arm(args)
     else:

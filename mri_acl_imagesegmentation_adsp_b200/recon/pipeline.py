@@ -32,7 +32,7 @@ from .cartesian import zero_filled_rss
 class HostPipeline:
     def __init__(self, slice_shape: Tuple[int, int, int], crop: Tuple[int, int] = (320, 320),
                  normalize: Optional[str] = "instance", eps: float = 0.0, sub_batch: int = 8, n_streams: int = 2,
-                 pack: Any = "auto", pack_threads: int = 0):
+                 pack: Any = "auto", pack_threads: int = 0, collective_calibration: bool = False):
         dev = D.require_cuda()
         if pack not in (True, False, "auto"):
             raise ValueError("pack must be True, False or 'auto'")
@@ -40,6 +40,10 @@ class HostPipeline:
         self.slice_shape, self.crop, self.normalize, self.eps = tuple(slice_shape), tuple(crop), normalize, eps
         self.sub = int(sub_batch)
         self.pack, self.pack_threads = pack, int(pack_threads)
+        # ranks of one box share the host memory system: with collective_calibration every rank of the default process
+        # group times both modes at the same moment and all keep the mode with the smaller summed time (the first call
+        # is then a collective: every rank must make it)
+        self.collective = bool(collective_calibration)
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
         self.stage = None            # device staging, full-width sub-batches  (allocated on first use)
         self.pstage = None           # (mask key, pinned packed buffers, device packed buffers, copy-done events)
@@ -139,6 +143,13 @@ class HostPipeline:
             torch.cuda.current_stream().synchronize()
             times[packed] = time.perf_counter() - t0
         self.calibration = {"direct_s": times[False], "packed_s": times[True], "slices": n}
+        if self.collective:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                t = torch.tensor([times[False], times[True]], dtype=torch.float64, device=self.dev)
+                dist.all_reduce(t)
+                times = {False: float(t[0]), True: float(t[1])}
+                self.calibration.update(direct_s_all_ranks=times[False], packed_s_all_ranks=times[True])
         self.pack = times[True] < times[False]
         if not self.pack:
             self.pstage = None                            # release the pinned staging buffers
