@@ -652,7 +652,7 @@ def extra_configs_leg(torch, dev, k, mask, peak) -> dict:
     from mri_acl_imagesegmentation_adsp_b200.infer.segment import segment_kspace
     from mri_acl_imagesegmentation_adsp_b200.models.unet_factory import build_unet
     from mri_acl_imagesegmentation_adsp_b200.prostate.t2 import t2_average_combine
-    from mri_acl_imagesegmentation_adsp_b200.recon.cartesian import recon_to_unet_input
+    from mri_acl_imagesegmentation_adsp_b200.recon.cartesian import recon_to_unet_input, zero_filled_rss
     from oracle import recon_oracle as O              # checker only
 
     def timed(fn, steps):
@@ -711,6 +711,20 @@ def extra_configs_leg(torch, dev, k, mask, peak) -> dict:
                          "segmentation_input_parity_rel_l2": {"value": err3, "tolerance": 1e-5, "ok": err3 <= 1e-5}}
     del net
     torch.cuda.empty_cache()
+    # the per-slice steps after the reconstruction (percentile clip -> resize -> in-mask z-score + preview)
+    from mri_acl_imagesegmentation_adsp_b200.preprocess.mri_preprocess import MRIKneePreprocessor
+    pre = MRIKneePreprocessor(out_size=CROP)
+    raw, _, _ = zero_filled_rss(k, mask, CROP, None)
+    bm = (raw > 0.3 * raw.amax(dim=(1, 2), keepdim=True)).to(torch.uint8)
+    t_post = timed(lambda: pre.clip_resize_zscore(raw, bm), 20)
+    r = pre.clip_resize_zscore(raw[:1], bm[:1])
+    wz, wp, wm, (wlo, whi) = O.post_chain(raw[0].cpu().numpy(), bm[0].cpu().numpy(), CROP, pre.clip_percentiles)
+    out["post_steps"] = {"workload": f"{B} RSS images 320x320 (output of the fused stage) -> percentile clip (1, 99.5) -> bilinear "
+                                     "resize 320x320 -> in-mask z-score + [0,1] preview, one C-ABI call",
+                         "ms": t_post, "slices_per_s": B / (t_post * 1e-3),
+                         "percentiles_bit_exact": bool(r["clip"][0, 0].item() == float(wlo) and r["clip"][0, 1].item() == float(whi)),
+                         "mask_bit_exact": bool(np.array_equal(r["mask"][0].cpu().numpy(), wm)),
+                         "img_z_max_abs_err": float(np.abs(r["img_z"][0].cpu().numpy() - wz).max())}
     return out
 
 

@@ -163,6 +163,39 @@ int mriacl_center_crop_or_pad(const void* in, void* out, int B, int H, int W, in
 int mriacl_normalize_instance_f32(const float* in, float* out, float* mean_std, int B, size_t n, float eps,
                                   void* cuda_stream);
 
+/* ---- the per-slice steps that follow the reconstruction on the reference's live call path
+ * (MRIKneePreprocessor.preprocess_record, REF/src/preprocess/mri_preprocess.py:59-84).  The Otsu / morphology body mask
+ * between clip and resize (:194-214) needs scikit-image and stays with the caller: masks are inputs here. ---- */
+
+/* lo = np.percentile(img, pmin), hi = np.percentile(img, pmax) per image of [B, n] float32 (method "linear" in
+ * numpy >= 2.0's float32 arithmetic, order statistics selected exactly), out = np.clip(img, lo, hi).
+ * out [B, n] or NULL; lo_hi [B, 2] or NULL.  Replaces _percentile_clip, mri_preprocess.py:182-185. */
+int mriacl_percentile_clip_f32(const float* in, float* out, float* lo_hi, int B, size_t n, float pmin, float pmax,
+                               void* cuda_stream);
+
+/* F.interpolate(size=(out_h, out_w), mode="bilinear", align_corners=False) of [B, H, W] float32.
+ * Replaces _resize_np, mri_preprocess.py:187-191. */
+int mriacl_resize_bilinear_f32(const float* in, float* out, int B, int H, int W, int out_h, int out_w, void* cuda_stream);
+
+/* the same interpolation of a uint8 mask followed by "> 0.5" (mri_preprocess.py:77): uint8 [B, H, W] -> [B, out_h, out_w]. */
+int mriacl_resize_mask_u8(const uint8_t* in, uint8_t* out, int B, int H, int W, int out_h, int out_w, void* cuda_stream);
+
+/* In-mask z-score and [0,1] preview of [B, n] float32 (in may alias out_z).  mask uint8 [B, n] or NULL (all inside).
+ * out_z = (x - mean) / std with the mean and POPULATION std of the pixels inside the mask (of the whole image when
+ * fewer than 10 are inside), std <= 1e-6 -> 1; out_01 = (x - lo) / float32(hi - lo + 1e-6) with the extrema inside the
+ * mask (whole image when it is empty).  stats [B, 6] = mean, std, lo, hi, pixels inside, 1 if the mask was used; any
+ * output may be NULL.  Replaces _zscore_in_mask / _preview_01, mri_preprocess.py:216-233. */
+int mriacl_zscore_preview_f32(const float* in, const uint8_t* mask, float* out_z, float* out_01, float* stats, int B,
+                              size_t n, void* cuda_stream);
+
+/* The three steps as one call on a batch (optional epilogue of the fused stage): percentile clip at full resolution,
+ * bilinear resize of the clipped image (and of the body mask, thresholded at 0.5), in-mask z-score + preview.
+ * img [B, H, W]; body_mask uint8 [B, H, W] or NULL; out_z [B, out_h, out_w] (required); out_01 or NULL; out_mask uint8
+ * (required with body_mask); clip_lo_hi [B, 2] (required, receives the percentiles); stats [B, 6] or NULL. */
+int mriacl_clip_resize_zscore_f32(const float* img, const uint8_t* body_mask, float* out_z, float* out_01,
+                                  uint8_t* out_mask, float* clip_lo_hi, float* stats, int B, int H, int W, int out_h,
+                                  int out_w, float pmin, float pmax, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,11 @@ SIGNATURES = {
     "mriacl_rss_f32": (_i, [_vp, _vp, _sz, _i, _sz, _i, _vp]),
     "mriacl_center_crop_or_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mriacl_normalize_instance_f32": (_i, [_vp, _vp, _vp, _i, _sz, _f, _vp]),
+    "mriacl_percentile_clip_f32": (_i, [_vp, _vp, _vp, _i, _sz, _f, _f, _vp]),
+    "mriacl_resize_bilinear_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mriacl_resize_mask_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mriacl_zscore_preview_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _sz, _vp]),
+    "mriacl_clip_resize_zscore_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp]),
 }
 
 
@@ -150,6 +155,27 @@ class ReconLibrary:
 
     def normalize_instance(self, in_ptr, out_ptr, mean_std_ptr, b, n, eps, stream=0) -> None:
         self._check(self._lib.mriacl_normalize_instance_f32(in_ptr, out_ptr, mean_std_ptr or None, b, n, eps, stream or None))
+
+
+    # -- steps after the reconstruction (mri_preprocess.py:182-191,216-233) ---------------
+    def percentile_clip(self, in_ptr, out_ptr, lo_hi_ptr, b, n, pmin, pmax, stream=0) -> None:
+        self._check(self._lib.mriacl_percentile_clip_f32(in_ptr, out_ptr or None, lo_hi_ptr or None, b, n, pmin, pmax, stream or None))
+
+    def resize_bilinear(self, in_ptr, out_ptr, b, h, w, oh, ow, stream=0) -> None:
+        self._check(self._lib.mriacl_resize_bilinear_f32(in_ptr, out_ptr, b, h, w, oh, ow, stream or None))
+
+    def resize_mask(self, in_ptr, out_ptr, b, h, w, oh, ow, stream=0) -> None:
+        self._check(self._lib.mriacl_resize_mask_u8(in_ptr, out_ptr, b, h, w, oh, ow, stream or None))
+
+    def zscore_preview(self, in_ptr, mask_ptr, z_ptr, p01_ptr, stats_ptr, b, n, stream=0) -> None:
+        self._check(self._lib.mriacl_zscore_preview_f32(in_ptr, mask_ptr or None, z_ptr or None, p01_ptr or None,
+                                                        stats_ptr or None, b, n, stream or None))
+
+    def clip_resize_zscore(self, img_ptr, mask_ptr, z_ptr, p01_ptr, out_mask_ptr, lo_hi_ptr, stats_ptr, b, h, w, oh, ow,
+                           pmin, pmax, stream=0) -> None:
+        self._check(self._lib.mriacl_clip_resize_zscore_f32(img_ptr, mask_ptr or None, z_ptr, p01_ptr or None,
+                                                            out_mask_ptr or None, lo_hi_ptr, stats_ptr or None,
+                                                            b, h, w, oh, ow, pmin, pmax, stream or None))
 
 
 _lock = threading.Lock()

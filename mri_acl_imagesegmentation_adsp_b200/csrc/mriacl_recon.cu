@@ -21,6 +21,9 @@
 #include "rowpass16.cuh"
 #include "rowpass640.cuh"
 #include "rowpass_generic.cuh"
+#ifndef MRIACL_EMU
+#include "post_kernels.cuh"
+#endif
 #ifdef MRIACL_EXPERIMENTAL
 // schedules that were built, measured and found slower than `sequential`: kept as negative
 // results for the emulator tests and for A/B runs, not part of the product library
@@ -1186,6 +1189,97 @@ int mriacl_normalize_instance_f32(const float* in, float* out, float* mean_std, 
   MRIACL_LAUNCH(normalize_instance_kernel, B, 256, 0, (rt_stream_t)cuda_stream, np);
   if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
   return MRIACL_OK;
+}
+
+// ---- the per-slice steps after the reconstruction (REF/src/preprocess/mri_preprocess.py:182-191,216-233) ----
+#ifdef MRIACL_EMU
+#define MRIACL_POST_GUARD return fail(MRIACL_ERR_UNSUPPORTED, "not part of the emulation build")
+#else
+#define MRIACL_POST_GUARD do {} while (0)
+#endif
+
+int mriacl_percentile_clip_f32(const float* in, float* out, float* lo_hi, int B, size_t n, float pmin, float pmax,
+                               void* cuda_stream) {
+  MRIACL_POST_GUARD;
+#ifndef MRIACL_EMU
+  if (B < 0 || n < 1) return fail(MRIACL_ERR_INVALID, "bad dims B=%d n=%zu", B, n);
+  if (!(pmin >= 0.f && pmin < pmax && pmax <= 100.f)) return fail(MRIACL_ERR_INVALID, "percentiles must satisfy 0 <= pmin < pmax <= 100");
+  if (B == 0) return MRIACL_OK;
+  if (!in || (!out && !lo_hi)) return fail(MRIACL_ERR_INVALID, "null pointer");
+  PercentileParams p{in, out, lo_hi, (long long)n, pmin, pmax};
+  MRIACL_LAUNCH(percentile_clip_kernel, B, POST_T, 0, (rt_stream_t)cuda_stream, p);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+#endif
+}
+
+int mriacl_resize_bilinear_f32(const float* in, float* out, int B, int H, int W, int out_h, int out_w, void* cuda_stream) {
+  MRIACL_POST_GUARD;
+#ifndef MRIACL_EMU
+  if (B < 0 || H < 1 || W < 1 || out_h < 1 || out_w < 1) return fail(MRIACL_ERR_INVALID, "bad dims");
+  if (B == 0) return MRIACL_OK;
+  if (!in || !out) return fail(MRIACL_ERR_INVALID, "null pointer");
+  ResizeParams p{in, nullptr, out, nullptr, nullptr, B, H, W, out_h, out_w};
+  MRIACL_LAUNCH(resize_bilinear_kernel, grid_for((long long)B * out_h * out_w, 256), 256, 0, (rt_stream_t)cuda_stream, p);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+#endif
+}
+
+int mriacl_resize_mask_u8(const uint8_t* in, uint8_t* out, int B, int H, int W, int out_h, int out_w, void* cuda_stream) {
+  MRIACL_POST_GUARD;
+#ifndef MRIACL_EMU
+  if (B < 0 || H < 1 || W < 1 || out_h < 1 || out_w < 1) return fail(MRIACL_ERR_INVALID, "bad dims");
+  if (B == 0) return MRIACL_OK;
+  if (!in || !out) return fail(MRIACL_ERR_INVALID, "null pointer");
+  ResizeParams p{nullptr, in, nullptr, out, nullptr, B, H, W, out_h, out_w};
+  MRIACL_LAUNCH(resize_bilinear_kernel, grid_for((long long)B * out_h * out_w, 256), 256, 0, (rt_stream_t)cuda_stream, p);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+#endif
+}
+
+int mriacl_zscore_preview_f32(const float* in, const uint8_t* mask, float* out_z, float* out_01, float* stats, int B,
+                              size_t n, void* cuda_stream) {
+  MRIACL_POST_GUARD;
+#ifndef MRIACL_EMU
+  if (B < 0 || n < 1) return fail(MRIACL_ERR_INVALID, "bad dims B=%d n=%zu", B, n);
+  if (B == 0) return MRIACL_OK;
+  if (!in || (!out_z && !out_01 && !stats)) return fail(MRIACL_ERR_INVALID, "null pointer");
+  ZscoreParams p{in, mask, out_z, out_01, stats, (long long)n};
+  MRIACL_LAUNCH(zscore_preview_kernel, B, POST_T, 0, (rt_stream_t)cuda_stream, p);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+#endif
+}
+
+int mriacl_clip_resize_zscore_f32(const float* img, const uint8_t* body_mask, float* out_z, float* out_01,
+                                  uint8_t* out_mask, float* clip_lo_hi, float* stats, int B, int H, int W, int out_h,
+                                  int out_w, float pmin, float pmax, void* cuda_stream) {
+  MRIACL_POST_GUARD;
+#ifndef MRIACL_EMU
+  if (B < 0 || H < 1 || W < 1 || out_h < 1 || out_w < 1) return fail(MRIACL_ERR_INVALID, "bad dims");
+  if (!(pmin >= 0.f && pmin < pmax && pmax <= 100.f)) return fail(MRIACL_ERR_INVALID, "percentiles must satisfy 0 <= pmin < pmax <= 100");
+  if (B == 0) return MRIACL_OK;
+  if (!img || !out_z || !clip_lo_hi) return fail(MRIACL_ERR_INVALID, "null pointer (img, out_z and clip_lo_hi are required)");
+  if (body_mask && !out_mask) return fail(MRIACL_ERR_INVALID, "out_mask is required when a body mask is given");
+  rt_stream_t st = (rt_stream_t)cuda_stream;
+  // 1. exact percentiles of every full-resolution image (the clipped image itself is never materialised)
+  PercentileParams pp{img, nullptr, clip_lo_hi, (long long)H * W, pmin, pmax};
+  MRIACL_LAUNCH(percentile_clip_kernel, B, POST_T, 0, st, pp);
+  // 2. clip every tap, interpolate to (out_h, out_w); the mask goes through the same interpolation and a 0.5 threshold
+  ResizeParams ri{img, nullptr, out_z, nullptr, clip_lo_hi, B, H, W, out_h, out_w};
+  MRIACL_LAUNCH(resize_bilinear_kernel, grid_for((long long)B * out_h * out_w, 256), 256, 0, st, ri);
+  if (body_mask) {
+    ResizeParams rm{nullptr, body_mask, nullptr, out_mask, nullptr, B, H, W, out_h, out_w};
+    MRIACL_LAUNCH(resize_bilinear_kernel, grid_for((long long)B * out_h * out_w, 256), 256, 0, st, rm);
+  }
+  // 3. statistics inside the resized mask, z-score in place, preview
+  ZscoreParams zp{out_z, body_mask ? out_mask : nullptr, out_z, out_01, stats, (long long)out_h * out_w};
+  MRIACL_LAUNCH(zscore_preview_kernel, B, POST_T, 0, st, zp);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+#endif
 }
 
 }  // extern "C"

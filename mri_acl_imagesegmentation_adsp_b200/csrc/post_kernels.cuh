@@ -1,0 +1,239 @@
+// post_kernels.cuh -- the per-slice steps that follow the reconstruction on the reference's live call path
+// (REF/src/preprocess/mri_preprocess.py:59-84): percentile clip (:182-185), bilinear resize (:187-191), in-mask
+// z-score (:216-224) and the [0,1] preview (:226-233).  (The Otsu / morphology body mask between clip and resize needs
+// scikit-image and stays on the host: the mask is an input here.)
+//
+// Everything is float32 and follows the reference's own arithmetic step by step, because parity is judged on it:
+//  * np.percentile (numpy >= 2.0, method "linear") on a float32 image works entirely in float32: q32 = float32(q) / 100,
+//    virtual index v = float32(n - 1) * q32, i = floor(v), g = v - i, result = a + (b - a) * g for g < 0.5, else
+//    b - (b - a) * (1 - g), with a, b the i-th and (i+1)-th smallest values -- unfused multiplies and adds.
+//    The two order statistics are found EXACTLY by a radix select over the monotone integer image of the floats
+//    (four 8-bit passes, one CTA per image, all four ranks of the two percentiles at once).
+//  * F.interpolate(mode="bilinear", align_corners=False) on the CPU: scale = in / out (float32), source coordinate
+//    s = scale * (d + 0.5) - 0.5 clamped at 0, taps i0 = int(s), i1 = i0 + (i0 < in - 1), weights (1 - l, l) with
+//    l = s - i0, value = h0 * (w0 * p00 + w1 * p01) + h1 * (w0 * p10 + w1 * p11), unfused.
+//  * z-score: mean and POPULATION standard deviation of the pixels inside the mask (of the whole image when fewer than
+//    ten are inside), std <= 1e-6 replaced by 1; preview: (x - lo) / float32(hi - lo + 1e-6) with lo / hi the extrema
+//    inside the mask (of the whole image when the mask is empty).  Statistics are accumulated in double.
+#pragma once
+#include "common.cuh"
+
+namespace mriacl {
+
+constexpr int POST_T = 1024;          // threads of the one-CTA-per-image kernels
+constexpr int POST_COPIES = 8;        // privatised histogram copies (hot exponent bins would serialise a single one)
+
+__device__ __forceinline__ unsigned post_key(float x) {
+  const unsigned u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);       // monotone: key(a) < key(b)  <=>  a < b
+}
+__device__ __forceinline__ float post_unkey(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// numpy's float32 lerp between the order statistics a <= b
+__device__ __forceinline__ float post_lerp(float a, float b, float g) {
+  const float d = __fsub_rn(b, a);
+  return g < 0.5f ? __fadd_rn(a, __fmul_rn(d, g)) : __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.0f, g)));
+}
+
+struct PercentileParams {
+  const float* in;      // [B][n]
+  float* out;           // [B][n] clipped image, or nullptr
+  float* lo_hi;         // [B][2] or nullptr
+  long long n;
+  float pmin, pmax;     // percent, 0..100
+};
+
+// one CTA per image
+__global__ void __launch_bounds__(POST_T) percentile_clip_kernel(PercentileParams p) {
+  __shared__ unsigned hist[4][POST_COPIES][256];
+  __shared__ unsigned prefix[4];
+  __shared__ unsigned long long rank[4];
+  __shared__ int alias[4];
+  __shared__ float s_lo_hi[2];
+  const int tid = threadIdx.x, copy = (tid >> 5) & (POST_COPIES - 1);
+  const float* x = p.in + (long long)blockIdx.x * p.n;
+  const long long n = p.n;
+
+  // virtual indices in float32, exactly as numpy computes them
+  const float nm1 = (float)(n - 1);
+  const float v_lo = __fmul_rn(nm1, __fdiv_rn(p.pmin, 100.0f)), v_hi = __fmul_rn(nm1, __fdiv_rn(p.pmax, 100.0f));
+  const float f_lo = floorf(v_lo), f_hi = floorf(v_hi);
+  if (tid == 0) {
+    const long long i_lo = (long long)f_lo, i_hi = (long long)f_hi;
+    rank[0] = (unsigned long long)min(max(i_lo, 0LL), n - 1);
+    rank[1] = (unsigned long long)min(max(i_lo + 1, 0LL), n - 1);
+    rank[2] = (unsigned long long)min(max(i_hi, 0LL), n - 1);
+    rank[3] = (unsigned long long)min(max(i_hi + 1, 0LL), n - 1);
+    for (int t = 0; t < 4; ++t) prefix[t] = 0u;
+  }
+  __syncthreads();
+
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid == 0)
+      for (int t = 0; t < 4; ++t) {          // ranks that still share a prefix share a histogram
+        alias[t] = t;
+        for (int u = 0; u < t; ++u) if (prefix[u] == prefix[t]) { alias[t] = u; break; }
+      }
+    for (int i = tid; i < 4 * POST_COPIES * 256; i += POST_T) (&hist[0][0][0])[i] = 0u;
+    __syncthreads();
+    const unsigned pf0 = prefix[0], pf1 = prefix[1], pf2 = prefix[2], pf3 = prefix[3];
+    const bool own1 = alias[1] == 1, own2 = alias[2] == 2, own3 = alias[3] == 3;
+    for (long long i = tid; i < n; i += POST_T) {
+      const unsigned k = post_key(x[i]);
+      const unsigned hi_bits = pass == 0 ? 0u : (k >> (shift + 8));
+      const unsigned bin = (k >> shift) & 255u;
+      if (hi_bits == pf0) atomicAdd(&hist[0][copy][bin], 1u);
+      if (own1 && hi_bits == pf1) atomicAdd(&hist[1][copy][bin], 1u);
+      if (own2 && hi_bits == pf2) atomicAdd(&hist[2][copy][bin], 1u);
+      if (own3 && hi_bits == pf3) atomicAdd(&hist[3][copy][bin], 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < 4 * 256; i += POST_T) {      // fold the copies
+      unsigned s = 0;
+      for (int c = 0; c < POST_COPIES; ++c) s += hist[i >> 8][c][i & 255];
+      hist[i >> 8][0][i & 255] = s;
+    }
+    __syncthreads();
+    if (tid < 4) {
+      const unsigned* h = hist[alias[tid]][0];
+      unsigned long long r = rank[tid];
+      int b = 0;
+      for (; b < 255; ++b) { if (r < h[b]) break; r -= h[b]; }
+      rank[tid] = r;
+      prefix[tid] = (prefix[tid] << 8) | (unsigned)b;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float a0 = post_unkey(prefix[0]), b0 = post_unkey(prefix[1]), a1 = post_unkey(prefix[2]), b1 = post_unkey(prefix[3]);
+    s_lo_hi[0] = post_lerp(a0, b0, __fsub_rn(v_lo, f_lo));
+    s_lo_hi[1] = post_lerp(a1, b1, __fsub_rn(v_hi, f_hi));
+    if (p.lo_hi) { p.lo_hi[2 * blockIdx.x] = s_lo_hi[0]; p.lo_hi[2 * blockIdx.x + 1] = s_lo_hi[1]; }
+  }
+  __syncthreads();
+  if (p.out) {
+    const float lo = s_lo_hi[0], hi = s_lo_hi[1];
+    float* y = p.out + (long long)blockIdx.x * n;
+    for (long long i = tid; i < n; i += POST_T) y[i] = fminf(fmaxf(x[i], lo), hi);      // np.clip = minimum(maximum(x, lo), hi)
+  }
+}
+
+struct ResizeParams {
+  const float* in;            // [B][H][W] float32, or
+  const unsigned char* in_u8; // [B][H][W] uint8 (a mask: values are used as 0 / 1 floats), exactly one of the two is set
+  float* out;                 // [B][oh][ow] float32, or
+  unsigned char* out_u8;      // [B][oh][ow] uint8 = (resized > 0.5)
+  const float* lo_hi;         // [B][2] clip applied to every tap before the interpolation, or nullptr
+  int B, H, W, oh, ow;
+};
+
+// thread = output pixel
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(ResizeParams p) {
+  const long long total = (long long)p.B * p.oh * p.ow;
+  const float sh = __fdiv_rn((float)p.H, (float)p.oh), sw = __fdiv_rn((float)p.W, (float)p.ow);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % p.ow);
+    const long long t = i / p.ow;
+    const int oy = (int)(t % p.oh), b = (int)(t / p.oh);
+    float sy = __fsub_rn(__fmul_rn(sh, __fadd_rn((float)oy, 0.5f)), 0.5f), sx = __fsub_rn(__fmul_rn(sw, __fadd_rn((float)ox, 0.5f)), 0.5f);
+    sy = sy < 0.f ? 0.f : sy; sx = sx < 0.f ? 0.f : sx;
+    int y0 = (int)sy, x0 = (int)sx;
+    y0 = min(y0, p.H - 1); x0 = min(x0, p.W - 1);
+    const int y1 = y0 + (y0 < p.H - 1 ? 1 : 0), x1 = x0 + (x0 < p.W - 1 ? 1 : 0);
+    const float ly = __fsub_rn(sy, (float)y0), lx = __fsub_rn(sx, (float)x0);
+    const float hy = __fsub_rn(1.0f, ly), hx = __fsub_rn(1.0f, lx);
+    const long long base = (long long)b * p.H * p.W;
+    float p00, p01, p10, p11;
+    if (p.in) {
+      p00 = p.in[base + (long long)y0 * p.W + x0]; p01 = p.in[base + (long long)y0 * p.W + x1];
+      p10 = p.in[base + (long long)y1 * p.W + x0]; p11 = p.in[base + (long long)y1 * p.W + x1];
+      if (p.lo_hi) {
+        const float lo = p.lo_hi[2 * b], hi = p.lo_hi[2 * b + 1];
+        p00 = fminf(fmaxf(p00, lo), hi); p01 = fminf(fmaxf(p01, lo), hi);
+        p10 = fminf(fmaxf(p10, lo), hi); p11 = fminf(fmaxf(p11, lo), hi);
+      }
+    } else {
+      p00 = (float)p.in_u8[base + (long long)y0 * p.W + x0]; p01 = (float)p.in_u8[base + (long long)y0 * p.W + x1];
+      p10 = (float)p.in_u8[base + (long long)y1 * p.W + x0]; p11 = (float)p.in_u8[base + (long long)y1 * p.W + x1];
+    }
+    const float top = __fadd_rn(__fmul_rn(hx, p00), __fmul_rn(lx, p01)), bot = __fadd_rn(__fmul_rn(hx, p10), __fmul_rn(lx, p11));
+    const float v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+    if (p.out) p.out[i] = v; else p.out_u8[i] = v > 0.5f ? 1 : 0;
+  }
+}
+
+struct ZscoreParams {
+  const float* in;            // [B][n] (resized, clipped) image; may alias out_z
+  const unsigned char* mask;  // [B][n] or nullptr (= every pixel inside)
+  float* out_z;               // [B][n] (x - mean) / std, or nullptr
+  float* out_01;              // [B][n] preview, or nullptr
+  float* stats;               // [B][6]: mean, std (after the floor), lo, hi, pixels inside the mask, 1 if the mask was used
+  long long n;
+};
+
+template <class T, class Op> __device__ __forceinline__ T post_block_reduce(T v, T* scratch /* 32 */, Op op, T identity) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T r = identity;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = op(r, scratch[w]);
+  return r;
+}
+
+// one CTA per image: three sweeps (count / sum / extrema -> mean; squared deviations -> std; outputs)
+__global__ void __launch_bounds__(POST_T) zscore_preview_kernel(ZscoreParams p) {
+  __shared__ double sd[32];
+  __shared__ float sf[32];
+  const int tid = threadIdx.x;
+  const long long n = p.n;
+  const float* x = p.in + (long long)blockIdx.x * n;
+  const unsigned char* m = p.mask ? p.mask + (long long)blockIdx.x * n : nullptr;
+  auto add = [](double a, double b) { return a + b; };
+  auto fmn = [](float a, float b) { return fminf(a, b); };
+  auto fmx = [](float a, float b) { return fmaxf(a, b); };
+
+  double cnt_in = 0.0, sum_in = 0.0, sum_all = 0.0;
+  float mn_in = INFINITY, mx_in = -INFINITY, mn_all = INFINITY, mx_all = -INFINITY;
+  for (long long i = tid; i < n; i += POST_T) {
+    const float v = x[i];
+    sum_all += (double)v; mn_all = fminf(mn_all, v); mx_all = fmaxf(mx_all, v);
+    if (!m || m[i] > 0) { cnt_in += 1.0; sum_in += (double)v; mn_in = fminf(mn_in, v); mx_in = fmaxf(mx_in, v); }
+  }
+  cnt_in = post_block_reduce(cnt_in, sd, add, 0.0);
+  sum_in = post_block_reduce(sum_in, sd, add, 0.0);
+  sum_all = post_block_reduce(sum_all, sd, add, 0.0);
+  mn_in = post_block_reduce(mn_in, sf, fmn, INFINITY);
+  mx_in = post_block_reduce(mx_in, sf, fmx, -INFINITY);
+  mn_all = post_block_reduce(mn_all, sf, fmn, INFINITY);
+  mx_all = post_block_reduce(mx_all, sf, fmx, -INFINITY);
+  const bool use_mask = cnt_in >= 10.0;                     // `vals.size < 10` -> statistics of the whole image
+  const double mean_d = use_mask ? sum_in / cnt_in : sum_all / (double)n;
+  double m2 = 0.0;
+  for (long long i = tid; i < n; i += POST_T) {
+    if (!use_mask || !m || m[i] > 0) { const double d = (double)x[i] - mean_d; m2 += d * d; }
+  }
+  m2 = post_block_reduce(m2, sd, add, 0.0);
+  const float mean = (float)mean_d;
+  float stdv = (float)sqrt(m2 / (use_mask ? cnt_in : (double)n));   // np.std: population
+  stdv = stdv > 1e-6f ? stdv : 1.0f;
+  const float lo = cnt_in > 0.0 ? mn_in : mn_all, hi = cnt_in > 0.0 ? mx_in : mx_all;
+  const float den = (float)((double)hi - (double)lo + 1e-6);
+  if (tid == 0 && p.stats) {
+    float* s = p.stats + 6 * (long long)blockIdx.x;
+    s[0] = mean; s[1] = stdv; s[2] = lo; s[3] = hi; s[4] = (float)cnt_in; s[5] = use_mask ? 1.f : 0.f;
+  }
+  float* z = p.out_z ? p.out_z + (long long)blockIdx.x * n : nullptr;
+  float* q = p.out_01 ? p.out_01 + (long long)blockIdx.x * n : nullptr;
+  for (long long i = tid; i < n; i += POST_T) {
+    const float v = x[i];
+    if (q) q[i] = __fdiv_rn(__fsub_rn(v, lo), den);
+    if (z) z[i] = __fdiv_rn(__fsub_rn(v, mean), stdv);
+  }
+}
+
+}  // namespace mriacl

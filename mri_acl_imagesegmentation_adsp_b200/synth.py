@@ -92,3 +92,49 @@ FROZEN_MASKS = ((368, 4, 0.08, 0), (368, 8, 0.04, 0), (368, 4, 0.08, 1), (368, 4
 
 def mask_name(width: int, acceleration: int, center_fraction: float, offset: int = 0) -> str:
     return f"equispaced({width},{acceleration},{center_fraction:g},{offset})"
+
+
+def magnitude_image(shape: Tuple[int, int], seed: int, flat: bool = False) -> np.ndarray:
+    """float32 ``(H, W)`` magnitude-like image for the steps after the reconstruction: an off-centre ellipse with smooth
+    shading and Rician-looking noise (``flat``: a constant image, the std-floor case).  Pure numpy from ``seed``."""
+    h, w = shape
+    if flat:
+        return np.full(shape, 0.25, dtype=np.float32)
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.linspace(-1, 1, h, dtype=np.float32), np.linspace(-1, 1, w, dtype=np.float32), indexing="ij")
+    body = (((xx - 0.1) / 0.7) ** 2 + ((yy + 0.05) / 0.55) ** 2 <= 1).astype(np.float32)
+    body += 0.5 * (((xx + 0.2) / 0.2) ** 2 + ((yy - 0.1) / 0.15) ** 2 <= 1)
+    shade = (1.0 + 0.3 * xx - 0.2 * yy).astype(np.float32)
+    n1 = rng.standard_normal(shape, dtype=np.float32)
+    n2 = rng.standard_normal(shape, dtype=np.float32)
+    return np.sqrt((body * shade + 0.03 * n1) ** 2 + (0.03 * n2) ** 2).astype(np.float32)
+
+
+def body_mask_standin(img: np.ndarray, frac: float = 0.3) -> np.ndarray:
+    """uint8 mask ``img > frac * max``: a stand-in for the reference's Otsu + morphology body mask (scikit-image is not
+    available here; the steps under test only need SOME mask)."""
+    return (img > frac * img.max()).astype(np.uint8)
+
+
+#: (name, input shape, output size, seed, mask rule) of the post-reconstruction golden cases (tests/golden/post_vectors.npz)
+POST_CASES = (("knee_640x368", (640, 368), (320, 320), 501, "standin"),
+              ("knee_320x320_identity", (320, 320), (320, 320), 502, "standin"),
+              ("odd_37x53_to_24x40", (37, 53), (24, 40), 503, "standin"),
+              ("tiny_mask", (37, 53), (24, 40), 504, "tiny"),          # < 10 pixels inside: whole-image statistics
+              ("empty_mask", (37, 53), (24, 40), 505, "empty"),        # preview falls back to the image extrema
+              ("flat_image", (32, 32), (16, 16), 0, "flat"))           # std <= 1e-6 -> 1
+
+
+def post_case_inputs(name: str):
+    for nm, shape, out, seed, rule in POST_CASES:
+        if nm == name:
+            img = magnitude_image(shape, seed, flat=(rule == "flat"))
+            if rule in ("standin", "flat"):
+                mk = body_mask_standin(img) if rule == "standin" else np.ones(shape, np.uint8)
+            elif rule == "tiny":
+                mk = np.zeros(shape, np.uint8)
+                mk[10:13, 20:23] = 1
+            else:
+                mk = np.zeros(shape, np.uint8)
+            return img, mk, out
+    raise KeyError(name)

@@ -382,6 +382,91 @@ def prostate_chain(kspace: np.ndarray, mask_w: Optional[np.ndarray], pad: Tuple[
     return t2_average_combine(apply_mask(kspace, mask_w), pad, crop)
 
 
+# --------------------------------------------------------------------------- after the reconstruction
+# REF/src/preprocess/mri_preprocess.py:59-84: clip -> (body mask) -> resize -> z-score -> preview
+
+def percentile_clip(img: np.ndarray, pmin: float, pmax: float):
+    """``_percentile_clip`` (``mri_preprocess.py:182-185``); also returns (lo, hi)."""
+    lo, hi = np.percentile(img, pmin), np.percentile(img, pmax)
+    return np.clip(img, lo, hi), lo, hi
+
+
+def percentile_f32(img: np.ndarray, q: float) -> np.float32:
+    """What ``np.percentile`` (numpy >= 2.0, method 'linear') does to a float32 array, spelled out: the quantile, the
+    virtual index and the interpolation are all float32 -- the arithmetic the CUDA kernel restates."""
+    f32 = np.float32
+    s = np.sort(np.asarray(img, dtype=f32).ravel())
+    n = s.size
+    v = f32(f32(n - 1) * (f32(q) / f32(100)))
+    i = int(np.floor(v))
+    g = f32(v - f32(i))
+    a, b = s[min(i, n - 1)], s[min(i + 1, n - 1)]
+    d = f32(b - a)
+    return f32(a + f32(d * g)) if g < f32(0.5) else f32(b - f32(d * f32(f32(1) - g)))
+
+
+def resize_bilinear(img: np.ndarray, out_hw: Tuple[int, int]) -> np.ndarray:
+    """``_resize_np`` (``mri_preprocess.py:187-191``): ``F.interpolate(mode='bilinear', align_corners=False)`` restated in
+    numpy float32 (ATen ``area_pixel_compute_source_index``: scale = in / out, s = scale * (d + 0.5) - 0.5 clamped at
+    0; taps i0 = int(s), i1 = i0 + (i0 < in - 1); value = h0 * (w0 p00 + w1 p01) + h1 * (w0 p10 + w1 p11))."""
+    f32 = np.float32
+    x = np.asarray(img, dtype=f32)
+    H, W = x.shape
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+
+    def taps(n_in, n_out):
+        scale = f32(n_in) / f32(n_out)
+        s = scale * (np.arange(n_out, dtype=f32) + f32(0.5)) - f32(0.5)
+        s = np.where(s < 0, f32(0), s).astype(f32)
+        i0 = np.minimum(s.astype(np.int64), n_in - 1)
+        i1 = i0 + (i0 < n_in - 1)
+        l1 = (s - i0.astype(f32)).astype(f32)
+        return i0, i1, (f32(1) - l1).astype(f32), l1
+
+    y0, y1, hy, ly = taps(H, oh)
+    x0, x1, hx, lx = taps(W, ow)
+    top = hx[None, :] * x[y0][:, x0] + lx[None, :] * x[y0][:, x1]
+    bot = hx[None, :] * x[y1][:, x0] + lx[None, :] * x[y1][:, x1]
+    return (hy[:, None] * top + ly[:, None] * bot).astype(f32)
+
+
+def resize_mask(mask: np.ndarray, out_hw: Tuple[int, int]) -> np.ndarray:
+    """``(self._resize_np(mk.astype(np.float32), self.out_size) > 0.5).astype(np.uint8)`` (``mri_preprocess.py:77``)."""
+    return (resize_bilinear(mask.astype(np.float32), out_hw) > 0.5).astype(np.uint8)
+
+
+def zscore_in_mask(img: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """``_zscore_in_mask`` (``mri_preprocess.py:216-224``): population std, < 10 pixels -> whole image, std floor."""
+    vals = img[mask > 0]
+    if vals.size < 10:
+        mean, std = img.mean(), img.std()
+    else:
+        mean, std = vals.mean(), vals.std()
+    std = std if std > 1e-6 else 1.0
+    return ((img - mean) / std).astype(np.float32)
+
+
+def preview_01(img: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """``_preview_01`` (``mri_preprocess.py:226-233``)."""
+    vals = img[mask > 0]
+    if vals.size > 0:
+        lo, hi = float(vals.min()), float(vals.max())
+    else:
+        lo, hi = float(img.min()), float(img.max())
+    return ((img - lo) / (hi - lo + 1e-6)).astype(np.float32)
+
+
+def post_chain(img: np.ndarray, body_mask: Optional[np.ndarray], out_hw: Tuple[int, int] = (320, 320),
+               clip: Tuple[float, float] = (1.0, 99.5)):
+    """The tail of ``preprocess_record`` (``mri_preprocess.py:62-84``) with the body mask given (Otsu / morphology need
+    scikit-image): clip -> resize image and mask -> z-score -> preview.  Returns (img_z, img_01, mask_r, (lo, hi))."""
+    clipped, lo, hi = percentile_clip(img, *clip)
+    img_r = resize_bilinear(clipped, out_hw)
+    mk = np.ones(img.shape, np.uint8) if body_mask is None else body_mask
+    mk_r = resize_mask(mk, out_hw)
+    return zscore_in_mask(img_r, mk_r), preview_01(img_r, mk_r), mk_r, (np.float32(lo), np.float32(hi))
+
+
 def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
     """||a-b||_2 / ||b||_2 in float64 -- the parity metric of BASELINE.json."""
     a = np.asarray(a)

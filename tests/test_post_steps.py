@@ -1,0 +1,143 @@
+"""The per-slice steps after the reconstruction (REF/src/preprocess/mri_preprocess.py:182-191,216-233).
+
+CPU: the oracle's restatement against the golden vectors frozen from the live reference (oracle/make_golden_post.py) and --
+where /root/reference exists -- against the reference itself.  GPU: the CUDA kernels through the Python twins / the C ABI
+against both.  Tolerances: percentiles and resized masks bit-exact; float images 2e-6 of the image's dynamic range (the
+reference's torch CPU interpolation and numpy's pairwise float32 means round differently in the last place)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mri_acl_imagesegmentation_adsp_b200 import synth
+from oracle import recon_oracle as O
+from oracle import ref_shim
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CLIP = (1.0, 99.5)
+
+
+@pytest.fixture(scope="module")
+def post_golden():
+    return np.load(os.path.join(HERE, "golden", "post_vectors.npz")), json.load(open(os.path.join(HERE, "golden", "post_manifest.json")))
+
+
+def _close(a, b, scale):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max()) <= 2e-6 * scale
+
+
+CASES = [c[0] for c in synth.POST_CASES]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_post_chain_vs_golden(post_golden, name):
+    g, man = post_golden
+    c = man["cases"][name]
+    img, mk, out = synth.post_case_inputs(name)
+    z, p01, mr, (lo, hi) = O.post_chain(img, mk, out, CLIP)
+    sub = c["float_subsample"]
+    assert np.array_equal(np.array([lo, hi], np.float32), g[f"{name}/lo_hi"])
+    assert O.percentile_f32(img, CLIP[0]) == g[f"{name}/lo_hi"][0] and O.percentile_f32(img, CLIP[1]) == g[f"{name}/lo_hi"][1]
+    assert np.array_equal(mr, g[f"{name}/mask_r"])
+    img_r = O.resize_bilinear(O.percentile_clip(img, *CLIP)[0], out)
+    assert _close(img_r[::sub, ::sub], g[f"{name}/img_r"], float(img.max()))
+    assert _close(z[::sub, ::sub], g[f"{name}/img_z"], max(1.0, float(np.abs(g[f"{name}/img_z"]).max())))
+    assert _close(p01[::sub, ::sub], g[f"{name}/img_01"], 4.0)        # (tiny-mask case: values far outside [0, 1])
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
+def test_oracle_post_steps_vs_live_reference():
+    pre = ref_shim.knee_preprocessor_cls()
+    rng = np.random.default_rng(9)
+    for shape, out in (((64, 48), (32, 32)), ((33, 47), (50, 20)), ((320, 320), (320, 320))):
+        img = np.abs(rng.standard_normal(shape)).astype(np.float32) * 3
+        mk = (img > 1.0).astype(np.uint8)
+        for q in (0.0, 1.0, 37.3, 50.0, 99.5, 100.0):
+            assert O.percentile_f32(img, q) == np.percentile(img, q)
+        want = pre._percentile_clip(img, *CLIP)
+        assert np.array_equal(O.percentile_clip(img, *CLIP)[0], want)
+        assert _close(O.resize_bilinear(want, out), pre._resize_np(want, out), 10.0)
+        assert np.array_equal(O.resize_mask(mk, out), (pre._resize_np(mk.astype(np.float32), out) > 0.5).astype(np.uint8))
+        r = pre._resize_np(want, out)
+        mr = O.resize_mask(mk, out)
+        assert np.array_equal(O.zscore_in_mask(r, mr), pre._zscore_in_mask(r, mr))
+        assert np.array_equal(O.preview_01(r, mr), pre._preview_01(r, mr))
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_post_chain_vs_golden_and_oracle(post_golden, name):
+    from mri_acl_imagesegmentation_adsp_b200.preprocess.mri_preprocess import MRIKneePreprocessor
+    g, man = post_golden
+    c = man["cases"][name]
+    sub = c["float_subsample"]
+    img, mk, out = synth.post_case_inputs(name)
+    pre = MRIKneePreprocessor(out_size=out, clip_percentiles=CLIP)
+    r = pre.clip_resize_zscore(torch.from_numpy(img[None]).cuda(), torch.from_numpy(mk[None]).cuda())
+    assert np.array_equal(r["clip"][0].cpu().numpy(), g[f"{name}/lo_hi"])                      # percentiles: bit-exact
+    assert np.array_equal(r["mask"][0].cpu().numpy(), g[f"{name}/mask_r"])                     # resized mask: bit-exact
+    z, p01 = r["img_z"][0].cpu().numpy(), r["img_01"][0].cpu().numpy()
+    assert _close(z[::sub, ::sub], g[f"{name}/img_z"], max(1.0, float(np.abs(g[f"{name}/img_z"]).max())))
+    assert _close(p01[::sub, ::sub], g[f"{name}/img_01"], 4.0)
+    wz, wp, wm, _ = O.post_chain(img, mk, out, CLIP)
+    assert _close(z, wz, max(1.0, float(np.abs(wz).max()))) and _close(p01, wp, 4.0) and np.array_equal(r["mask"][0].cpu().numpy(), wm)
+    # the twins of the reference's static methods, one step at a time (numpy in -> numpy out)
+    clipped = MRIKneePreprocessor._percentile_clip(img, *CLIP)
+    assert isinstance(clipped, np.ndarray) and np.array_equal(clipped, O.percentile_clip(img, *CLIP)[0])
+    step = c["clipped_row_step"]
+    assert np.array_equal(clipped[::step, ::sub], g[f"{name}/clipped"])
+    img_r = MRIKneePreprocessor._resize_np(clipped, out)
+    assert _close(img_r[::sub, ::sub], g[f"{name}/img_r"], float(img.max()))
+    assert _close(MRIKneePreprocessor._zscore_in_mask(img_r, wm), O.zscore_in_mask(img_r, wm), max(1.0, float(np.abs(wz).max())))
+    assert _close(MRIKneePreprocessor._preview_01(img_r, wm), O.preview_01(img_r, wm), 4.0)
+
+
+@pytest.mark.gpu
+def test_gpu_percentiles_exact_on_hard_inputs():
+    """ties, negative values, denormals, extreme percentiles, a batch of different images in one call."""
+    from mri_acl_imagesegmentation_adsp_b200.adapters import recon_cabi
+    lib = recon_cabi.library()
+    rng = np.random.default_rng(3)
+    imgs = np.stack([rng.standard_normal(5000).astype(np.float32) * 10,
+                     np.round(rng.standard_normal(5000) * 3).astype(np.float32),            # heavy ties, +-0
+                     (rng.standard_normal(5000) * 1e-41).astype(np.float32),               # denormals
+                     np.abs(rng.standard_normal(5000)).astype(np.float32) ** 8])           # huge dynamic range
+    t = torch.from_numpy(imgs).cuda()
+    out = torch.empty_like(t)
+    lh = torch.empty((4, 2), dtype=torch.float32, device="cuda")
+    for pmin, pmax in ((1.0, 99.5), (0.0, 100.0), (37.3, 37.4), (49.99, 50.01)):
+        lib.percentile_clip(t.data_ptr(), out.data_ptr(), lh.data_ptr(), 4, 5000, pmin, pmax, 0)
+        torch.cuda.synchronize()
+        for b in range(4):
+            lo, hi = np.percentile(imgs[b], pmin), np.percentile(imgs[b], pmax)
+            assert lh[b, 0].item() == lo and lh[b, 1].item() == hi, (b, pmin, pmax)
+            assert np.array_equal(out[b].cpu().numpy(), np.clip(imgs[b], lo, hi))
+    with pytest.raises(ValueError):
+        lib.percentile_clip(t.data_ptr(), out.data_ptr(), lh.data_ptr(), 4, 5000, 60.0, 40.0, 0)
+
+
+@pytest.mark.gpu
+def test_gpu_preprocess_records_contract():
+    """the k-space branch of preprocess_records on the device: slice_keep band, (S,1,H,W) float32 tensor, previews, masks."""
+    from mri_acl_imagesegmentation_adsp_b200.preprocess.mri_preprocess import MRIKneePreprocessor
+    ks = [synth.phantom_kspace((1, 64, 48), 40 + i)[0] for i in range(10)]
+    recs = [{"kspace": k, "meta": {"slice_idx": 100 + i}} for i, k in enumerate(ks)]
+    fn = lambda im: synth.body_mask_standin(im, 0.3)
+    pre = MRIKneePreprocessor(out_size=(32, 32), body_mask_fn=fn)
+    out = pre.preprocess_records(recs)
+    assert out["tensor"].shape == (4, 1, 32, 32) and out["tensor"].dtype == torch.float32 and out["tensor"].device.type == "cpu"
+    assert out["preview"].shape == (4, 32, 32) and out["mask"].shape == (4, 32, 32) and out["mask"].dtype == np.uint8
+    assert out["indices"] == [103, 104, 105, 106] and out["sources"] == ["kspace"] * 4
+    for j, i in enumerate(range(3, 7)):
+        img = O.ifft2c_single(ks[i])
+        clipped = O.percentile_clip(img, *CLIP)[0]
+        z, p01, mr, _ = O.post_chain(img, fn(clipped), (32, 32), CLIP)
+        assert np.array_equal(out["mask"][j], mr)
+        assert _close(out["tensor"][j, 0].numpy(), z, max(1.0, float(np.abs(z).max()))) and _close(out["preview"][j], p01, 4.0)
+    with pytest.raises(ValueError):
+        pre.preprocess_records([])
+    with pytest.raises(ValueError):
+        MRIKneePreprocessor(use_n4=True)
