@@ -725,7 +725,50 @@ def extra_configs_leg(torch, dev, k, mask, peak) -> dict:
                          "percentiles_bit_exact": bool(r["clip"][0, 0].item() == float(wlo) and r["clip"][0, 1].item() == float(whi)),
                          "mask_bit_exact": bool(np.array_equal(r["mask"][0].cpu().numpy(), wm)),
                          "img_z_max_abs_err": float(np.abs(r["img_z"][0].cpu().numpy() - wz).max())}
+    # GRAPPA weight application at the prostate file shape, one average (30 slices) per launch
+    from mri_acl_imagesegmentation_adsp_b200.prostate.grappa import Grappa
+    S, Cc, RO, PE = 30, 16, 640, 451
+    keep = np.zeros(PE, dtype=bool)
+    keep[::2] = True
+    keep[(PE - 24) // 2:(PE - 24) // 2 + 24] = True
+    g = torch.Generator(device=dev).manual_seed(78)
+    kg = torch.view_as_complex(torch.randn((S, Cc, RO, PE, 2), device=dev, generator=g))
+    kg[..., torch.from_numpy(~keep).to(dev)] = 0
+    gr = Grappa(np.transpose(kg[0].cpu().numpy(), (2, 0, 1)), kernel_size=(5, 5), coil_axis=1)
+    rngw = np.random.default_rng(5)
+    kv = gr.kernel_var_dict
+    wd = {int(i): (0.05 * (rngw.standard_normal((Cc, int(kv["patches"][i].sum()))) +
+                           1j * rngw.standard_normal((Cc, int(kv["patches"][i].sum()))))).astype(np.complex64) for i in kv["patch_indices"]}
+    plan = gr._device_plan(dev)
+    Wd = gr._pack_weights([wd] * S, plan)
+    lib = cabi_library()
+
+    def run_grappa():
+        lib.grappa_apply(kg.data_ptr(), Cc * RO * PE, 1, PE, RO * PE, S, PE, RO, Cc, 5, 5, plan["hole_xy"].data_ptr(), plan["n_items"],
+                         plan["item_geom"].data_ptr(), plan["item_first"].data_ptr(), plan["item_count"].data_ptr(),
+                         plan["src_start"].data_ptr(), plan["src_off"].data_ptr(), plan["max_src"], plan["w_start"].data_ptr(),
+                         Wd.data_ptr(), Wd.shape[1], 0 if torch.cuda.current_stream().cuda_stream == 0 else torch.cuda.current_stream().cuda_stream)
+
+    t_gr = timed(run_grappa, 5)
+    holes = int(plan["hole_xy"].numel())
+    flops = 0.0
+    for gi, gidx in enumerate(plan["geoms"]):
+        n_s = int(kv["patches"][gidx][..., 0].sum())
+        flops += 8.0 * Cc * n_s * Cc * len(kv["holes_x"][gidx])
+    flops *= S
+    sm_clock = 1.965e9
+    fp32_peak = 148 * 128 * 2 * sm_clock
+    out["grappa_apply"] = {"workload": f"GRAPPA 5x5 weight application, {S} slices x {Cc} coils x {RO} x {PE} (R=2 + 24 ACS lines), one launch, "
+                                       "random weights (timing only; parity: tests/test_grappa_sense.py)",
+                           "ms": t_gr, "holes_per_slice": holes, "geometries": len(plan["geoms"]), "gflop": flops / 1e9,
+                           "tflops": flops / (t_gr * 1e-3) / 1e12, "fp32_peak_tflops": fp32_peak / 1e12,
+                           "frac_of_fp32_peak": flops / (t_gr * 1e-3) / fp32_peak, "slices_per_s": S / (t_gr * 1e-3)}
     return out
+
+
+def cabi_library():
+    from mri_acl_imagesegmentation_adsp_b200.adapters import recon_cabi
+    return recon_cabi.library()
 
 
 def main() -> None:

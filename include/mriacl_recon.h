@@ -196,6 +196,33 @@ int mriacl_clip_resize_zscore_f32(const float* img, const uint8_t* body_mask, fl
                                   uint8_t* out_mask, float* clip_lo_hi, float* stats, int B, int H, int W, int out_h,
                                   int out_w, float pmin, float pmax, void* cuda_stream);
 
+/* GRAPPA weight application, in place, for n_slices slices that share one kernel-geometry plan (one Grappa object of
+ * the reference) and carry their own weights.  Replaces Grappa.apply_weights,
+ * ZIP!/fastmri_prostate/reconstruction/grappa.py:173-222 (called per (average, slice) by prostate_t2_recon.py:52-63 and
+ * dwi/prostate_dwi_recon.py:92-97).  For every hole (x, y) of geometry g: k[x, y, :] += W_g @ S, S = the sampled
+ * neighbours of the kx x ky window in window-position-major, coil-minor order.
+ *   kspace_inout  complex64, element (slice, x, y, c) at slice*slice_stride + x*sx + y*sy + c*sc (complex elements):
+ *                 any axis order of the file works without a transpose.  Only holes are written; the sources of a hole are
+ *                 sampled positions, which are never written, so in place is race-free.
+ *   The plan tables are DEVICE int32 / int64 arrays built by the host mirror (prostate/grappa.py):
+ *   hole_xy [n_holes] = x*Y + y grouped by geometry; item_* [n_items]: geometry, first hole and hole count (<= 256) of each
+ *   work item; geom_src_start [n_geom+1] into src_off; src_off = (di + kx/2)*8 + (dj + ky/2) of every sampled window
+ *   position; max_sources = largest sources-per-geometry; geom_w_start [n_geom] = offset of W_g (C x n_s*C, row-major)
+ *   inside one slice's weight block; weights_c64 [n_slices][weights_per_slice].   C <= 16, kernel at most 7 x 7. */
+int mriacl_grappa_apply_c64(void* kspace_inout, long long slice_stride, long long sx, long long sy, long long sc,
+                            int n_slices, int X, int Y, int C, int kx, int ky,
+                            const int* hole_xy, int n_items, const int* item_geom, const int* item_first,
+                            const int* item_count, const int* geom_src_start, const int* src_off, int max_sources,
+                            const long long* geom_w_start, const void* weights_c64, long long weights_per_slice,
+                            void* cuda_stream);
+
+/* SENSE-style coil combine of [B, C, n] complex64 images with sensitivity maps [B, C, n] (shared_sens != 0: [1, C, n]):
+ * sum_c img_c * conj(sens_c); magnitude != 0: float32 |.| [B, n] (np.abs(np.sum(img * sens.conj(), axis=1)),
+ * ZIP!/fastmri_prostate/reconstruction/dwi/prostate_dwi_recon.py:106-109), else the complex sum [B, n]
+ * (sens_reduce, ZIP!/DL_reconstruction/models/varnet.py:199-203). */
+int mriacl_sense_combine(const void* img_c64, const void* sens_c64, void* out, int B, int C, size_t n, int shared_sens,
+                         int magnitude, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

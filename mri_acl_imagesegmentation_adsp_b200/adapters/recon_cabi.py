@@ -54,6 +54,9 @@ SIGNATURES = {
     "mriacl_resize_bilinear_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mriacl_resize_mask_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mriacl_zscore_preview_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _sz, _vp]),
+    "mriacl_grappa_apply_c64": (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i,
+                                     _vp, _vp, _ll, _vp]),
+    "mriacl_sense_combine": (_i, [_vp, _vp, _vp, _i, _i, _sz, _i, _i, _vp]),
     "mriacl_clip_resize_zscore_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp]),
 }
 
@@ -176,6 +179,19 @@ class ReconLibrary:
         self._check(self._lib.mriacl_clip_resize_zscore_f32(img_ptr, mask_ptr or None, z_ptr, p01_ptr or None,
                                                             out_mask_ptr or None, lo_hi_ptr, stats_ptr or None,
                                                             b, h, w, oh, ow, pmin, pmax, stream or None))
+
+
+    def grappa_apply(self, k_ptr, slice_stride, sx, sy, sc, n_slices, x, y, c, kx, ky, hole_xy_ptr, n_items, item_geom_ptr,
+                     item_first_ptr, item_count_ptr, geom_src_start_ptr, src_off_ptr, max_sources, geom_w_start_ptr,
+                     weights_ptr, weights_per_slice, stream=0) -> None:
+        self._check(self._lib.mriacl_grappa_apply_c64(k_ptr, slice_stride, sx, sy, sc, n_slices, x, y, c, kx, ky, hole_xy_ptr,
+                                                      n_items, item_geom_ptr, item_first_ptr, item_count_ptr,
+                                                      geom_src_start_ptr, src_off_ptr, max_sources, geom_w_start_ptr,
+                                                      weights_ptr, weights_per_slice, stream or None))
+
+    def sense_combine(self, img_ptr, sens_ptr, out_ptr, b, c, n, shared_sens: bool, magnitude: bool, stream=0) -> None:
+        self._check(self._lib.mriacl_sense_combine(img_ptr, sens_ptr, out_ptr, b, c, n, 1 if shared_sens else 0,
+                                                   1 if magnitude else 0, stream or None))
 
 
 _lock = threading.Lock()

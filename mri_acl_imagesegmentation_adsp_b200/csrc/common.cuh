@@ -54,9 +54,9 @@ template <bool INV> __device__ __forceinline__ cf mul_i(cf a) {
 // a * b for two variable operands: (a.x, a.x) * b + (a.y, a.y) * (i b)
 // (ptxas folds the swap-and-negate into the FIRST multiplicand only, so the rotated operand goes first)
 __device__ __forceinline__ cf cmul(cf a, cf b) { return pk_fma(mul_i<true>(b), bc(a.y), pk_mul(b, bc(a.x))); }
-// a * conj(b)
+// a * conj(b) = a.x (b.x, -b.y) + a.y (b.y, b.x)
 __device__ __forceinline__ cf cmulc(cf a, cf b) {
-  return pk_fma(mul_i<false>(b), bc(-a.y), pk_mul(make_float2(b.x, -b.y), bc(a.x)));
+  return pk_fma(make_float2(b.y, b.x), bc(a.y), pk_mul(make_float2(b.x, -b.y), bc(a.x)));
 }
 // a * (c + i s) for constants c, s (immediates after inlining): c a + s (i a)
 __device__ __forceinline__ cf cmul_k(cf a, float c, float s) { return pk_fma(mul_i<true>(a), bc(s), pk_mul(a, bc(c))); }

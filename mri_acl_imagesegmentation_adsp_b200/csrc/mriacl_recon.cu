@@ -23,6 +23,7 @@
 #include "rowpass_generic.cuh"
 #ifndef MRIACL_EMU
 #include "post_kernels.cuh"
+#include "grappa_kernels.cuh"
 #endif
 #ifdef MRIACL_EXPERIMENTAL
 // schedules that were built, measured and found slower than `sequential`: kept as negative
@@ -1277,6 +1278,68 @@ int mriacl_clip_resize_zscore_f32(const float* img, const uint8_t* body_mask, fl
   // 3. statistics inside the resized mask, z-score in place, preview
   ZscoreParams zp{out_z, body_mask ? out_mask : nullptr, out_z, out_01, stats, (long long)out_h * out_w};
   MRIACL_LAUNCH(zscore_preview_kernel, B, POST_T, 0, st, zp);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+#endif
+}
+
+// ---- GRAPPA weight application and the SENSE-style combine ----
+int mriacl_grappa_apply_c64(void* kspace_inout, long long slice_stride, long long sx, long long sy, long long sc,
+                            int n_slices, int X, int Y, int C, int kx, int ky,
+                            const int* hole_xy, int n_items, const int* item_geom, const int* item_first,
+                            const int* item_count, const int* geom_src_start, const int* src_off, int max_sources,
+                            const long long* geom_w_start, const void* weights_c64, long long weights_per_slice,
+                            void* cuda_stream) {
+  MRIACL_POST_GUARD;
+#ifndef MRIACL_EMU
+  if (n_slices < 0 || X < 1 || Y < 1 || C < 1 || n_items < 0) return fail(MRIACL_ERR_INVALID, "bad dims");
+  if (kx < 1 || ky < 1 || kx > 7 || ky > 7 || !(kx & 1) || !(ky & 1)) return fail(MRIACL_ERR_UNSUPPORTED, "kernel size must be odd and at most 7 x 7, got %d x %d", kx, ky);
+  if (max_sources < 0 || max_sources > kx * ky) return fail(MRIACL_ERR_INVALID, "max_sources %d outside 0..%d", max_sources, kx * ky);
+  if (n_slices == 0 || n_items == 0) return MRIACL_OK;
+  if (!kspace_inout || !hole_xy || !item_geom || !item_first || !item_count || !geom_src_start || !src_off || !geom_w_start || !weights_c64)
+    return fail(MRIACL_ERR_INVALID, "null pointer");
+  const size_t smem = (size_t)max_sources * C * GR_OUT * sizeof(cf);
+  if (smem > (size_t)SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "weight tile of %zu B does not fit shared memory (%d sources x %d coils)", smem, max_sources, C);
+  static std::mutex mu;
+  static std::map<int, size_t> allowed;             // per device: largest opt-in so far
+  const int dev = rt_device();
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (allowed[dev] < smem) {
+      if (rt_allow_smem((const void*)grappa_apply_kernel, (int)smem)) return fail(MRIACL_ERR_CUDA, "cudaFuncSetAttribute failed: %s", rt_last_error_string());
+      allowed[dev] = smem;
+    }
+  }
+  GrappaParams p{};
+  p.ksp = (const cf*)kspace_inout; p.out = (cf*)kspace_inout; p.ss = slice_stride; p.sx = sx; p.sy = sy; p.sc = sc; p.nc = C;
+  p.hole_xy = hole_xy; p.Y = Y; p.item_geom = item_geom; p.item_first = item_first; p.item_count = item_count;
+  p.geom_src_start = geom_src_start; p.src_off = src_off; p.geom_w_start = geom_w_start;
+  p.weights = (const cf*)weights_c64; p.w_per_slice = weights_per_slice; p.kx2 = kx / 2; p.ky2 = ky / 2;
+  const int groups = (C + GR_OUT - 1) / GR_OUT;
+  if (groups > 1) return fail(MRIACL_ERR_UNSUPPORTED, "more than %d coils: in-place application needs all outputs of a hole in one pass", GR_OUT);
+  for (int s0 = 0; s0 < n_slices; s0 += 65535) {     // grid.y limit
+    const int ns = std::min(65535, n_slices - s0);
+    GrappaParams q = p;
+    q.ksp = p.ksp + (long long)s0 * slice_stride; q.out = p.out + (long long)s0 * slice_stride;
+    q.weights = p.weights + (long long)s0 * weights_per_slice;
+    dim3 grid((unsigned)n_items, (unsigned)ns, 1);
+    grappa_apply_kernel<<<grid, GR_T, smem, (rt_stream_t)cuda_stream>>>(q);
+    launch_counter()++;
+  }
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+#endif
+}
+
+int mriacl_sense_combine(const void* img_c64, const void* sens_c64, void* out, int B, int C, size_t n, int shared_sens,
+                         int magnitude, void* cuda_stream) {
+  MRIACL_POST_GUARD;
+#ifndef MRIACL_EMU
+  if (B < 0 || C < 1 || n < 1) return fail(MRIACL_ERR_INVALID, "bad dims");
+  if (B == 0) return MRIACL_OK;
+  if (!img_c64 || !sens_c64 || !out) return fail(MRIACL_ERR_INVALID, "null pointer");
+  SenseParams p{(const cf*)img_c64, (const cf*)sens_c64, out, (long long)n, B, C, shared_sens ? 1 : 0, magnitude ? 1 : 0};
+  MRIACL_LAUNCH(sense_combine_kernel, grid_for((long long)B * (long long)n, 256), 256, 0, (rt_stream_t)cuda_stream, p);
   if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
   return MRIACL_OK;
 #endif

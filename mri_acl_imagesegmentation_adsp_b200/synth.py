@@ -138,3 +138,25 @@ def post_case_inputs(name: str):
                 mk = np.zeros(shape, np.uint8)
             return img, mk, out
     raise KeyError(name)
+
+
+#: GRAPPA golden cases: (name, PE, coils, RO, acceleration, ACS lines, calibration PE lines, seed); data layout (PE, coil, RO)
+#: with coil_axis = 1, the layout the T2 / DWI chains hand to Grappa (prostate_t2_recon.py:34)
+GRAPPA_CASES = (("small_r2", 24, 4, 20, 2, 6, 12, 601), ("medium_r3", 90, 8, 64, 3, 12, 24, 602))
+
+
+def grappa_case_inputs(name: str):
+    """(undersampled k-space (PE, C, RO) c64 with exact zeros on the skipped lines, calibration (PE_cal, C, RO) c64)."""
+    for nm, pe, nc, ro, acc, acs, cal, seed in GRAPPA_CASES:
+        if nm == name:
+            k = gaussian_kspace((pe, nc, ro), seed)
+            keep = np.zeros(pe, dtype=bool)
+            keep[::acc] = True
+            lo = (pe - acs) // 2
+            keep[lo:lo + acs] = True
+            k[~keep] = 0
+            # calibration with structure (a smooth kernel correlates neighbours, so the fit is well conditioned)
+            c = gaussian_kspace((cal + 4, nc, ro + 4), seed + 1)
+            calib = (c[2:-2, :, 2:-2] + 0.5 * (c[1:-3, :, 2:-2] + c[3:-1, :, 2:-2]) + 0.5 * (c[2:-2, :, 1:-3] + c[2:-2, :, 3:-1])).astype(np.complex64)
+            return k, calib
+    raise KeyError(name)

@@ -467,6 +467,73 @@ def post_chain(img: np.ndarray, body_mask: Optional[np.ndarray], out_hw: Tuple[i
     return zscore_in_mask(img_r, mk_r), preview_01(img_r, mk_r), mk_r, (np.float32(lo), np.float32(hi))
 
 
+# --------------------------------------------------------------------------- GRAPPA / SENSE
+def grappa_geometries(kspace: np.ndarray, kernel_size: Tuple[int, int] = (5, 5), coil_axis: int = -1):
+    """``Grappa.get_kernel_geometries`` (``ZIP!/fastmri_prostate/reconstruction/grappa.py:15-102``) restated literally:
+    pad, mask = |coil 0| > 0, all kx x ky windows, ``np.unique(axis=0)``, keep geometries with a hole at the centre that
+    are not empty.  Returns (padded k-space (X+2kx2, Y+2ky2, C), patches (n, kx, ky) bool, patch_indices, holes_x, holes_y)."""
+    k = np.moveaxis(kspace, coil_axis, -1)
+    kx, ky = kernel_size
+    kx2, ky2 = int(kx / 2), int(ky / 2)
+    k = np.pad(k, ((kx2, kx2), (ky2, ky2), (0, 0)), mode="constant")
+    mask = np.ascontiguousarray(np.abs(k[..., 0]) > 0)
+    P = np.lib.stride_tricks.sliding_window_view(mask, (kx, ky))
+    psh = P.shape[:2]
+    P, iidx = np.unique(P.reshape((-1, kx, ky)), return_inverse=True, axis=0)
+    iidx = np.asarray(iidx).reshape(-1)
+    valid = np.argwhere(~P[:, kx2, ky2]).squeeze()
+    invalid = np.argwhere(np.all(P == 0, axis=(1, 2)))
+    valid = np.atleast_1d(np.setdiff1d(valid, invalid, assume_unique=True))
+    hx, hy = {}, {}
+    for ii in valid:
+        x, y = np.unravel_index(np.flatnonzero(iidx == ii), psh)
+        hx[ii], hy[ii] = x + kx2, y + ky2
+    return k, P, valid, hx, hy
+
+
+def grappa_weights(calib: np.ndarray, P: np.ndarray, patch_indices, kernel_size=(5, 5), coil_axis: int = -1, lamda: float = 0.01):
+    """``Grappa.compute_weights`` (``grappa.py:104-171``)."""
+    calib = np.moveaxis(calib, coil_axis, -1)
+    kx, ky = kernel_size
+    kx2, ky2 = int(kx / 2), int(ky / 2)
+    nc = calib.shape[-1]
+    calib = np.pad(calib, ((kx2, kx2), (ky2, ky2), (0, 0)), mode="constant")
+    A = np.lib.stride_tricks.sliding_window_view(calib, (kx, ky, nc)).reshape((-1, kx, ky, nc))
+    Pc = np.tile(P[..., None], (1, 1, 1, nc))
+    out = {}
+    for ii in patch_indices:
+        S = A[:, Pc[ii, ...]]
+        T = A[:, kx2, ky2, :]
+        ShS = S.conj().T @ S
+        ShT = S.conj().T @ T
+        lamda0 = lamda * np.linalg.norm(ShS) / ShS.shape[0]
+        out[ii] = np.linalg.solve(ShS + lamda0 * np.eye(ShS.shape[0]), ShT).T
+    return out
+
+
+def grappa_apply(kspace: np.ndarray, weights, kernel_size=(5, 5), coil_axis: int = -1) -> np.ndarray:
+    """``Grappa.apply_weights`` (``grappa.py:173-222``) for the geometries of ``kspace`` itself: every hole of geometry ii gets
+    ``weights[ii] @ S`` (S = sampled window entries, window-position major / coil minor); result = recon + kspace, in the
+    input's dtype.  Vectorised over the holes of one geometry; same arithmetic (complex128 weights times complex64 sources)."""
+    kx, ky = kernel_size
+    kx2, ky2 = int(kx / 2), int(ky / 2)
+    k, P, valid, hx, hy = grappa_geometries(kspace, kernel_size, coil_axis)
+    recon = np.zeros(k.shape, dtype=k.dtype)
+    for ii in valid:
+        pi, pj = np.nonzero(P[ii])
+        xs, ys = hx[ii], hy[ii]
+        S = k[xs[:, None] + pi[None, :] - kx2, ys[:, None] + pj[None, :] - ky2, :]        # (holes, n_s, C)
+        recon[xs, ys, :] = S.reshape(len(xs), -1) @ np.asarray(weights[ii]).T
+    return np.moveaxis((recon + k)[kx2:-kx2, ky2:-ky2, :], -1, coil_axis)
+
+
+def sense_combine(img: np.ndarray, sens: np.ndarray, magnitude: bool = True) -> np.ndarray:
+    """``np.sum(img * sens.conj(), axis=1)`` (+ ``np.abs``): ``ZIP!/fastmri_prostate/reconstruction/dwi/prostate_dwi_recon.py:106-109``;
+    ``sens_reduce`` of ``ZIP!/DL_reconstruction/models/varnet.py:199-203`` is the same sum on real views (coil axis 1)."""
+    out = np.sum(img * sens.conj(), axis=1)
+    return np.abs(out) if magnitude else out
+
+
 def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
     """||a-b||_2 / ||b||_2 in float64 -- the parity metric of BASELINE.json."""
     a = np.asarray(a)

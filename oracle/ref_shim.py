@@ -118,13 +118,18 @@ def prostate():
         root = _zip_root()
         _stub("h5py")
         _stub("skimage")
+        # skimage.util.view_as_windows(arr, shape) with the default step 1 IS numpy's sliding_window_view: the one
+        # third-party function grappa.py needs is supplied by its numpy equivalent, nothing of the reference is changed
+        import numpy as _np
         _stub("skimage.util", view_as_windows=None)
+        sys.modules["skimage.util"].view_as_windows = lambda arr, window_shape, step=1: _np.lib.stride_tricks.sliding_window_view(arr, window_shape)
         if root not in sys.path:
             sys.path.insert(0, root)
         ns = types.SimpleNamespace()
         ns.utils = importlib.import_module("fastmri_prostate.reconstruction.utils")
         ns.mri_data = importlib.import_module("fastmri_prostate.data.mri_data")
         ns.t2 = importlib.import_module("fastmri_prostate.reconstruction.t2.prostate_t2_recon")
+        ns.grappa = importlib.import_module("fastmri_prostate.reconstruction.grappa")
         _cache["prostate"] = ns
     return _cache["prostate"]
 
