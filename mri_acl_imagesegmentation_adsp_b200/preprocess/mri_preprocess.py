@@ -175,13 +175,41 @@ class MRIKneePreprocessor:
         if s0 >= s1:
             s0, s1 = 0, ns
         recs = list(records[s0:s1])
-        ks = [self._record_kspace(r) for r in recs]
-        shapes = {tuple(k.shape) for k in ks}
-        if len(shapes) != 1:
-            raise ValueError(f"records of one volume must share a shape, got {sorted(shapes)}")
-        vol = np.stack([np.asarray(k, dtype=np.complex64) for k in ks]) if isinstance(ks[0], np.ndarray) else torch.stack(list(ks))
-        mv = D.to_device_complex(vol)
-        imgs = _ifft2c_abs_batch(mv.tensor)
+        # source precedence of _normalize_record_input (:262-296): image -> target / reconstruction* -> kspace
+        dev = D.require_cuda()
+        sources, planes, k_idx, ks = [], [None] * len(recs), [], []
+        for i, r in enumerate(recs):
+            if r.get("image", None) is not None:
+                planes[i] = self._ensure_2d(np.squeeze(np.asarray(r["image"])).astype(np.float32, copy=False), "image")
+                sources.append("image")
+                continue
+            for key in ("target", "reconstruction", "reconstruction_rss", "reconstruction_esc"):
+                if r.get(key, None) is not None:
+                    planes[i] = self._ensure_2d(np.squeeze(np.asarray(r[key])).astype(np.float32, copy=False), key)
+                    sources.append("target")
+                    break
+            else:
+                ks.append(self._record_kspace(r))
+                k_idx.append(i)
+                sources.append("kspace")
+        if ks:
+            shapes = {tuple(k.shape) for k in ks}
+            if len(shapes) != 1:
+                raise ValueError(f"records of one volume must share a shape, got {sorted(shapes)}")
+            vol = np.stack([np.asarray(k, dtype=np.complex64) for k in ks]) if isinstance(ks[0], np.ndarray) else torch.stack(list(ks))
+            rec_imgs = _ifft2c_abs_batch(D.to_device_complex(vol).tensor)       # ONE device call for all k-space records
+        if len(ks) == len(recs):
+            imgs = rec_imgs
+        else:
+            shapes = {tuple(p.shape) for p in planes if p is not None} | ({tuple(rec_imgs.shape[1:])} if ks else set())
+            if len(shapes) != 1:
+                raise ValueError(f"records of one volume must share a shape, got {sorted(shapes)}")
+            imgs = torch.empty((len(recs),) + next(iter(shapes)), dtype=torch.float32, device=dev)
+            for j, i in enumerate(k_idx):
+                imgs[i] = rec_imgs[j]
+            for i, p in enumerate(planes):
+                if p is not None:
+                    imgs[i] = torch.from_numpy(np.ascontiguousarray(p)).to(dev)
         masks = None
         if all(r.get("body_mask", None) is not None for r in recs):
             masks = torch.from_numpy(np.stack([np.asarray(r["body_mask"]) for r in recs]))
@@ -192,7 +220,7 @@ class MRIKneePreprocessor:
         metas = [r.get("meta", {}) for r in recs]
         return {"tensor": out["img_z"][:, None].cpu(), "preview": out["img_01"].cpu().numpy(),
                 "mask": out["mask"].cpu().numpy(), "indices": [m.get("slice_idx", s0 + i) for i, m in enumerate(metas)],
-                "sources": ["kspace"] * len(recs), "metas": metas}
+                "sources": sources, "metas": metas}
 
     @staticmethod
     def _record_kspace(record: Dict[str, Any]) -> np.ndarray:
