@@ -739,7 +739,7 @@ def extra_configs_leg(torch, dev, k, mask, peak) -> dict:
     kv = gr.kernel_var_dict
     wd = {int(i): (0.05 * (rngw.standard_normal((Cc, int(kv["patches"][i].sum()))) +
                            1j * rngw.standard_normal((Cc, int(kv["patches"][i].sum()))))).astype(np.complex64) for i in kv["patch_indices"]}
-    plan = gr._device_plan(dev)
+    plan = gr._device_plan(dev, lanes_along_x=True)      # PE (x) is the contiguous axis of the file layout
     Wd = gr._pack_weights([wd] * S, plan)
     lib = cabi_library()
 

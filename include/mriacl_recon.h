@@ -196,6 +196,13 @@ int mriacl_clip_resize_zscore_f32(const float* img, const uint8_t* body_mask, fl
                                   uint8_t* out_mask, float* clip_lo_hi, float* stats, int B, int H, int W, int out_h,
                                   int out_w, float pmin, float pmax, void* cuda_stream);
 
+/* The network-input epilogue of the consumer (KneeNPZ2DSlices.__getitem__, REF/src/dataio/datasets.py:90-95,128-131) for a
+ * whole volume: out[s, d] = in[clamp(s + d - k/2, 0, S-1)] (2.5-D stack of k neighbouring slices, k odd), or with repeat != 0
+ * out[s, d] = in[s] (one channel repeated for ImageNet encoders); mean_dev / std_dev: DEVICE float32 [k] per output channel,
+ * applied as (x - mean) / std, or both NULL.  in [S, n], out [S, k, n]. */
+int mriacl_stack25d_f32(const float* in, float* out, int S, size_t n, int k, int repeat, const float* mean_dev,
+                        const float* std_dev, void* cuda_stream);
+
 /* GRAPPA weight application, in place, for n_slices slices that share one kernel-geometry plan (one Grappa object of
  * the reference) and carry their own weights.  Replaces Grappa.apply_weights,
  * ZIP!/fastmri_prostate/reconstruction/grappa.py:173-222 (called per (average, slice) by prostate_t2_recon.py:52-63 and

@@ -56,6 +56,7 @@ SIGNATURES = {
     "mriacl_zscore_preview_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _sz, _vp]),
     "mriacl_grappa_apply_c64": (_i, [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i,
                                      _vp, _vp, _ll, _vp]),
+    "mriacl_stack25d_f32": (_i, [_vp, _vp, _i, _sz, _i, _i, _vp, _vp, _vp]),
     "mriacl_sense_combine": (_i, [_vp, _vp, _vp, _i, _i, _sz, _i, _i, _vp]),
     "mriacl_clip_resize_zscore_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp]),
 }
@@ -188,6 +189,10 @@ class ReconLibrary:
                                                       n_items, item_geom_ptr, item_first_ptr, item_count_ptr,
                                                       geom_src_start_ptr, src_off_ptr, max_sources, geom_w_start_ptr,
                                                       weights_ptr, weights_per_slice, stream or None))
+
+    def stack25d(self, in_ptr, out_ptr, s, n, k, repeat: bool, mean_ptr, std_ptr, stream=0) -> None:
+        self._check(self._lib.mriacl_stack25d_f32(in_ptr, out_ptr, s, n, k, 1 if repeat else 0, mean_ptr or None, std_ptr or None,
+                                                  stream or None))
 
     def sense_combine(self, img_ptr, sens_ptr, out_ptr, b, c, n, shared_sens: bool, magnitude: bool, stream=0) -> None:
         self._check(self._lib.mriacl_sense_combine(img_ptr, sens_ptr, out_ptr, b, c, n, 1 if shared_sens else 0,

@@ -12,8 +12,10 @@
 //     128-bit broadcast loads;
 //   * every thread owns TWO holes (tid and tid + 128 of the item) and all 16 output coils of both: 64 accumulator
 //     registers, each weight load feeds two complex FMAs, each source load sixteen (FFMA2 : LDS = 8 : 1);
-//   * source values are gathered straight from global memory through L1 (holes of one geometry are sorted by (x, y), so
-//     the 32 lanes of a warp read 32 neighbouring readout positions and the 25 window offsets re-hit the same lines).
+//   * source values are gathered straight from global memory through L1: the host plan orders the holes of a geometry so
+//     that the 32 lanes of a warp are neighbours along the axis with the SMALLER memory stride -- a warp's load then falls
+//     into ~4 cache lines instead of 32 (measured: 3.3 ms -> 1.9 ms; with lanes along the strided axis the L1 hit rate is
+//     2 % and 67 % of the stall samples are the scoreboard of these loads).
 // Coils beyond 16 outputs run as further output groups (grid.z); any coil count works for the sources.
 #pragma once
 #include "common.cuh"

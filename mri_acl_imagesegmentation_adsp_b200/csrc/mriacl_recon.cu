@@ -1283,6 +1283,21 @@ int mriacl_clip_resize_zscore_f32(const float* img, const uint8_t* body_mask, fl
 #endif
 }
 
+int mriacl_stack25d_f32(const float* in, float* out, int S, size_t n, int k, int repeat, const float* mean_dev,
+                        const float* std_dev, void* cuda_stream) {
+  MRIACL_POST_GUARD;
+#ifndef MRIACL_EMU
+  if (S < 0 || n < 1 || k < 1 || (k % 2 == 0 && !repeat)) return fail(MRIACL_ERR_INVALID, "bad dims S=%d n=%zu k=%d (k must be odd)", S, n, k);
+  if ((mean_dev == nullptr) != (std_dev == nullptr)) return fail(MRIACL_ERR_INVALID, "mean and std go together");
+  if (S == 0) return MRIACL_OK;
+  if (!in || !out) return fail(MRIACL_ERR_INVALID, "null pointer");
+  StackParams p{in, out, mean_dev, std_dev, (long long)n, S, k, repeat ? 1 : 0};
+  MRIACL_LAUNCH(stack25d_kernel, grid_for((long long)S * k * (long long)n, 256), 256, 0, (rt_stream_t)cuda_stream, p);
+  if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
+  return MRIACL_OK;
+#endif
+}
+
 // ---- GRAPPA weight application and the SENSE-style combine ----
 int mriacl_grappa_apply_c64(void* kspace_inout, long long slice_stride, long long sx, long long sy, long long sc,
                             int n_slices, int X, int Y, int C, int kx, int ky,

@@ -236,4 +236,30 @@ __global__ void __launch_bounds__(POST_T) zscore_preview_kernel(ZscoreParams p) 
   }
 }
 
+// 2.5-D stacking and the encoder's input normalisation (REF/src/dataio/datasets.py:90-95,128-131): channel d of output slice s
+// is input slice clamp(s + d - k/2, 0, S-1); with `repeat` a single channel is repeated to `k` channels instead (ImageNet
+// encoders); mean / std (per output channel) give (x - mean) / std, unfused like torch.
+struct StackParams {
+  const float* in;     // [S][n]
+  float* out;          // [S][k][n]
+  const float* mean;   // [k] or nullptr
+  const float* stdv;   // [k] or nullptr
+  long long n;
+  int S, k, repeat;
+};
+
+__global__ void __launch_bounds__(256) stack25d_kernel(StackParams p) {
+  const long long total = (long long)p.S * p.k * p.n;
+  const int half = p.k / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % p.n;
+    const long long t = i / p.n;
+    const int d = (int)(t % p.k), s = (int)(t / p.k);
+    const int src = p.repeat ? s : min(max(s + d - half, 0), p.S - 1);
+    float v = p.in[(long long)src * p.n + r];
+    if (p.mean) v = __fdiv_rn(__fsub_rn(v, p.mean[d]), p.stdv[d]);
+    p.out[i] = v;
+  }
+}
+
 }  // namespace mriacl

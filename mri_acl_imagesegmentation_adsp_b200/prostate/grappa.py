@@ -105,10 +105,13 @@ class Grappa:
         return weights
 
     # ------------------------------------------------------------------------------------------- apply (device)
-    def _device_plan(self, dev: torch.device):
+    def _device_plan(self, dev: torch.device, lanes_along_x: bool = False):
         """Kernel tables of this object's geometries: holes grouped by geometry (unpadded coordinates), work items of at most
-        256 holes, window offsets of the sampled positions, and where each geometry's weights sit in a slice's block."""
-        if self._plan is not None and self._plan["dev"] == dev:
+        256 holes, window offsets of the sampled positions, and where each geometry's weights sit in a slice's block.
+        ``lanes_along_x``: order the holes of a geometry y-major so that consecutive holes (the lanes of a warp) are neighbours
+        along the FIRST kernel axis -- chosen when that axis has the smaller memory stride, so a warp's source loads fall
+        into a few cache lines instead of 32."""
+        if self._plan is not None and self._plan["dev"] == dev and self._plan["lanes_along_x"] == lanes_along_x:
             return self._plan
         kv = self.kernel_var_dict
         kx, ky = self.kernel_size
@@ -127,7 +130,11 @@ class Grappa:
             max_src = max(max_src, len(ii))
             w_start.append(w_total)
             w_total += nc * len(ii) * nc
-            xy = (kv["holes_x"][g] - kx2).astype(np.int64) * Y + (kv["holes_y"][g] - ky2)
+            hx, hy = (kv["holes_x"][g] - kx2).astype(np.int64), (kv["holes_y"][g] - ky2).astype(np.int64)
+            if lanes_along_x:
+                order = np.lexsort((hx, hy))                      # y-major: consecutive entries step along x
+                hx, hy = hx[order], hy[order]
+            xy = hx * Y + hy
             hole_xy.append(xy)
             for f in range(0, len(xy), _ITEM_HOLES):
                 item_geom.append(gi)
@@ -135,7 +142,7 @@ class Grappa:
                 item_count.append(min(_ITEM_HOLES, len(xy) - f))
             n_holes += len(xy)
         i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32), device=dev)
-        self._plan = {"dev": dev, "X": X, "Y": Y, "nc": nc, "geoms": geoms, "n_items": len(item_geom), "max_src": max_src,
+        self._plan = {"dev": dev, "lanes_along_x": lanes_along_x, "X": X, "Y": Y, "nc": nc, "geoms": geoms, "n_items": len(item_geom), "max_src": max_src,
                       "w_total": w_total, "w_start_host": w_start,
                       "hole_xy": i32(np.concatenate(hole_xy) if hole_xy else np.zeros(0)), "item_geom": i32(item_geom),
                       "item_first": i32(item_first), "item_count": i32(item_count), "src_start": i32(src_start),
@@ -160,9 +167,9 @@ class Grappa:
         k = mv.tensor.clone() if mv.tensor.data_ptr() == getattr(kspace, "data_ptr", lambda: 0)() else mv.tensor
         if k.ndim != 4 or len(weights_list) != k.shape[0] or sorted(axes) != [0, 1, 2]:
             raise ValueError("kspace must be (S, d0, d1, d2) with one weights dict per slice and axes a permutation of (0, 1, 2)")
-        plan = self._device_plan(k.device)
         dims = k.shape[1:]
         strides = (dims[1] * dims[2], dims[2], 1)
+        plan = self._device_plan(k.device, lanes_along_x=strides[axes[0]] < strides[axes[1]])
         if (dims[axes[0]], dims[axes[1]], dims[axes[2]]) != (plan["X"], plan["Y"], plan["nc"]):
             raise ValueError(f"k-space {tuple(dims)} with axes {axes} does not match the geometry plan "
                              f"({plan['X']}, {plan['Y']}, {plan['nc']})")

@@ -139,3 +139,42 @@ def recon_to_unet_input(kspace: Any, mask: Any = None, crop: Tuple[int, int] = (
     (``src/dataio/datasets.py:90-95,133``)."""
     img, _, _ = zero_filled_rss(kspace, mask, crop, "instance", eps, **kw)
     return img[:, None] if isinstance(img, torch.Tensor) else img[:, None, :, :]
+
+
+#: smp.encoders.get_preprocessing_params("resnet34") with ImageNet weights (REF/src/dataio/datasets.py:69-73)
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def stack_2p5d(volume: Any, k: int = 1, imagenet_norm: bool = False, mean: Optional[Sequence[float]] = None,
+               std: Optional[Sequence[float]] = None) -> Any:
+    """The network-input epilogue of ``KneeNPZ2DSlices.__getitem__`` (``src/dataio/datasets.py:90-95,128-131``) for a whole
+    volume at once: ``(S,1,H,W)`` or ``(S,H,W)`` float32 -> ``(S,k,H,W)`` where channel ``d`` of slice ``s`` is slice
+    ``clamp(s + d - k//2, 0, S-1)``; with ``imagenet_norm`` a single channel is repeated to three and every channel is
+    normalised ``(x - mean) / std`` (defaults: the ImageNet parameters of smp's resnet encoders).  Pure indexing is bit-exact."""
+    mv = D.to_device_real(volume, name="volume")
+    x = mv.tensor
+    if x.ndim == 4:
+        if x.shape[1] != 1:
+            raise ValueError(f"volume must be (S,1,H,W) or (S,H,W), got {tuple(x.shape)}")
+        x = x[:, 0]
+    if x.ndim != 3:
+        raise ValueError(f"volume must be (S,1,H,W) or (S,H,W), got {tuple(volume.shape)}")
+    k = int(k)
+    if k < 1 or k % 2 == 0:
+        raise ValueError("k must be a positive odd number of slices")
+    repeat = bool(imagenet_norm and k == 1)
+    kout = 3 if repeat else k
+    S, H, W = x.shape
+    mean_t = std_t = None
+    if imagenet_norm:
+        m = tuple(IMAGENET_MEAN if mean is None else mean)
+        sd = tuple(IMAGENET_STD if std is None else std)
+        if len(m) != kout or len(sd) != kout:
+            raise ValueError(f"mean / std need {kout} entries")          # (torch would fail to broadcast the same way)
+        mean_t = torch.tensor(m, dtype=torch.float32, device=x.device)
+        std_t = torch.tensor(sd, dtype=torch.float32, device=x.device)
+    out = torch.empty((S, kout, H, W), dtype=torch.float32, device=x.device)
+    if S:
+        D.lib().stack25d(x.contiguous().data_ptr(), out.data_ptr(), S, H * W, kout, repeat, mean_t.data_ptr() if mean_t is not None else 0,
+                         std_t.data_ptr() if std_t is not None else 0, D.stream_ptr())
+    return mv.back(out)

@@ -141,3 +141,43 @@ def test_gpu_preprocess_records_contract():
         pre.preprocess_records([])
     with pytest.raises(ValueError):
         MRIKneePreprocessor(use_n4=True)
+
+
+def _dataset_getitem_inputs(vol, k, imagenet):
+    """what KneeNPZ2DSlices.__getitem__ (REF/src/dataio/datasets.py:86-131) hands the network for every slice of one volume
+    (no augmentation), restated with the same numpy / torch calls."""
+    S = vol.shape[0]
+    mean = torch.tensor((0.485, 0.456, 0.406)).view(-1, 1, 1)
+    std = torch.tensor((0.229, 0.224, 0.225)).view(-1, 1, 1)
+    outs = []
+    for s in range(S):
+        if k == 1:
+            x = vol[s]
+        else:
+            half = k // 2
+            idxs = [min(max(s + d, 0), S - 1) for d in range(-half, half + 1)]
+            x = np.concatenate([vol[j] for j in idxs], axis=0)
+        t = torch.from_numpy(x.copy()).float()
+        if imagenet and t.shape[0] == 1:
+            t = t.repeat(3, 1, 1)
+        if imagenet:
+            t = (t - mean) / std
+        outs.append(t.contiguous())
+    return torch.stack(outs)
+
+
+@pytest.mark.gpu
+def test_gpu_stack_2p5d_matches_the_dataset_rule():
+    from mri_acl_imagesegmentation_adsp_b200.recon.cartesian import stack_2p5d
+    rng = np.random.default_rng(12)
+    vol = rng.standard_normal((7, 1, 20, 24)).astype(np.float32)
+    for k, imagenet in ((1, False), (3, False), (5, False), (1, True), (3, True)):
+        got = stack_2p5d(vol, k, imagenet_norm=imagenet)
+        want = _dataset_getitem_inputs(vol, k, imagenet).numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), (k, imagenet)          # bit-exact, normalisation included
+    dev = stack_2p5d(torch.from_numpy(vol).cuda(), 3)
+    assert dev.is_cuda and dev.shape == (7, 3, 20, 24)
+    with pytest.raises(ValueError):
+        stack_2p5d(vol, 2)
+    with pytest.raises(ValueError):
+        stack_2p5d(vol, 5, imagenet_norm=True)           # five channels against three ImageNet means
