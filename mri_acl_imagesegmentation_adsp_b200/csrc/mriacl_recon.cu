@@ -1199,6 +1199,19 @@ int mriacl_normalize_instance_f32(const float* in, float* out, float* mean_std, 
 #define MRIACL_POST_GUARD do {} while (0)
 #endif
 
+#ifndef MRIACL_EMU
+static int post_allow_smem() {          // once per device: the percentile kernel's 128 KB of lane-private histograms
+  static std::mutex mu;
+  static std::map<int, bool> done;
+  const int dev = rt_device();
+  std::lock_guard<std::mutex> lk(mu);
+  if (done[dev]) return 0;
+  if (rt_allow_smem((const void*)percentile_clip_kernel, POST_HIST_BYTES)) return 1;
+  done[dev] = true;
+  return 0;
+}
+#endif
+
 int mriacl_percentile_clip_f32(const float* in, float* out, float* lo_hi, int B, size_t n, float pmin, float pmax,
                                void* cuda_stream) {
   MRIACL_POST_GUARD;
@@ -1208,7 +1221,8 @@ int mriacl_percentile_clip_f32(const float* in, float* out, float* lo_hi, int B,
   if (B == 0) return MRIACL_OK;
   if (!in || (!out && !lo_hi)) return fail(MRIACL_ERR_INVALID, "null pointer");
   PercentileParams p{in, out, lo_hi, (long long)n, pmin, pmax};
-  MRIACL_LAUNCH(percentile_clip_kernel, B, POST_T, 0, (rt_stream_t)cuda_stream, p);
+  if (post_allow_smem()) return fail(MRIACL_ERR_CUDA, "cudaFuncSetAttribute failed: %s", rt_last_error_string());
+  MRIACL_LAUNCH(percentile_clip_kernel, B, POST_T, POST_HIST_BYTES, (rt_stream_t)cuda_stream, p);
   if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
   return MRIACL_OK;
 #endif
@@ -1267,7 +1281,8 @@ int mriacl_clip_resize_zscore_f32(const float* img, const uint8_t* body_mask, fl
   rt_stream_t st = (rt_stream_t)cuda_stream;
   // 1. exact percentiles of every full-resolution image (the clipped image itself is never materialised)
   PercentileParams pp{img, nullptr, clip_lo_hi, (long long)H * W, pmin, pmax};
-  MRIACL_LAUNCH(percentile_clip_kernel, B, POST_T, 0, st, pp);
+  if (post_allow_smem()) return fail(MRIACL_ERR_CUDA, "cudaFuncSetAttribute failed: %s", rt_last_error_string());
+  MRIACL_LAUNCH(percentile_clip_kernel, B, POST_T, POST_HIST_BYTES, st, pp);
   // 2. clip every tap, interpolate to (out_h, out_w); the mask goes through the same interpolation and a 0.5 threshold
   ResizeParams ri{img, nullptr, out_z, nullptr, clip_lo_hi, B, H, W, out_h, out_w};
   MRIACL_LAUNCH(resize_bilinear_kernel, grid_for((long long)B * out_h * out_w, 256), 256, 0, st, ri);

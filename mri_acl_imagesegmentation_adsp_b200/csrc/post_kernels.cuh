@@ -21,7 +21,8 @@
 namespace mriacl {
 
 constexpr int POST_T = 1024;          // threads of the one-CTA-per-image kernels
-constexpr int POST_COPIES = 8;        // privatised histogram copies (hot exponent bins would serialise a single one)
+constexpr int POST_HIST_BYTES = 4 * 256 * 32 * 4;   // dynamic shared memory of percentile_clip_kernel
+constexpr int POST_ILP = 4;           // 128-bit loads a thread keeps in flight per sweep iteration
 
 __device__ __forceinline__ unsigned post_key(float x) {
   const unsigned u = __float_as_uint(x);
@@ -47,12 +48,14 @@ struct PercentileParams {
 
 // one CTA per image
 __global__ void __launch_bounds__(POST_T) percentile_clip_kernel(PercentileParams p) {
-  __shared__ unsigned hist[4][POST_COPIES][256];
+  MRIACL_DYN_SMEM(unsigned, hist);          // [4 ranks][256 bins][32 lanes]: a lane owns its column, so the lanes of a warp never
+                                            // meet on an address or a bank however the values cluster (POST_HIST_BYTES)
+  __shared__ unsigned folded[4][256];
   __shared__ unsigned prefix[4];
   __shared__ unsigned long long rank[4];
   __shared__ int alias[4];
   __shared__ float s_lo_hi[2];
-  const int tid = threadIdx.x, copy = (tid >> 5) & (POST_COPIES - 1);
+  const int tid = threadIdx.x, lane = tid & 31;
   const float* x = p.in + (long long)blockIdx.x * p.n;
   const long long n = p.n;
 
@@ -77,28 +80,59 @@ __global__ void __launch_bounds__(POST_T) percentile_clip_kernel(PercentileParam
         alias[t] = t;
         for (int u = 0; u < t; ++u) if (prefix[u] == prefix[t]) { alias[t] = u; break; }
       }
-    for (int i = tid; i < 4 * POST_COPIES * 256; i += POST_T) (&hist[0][0][0])[i] = 0u;
+    for (int i = tid; i < 4 * 256 * 32; i += POST_T) hist[i] = 0u;
     __syncthreads();
     const unsigned pf0 = prefix[0], pf1 = prefix[1], pf2 = prefix[2], pf3 = prefix[3];
     const bool own1 = alias[1] == 1, own2 = alias[2] == 2, own3 = alias[3] == 3;
-    for (long long i = tid; i < n; i += POST_T) {
-      const unsigned k = post_key(x[i]);
+    // An image's values share a handful of exponent bytes, so in the first passes most lanes of a warp hit the same bin:
+    // with one histogram per CTA those shared-memory atomics serialise 32 ways (and a match_any vote to merge them costs as
+    // much); with a column per lane they never collide inside a warp.
+    auto count = [&](unsigned k, bool in_range) {
       const unsigned hi_bits = pass == 0 ? 0u : (k >> (shift + 8));
-      const unsigned bin = (k >> shift) & 255u;
-      if (hi_bits == pf0) atomicAdd(&hist[0][copy][bin], 1u);
-      if (own1 && hi_bits == pf1) atomicAdd(&hist[1][copy][bin], 1u);
-      if (own2 && hi_bits == pf2) atomicAdd(&hist[2][copy][bin], 1u);
-      if (own3 && hi_bits == pf3) atomicAdd(&hist[3][copy][bin], 1u);
+      const unsigned slot = ((k >> shift) & 255u) * 32u + lane;
+      if (in_range && hi_bits == pf0) atomicAdd(&hist[slot], 1u);
+      if (in_range && own1 && hi_bits == pf1) atomicAdd(&hist[8192 + slot], 1u);
+      if (in_range && own2 && hi_bits == pf2) atomicAdd(&hist[16384 + slot], 1u);
+      if (in_range && own3 && hi_bits == pf3) atomicAdd(&hist[24576 + slot], 1u);
+    };
+    // each sweep is bound by the latency of its loads, so a thread keeps POST_ILP 128-bit loads in flight per iteration
+    const bool vec = (n & 3) == 0 && ((reinterpret_cast<unsigned long long>(x) & 15ull) == 0);
+    if (vec) {
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      const long long n4 = n >> 2;
+      const long long n_iter = (n4 + (long long)POST_T * POST_ILP - 1) / ((long long)POST_T * POST_ILP);
+      for (long long it = 0; it < n_iter; ++it) {
+        float4 v[POST_ILP];
+        bool ok[POST_ILP];
+#pragma unroll
+        for (int u = 0; u < POST_ILP; ++u) {
+          const long long i4 = (it * POST_ILP + u) * POST_T + tid;
+          ok[u] = i4 < n4;
+          v[u] = ok[u] ? x4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < POST_ILP; ++u) {
+          count(post_key(v[u].x), ok[u]); count(post_key(v[u].y), ok[u]);
+          count(post_key(v[u].z), ok[u]); count(post_key(v[u].w), ok[u]);
+        }
+      }
+    } else {
+      const long long n_iter = (n + POST_T - 1) / POST_T;
+      for (long long it = 0; it < n_iter; ++it) {
+        const long long i = it * POST_T + tid;
+        count(i < n ? post_key(x[i]) : 0u, i < n);
+      }
     }
     __syncthreads();
-    for (int i = tid; i < 4 * 256; i += POST_T) {      // fold the copies
-      unsigned s = 0;
-      for (int c = 0; c < POST_COPIES; ++c) s += hist[i >> 8][c][i & 255];
-      hist[i >> 8][0][i & 255] = s;
+    for (int i = tid; i < 4 * 256; i += POST_T) {      // fold the lane columns
+      unsigned sum = 0;
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) sum += hist[i * 32 + ((c + lane) & 31)];
+      folded[i >> 8][i & 255] = sum;
     }
     __syncthreads();
     if (tid < 4) {
-      const unsigned* h = hist[alias[tid]][0];
+      const unsigned* h = folded[alias[tid]];
       unsigned long long r = rank[tid];
       int b = 0;
       for (; b < 255; ++b) { if (r < h[b]) break; r -= h[b]; }
