@@ -160,3 +160,30 @@ def grappa_case_inputs(name: str):
             calib = (c[2:-2, :, 2:-2] + 0.5 * (c[1:-3, :, 2:-2] + c[3:-1, :, 2:-2]) + 0.5 * (c[2:-2, :, 1:-3] + c[2:-2, :, 3:-1])).astype(np.complex64)
             return k, calib
     raise KeyError(name)
+
+
+#: full T2 reconstruction case (prostate_t2_recon.py:9-78): (averages, slices, coils, RO, PE), ACS lines, calibration lines,
+#: seed.  RO = 320 so that the reference's hard-wired (320, 320) crop is the whole image; PE 60 -> padding 130 | 130.
+#: PE is kept small on purpose: numpy 2.3.5's np.unravel_index returns wrong coordinates for an (m, 1)-shaped index array
+#: with m > 8192, which is what Grappa.get_kernel_geometries (grappa.py:88-90) hands it -- under this numpy the vendored
+#: class silently leaves every hole after the 8192nd of a geometry unfilled (tests/test_grappa_sense.py shows it).  The
+#: golden cases stay below that size so that they pin the algorithm, not the library bug.
+T2_RECON_CASE = ((3, 2, 4, 320, 60), 12, 24, 701)
+
+
+def t2_recon_case_inputs():
+    """(kspace (3,S,C,RO,PE) c64 with R = 2 interleaved between odd / even averages + ACS, calibration (S,C,RO,PE_cal), header)."""
+    (na, ns, nc, ro, pe), acs, cal, seed = T2_RECON_CASE
+    k = gaussian_kspace((na, ns, nc, ro, pe), seed)
+    lo = (pe - acs) // 2
+    for a in range(na):
+        keep = np.zeros(pe, dtype=bool)
+        keep[(a % 2)::2] = True               # the second average samples the other set of lines
+        keep[lo:lo + acs] = True
+        k[a][..., ~keep] = 0
+    c = gaussian_kspace((ns, nc, ro + 4, cal + 4), seed + 1)
+    calib = (c[:, :, 2:-2, 2:-2] + 0.5 * (c[:, :, 1:-3, 2:-2] + c[:, :, 3:-1, 2:-2]) + 0.5 * (c[:, :, 2:-2, 1:-3] + c[:, :, 2:-2, 3:-1])).astype(np.complex64)
+    hdr = ("<?xml version=\"1.0\"?><ismrmrdHeader xmlns=\"http://www.ismrm.org/ISMRMRD\"><encoding><encodedSpace><matrixSize>"
+           f"<x>{ro}</x><y>{pe}</y><z>1</z></matrixSize></encodedSpace><encodingLimits><kspace_encoding_step_1><minimum>0</minimum>"
+           f"<maximum>{pe - 1}</maximum><center>{pe // 2}</center></kspace_encoding_step_1></encodingLimits></encoding></ismrmrdHeader>")
+    return k, calib, hdr

@@ -49,6 +49,12 @@ def main() -> None:
     img = synth.gaussian_kspace((3, 5, 12, 10), 611)
     sens = synth.gaussian_kspace((3, 5, 12, 10), 612)
     vec["sense/abs_sum"] = np.abs(np.sum(img * (sens.conj()), axis=1)).astype(np.float32)
+    # the whole T2 reconstruction (prostate_t2_recon.py:9-78) on a small three-average volume, header parsing included
+    k, calib, hdr = synth.t2_recon_case_inputs()
+    rec = ref_shim.prostate().t2.t2_reconstruction(k.copy(), calib.copy(), hdr)["reconstruction_rss"]
+    vec["t2_recon/reconstruction_rss_sub2"] = rec[:, ::2, ::2].astype(np.float32)
+    vec["t2_recon/padding"] = np.array([ref_shim.prostate().mri_data.get_padding(hdr)], dtype=np.float64)
+    man["t2_recon"] = {"shape": list(synth.T2_RECON_CASE[0]), "out": list(rec.shape), "dtype": str(rec.dtype)}
     np.savez_compressed(OUT, **vec)
     with open(os.path.join(ROOT, "tests", "golden", "grappa_manifest.json"), "w") as f:
         json.dump(man, f, indent=1)

@@ -527,6 +527,26 @@ def grappa_apply(kspace: np.ndarray, weights, kernel_size=(5, 5), coil_axis: int
     return np.moveaxis((recon + k)[kx2:-kx2, ky2:-ky2, :], -1, coil_axis)
 
 
+def t2_reconstruction(kspace_data: np.ndarray, calib_data: np.ndarray, pad: Tuple[int, int],
+                      crop: Tuple[int, int] = (320, 320)) -> np.ndarray:
+    """``t2_reconstruction`` (``ZIP!/fastmri_prostate/reconstruction/t2/prostate_t2_recon.py:9-78``) restated with the
+    functions above: geometries from slice 0 of averages 0 and 1, per-slice weights for both, averages 0/1/2 filled with
+    objects 1/2/1 into a complex128 array, then :func:`t2_average_combine`.  Returns ``(S, oh, ow)`` float64."""
+    num_avg, num_slices = kspace_data.shape[:2]
+    geo = []
+    for a in (0, 1):
+        _, P, valid, _, _ = grappa_geometries(np.transpose(kspace_data[a, 0], (2, 0, 1)), (5, 5), 1)
+        geo.append((P, valid))
+    weights = [[grappa_weights(np.transpose(calib_data[s], (2, 0, 1)), P, valid, (5, 5), 1) for s in range(num_slices)]
+               for P, valid in geo]
+    post = np.zeros(kspace_data.shape, dtype=complex)
+    for average, gi in zip((0, 1, 2), (0, 1, 0)):
+        for s in range(num_slices):
+            filled = grappa_apply(np.transpose(kspace_data[average, s], (2, 0, 1)), weights[gi][s], (5, 5), 1)
+            post[average, s] = np.moveaxis(np.moveaxis(filled, 0, 1), 1, 2)
+    return t2_average_combine(post, pad, crop)
+
+
 def sense_combine(img: np.ndarray, sens: np.ndarray, magnitude: bool = True) -> np.ndarray:
     """``np.sum(img * sens.conj(), axis=1)`` (+ ``np.abs``): ``ZIP!/fastmri_prostate/reconstruction/dwi/prostate_dwi_recon.py:106-109``;
     ``sens_reduce`` of ``ZIP!/DL_reconstruction/models/varnet.py:199-203`` is the same sum on real views (coil axis 1)."""
