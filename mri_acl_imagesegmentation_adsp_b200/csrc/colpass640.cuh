@@ -248,32 +248,40 @@ constexpr int CP_BAR_FULL = 1, CP_BAR_EMPTY = 3, CP_BAR_COMPUTE = 5;   // FULL: 
 // Called by CP_WS_T consecutive threads (tid 0 .. CP_WS_T-1) with two item buffers at `sm`.  uses[b] counts
 // how often buffer b has been filled since full_init (it selects the mbarrier phase), so the function can be
 // called again and again by a persistent CTA.
+// G = columns per item (8: the stand-alone kernel; 4: half-size items, so that two column teams fit beside a row team on one
+// SM -- p.n_groups must then count groups of 4); BARB = first named barrier of this team minus one (a team uses five).
+template <int G = CP_G, int BARB = 0>
 __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, FullBarrier* full_bar, int tid,
                                                int first, int stride, int count, int* uses) {
+  static_assert(G == 8 || G == 4 || G == 2, "items of 8, 4 or 2 columns");
+  constexpr int BUF = G * CP_PITCH;                      // complex elements of one item buffer
+  constexpr int BAR_FULL = BARB + CP_BAR_FULL, BAR_EMPTY = BARB + CP_BAR_EMPTY, BAR_COMPUTE = BARB + CP_BAR_COMPUTE;
+  constexpr int RPI = 32 / G;                            // rows per gather instruction
+  constexpr int NC = G / 2;                              // columns a transform thread owns on a full item
   if (tid >= CP_T) {
     // ------------------------------ producer warp ------------------------------
     const int lane = tid - CP_T;
-    const int k_ld = lane & 7, hs = lane >> 3;          // 8 columns x 4 rows per instruction
-    const long long row_step = 4LL * p.W;
+    const int k_ld = lane % G, hs = lane / G;           // G columns x (32 / G) rows per instruction
+    const long long row_step = (long long)RPI * p.W;
     const unsigned long long pol = l2_policy_evict_first();
     for (int k = 0; k < count; ++k) {
       const int item = first + k * stride;
       const int buf = k & 1;
-      if (k >= 2) named_bar_sync(CP_BAR_EMPTY + buf, CP_WS_T);   // buffer released by the compute warps
+      if (k >= 2) named_bar_sync(BAR_EMPTY + buf, CP_WS_T);   // buffer released by the compute warps
       const int fl = item / p.n_groups, g = item - fl * p.n_groups;
       const int f = p.frame0 + fl;
       const int b = f / (p.A * p.C), a = (f / p.C) % p.A, c = f % p.C;
-      const int j0 = g * CP_G;
+      const int j0 = g * G;
       if (j0 + k_ld < p.n_act && !MRIACL_DBG_SKIP(p, 1)) {
         const cf* src = p.ksp + b * p.sb + a * p.sa + ((long long)c * CP_N + hs) * p.W + p.act_w[j0 + k_ld];
-        cf* dst = sm + buf * CP_BUF + k_ld * CP_PITCH + hs;
+        cf* dst = sm + buf * BUF + k_ld * CP_PITCH + hs;
         if (p.l2_hints & 1) {
 #pragma unroll 1
           for (int blk = 0; blk < 8; ++blk) {
             cf* d = dst + CP_BLK * ((blk + 4) & 7);
 #pragma unroll
-            for (int q = 0; q < 20; ++q) {
-              cp_async8_hint(d + 4 * q, src, pol);
+            for (int q = 0; q < 80 / RPI; ++q) {
+              cp_async8_hint(d + RPI * q, src, pol);
               src += row_step;
             }
           }
@@ -282,15 +290,15 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
           for (int blk = 0; blk < 8; ++blk) {
             cf* d = dst + CP_BLK * ((blk + 4) & 7);
 #pragma unroll
-            for (int q = 0; q < 20; ++q) {
-              cp_async8(d + 4 * q, src);
+            for (int q = 0; q < 80 / RPI; ++q) {
+              cp_async8(d + RPI * q, src);
               src += row_step;
             }
           }
         }
       }
       // fires when this lane's copies have landed; the warp moves straight on to the next item's gather
-      full_signal_async(&full_bar[buf], CP_BAR_FULL + buf, CP_WS_T);
+      full_signal_async(&full_bar[buf], BAR_FULL + buf, CP_WS_T);
     }
     cp_async_wait_group<0>();
     return;
@@ -322,51 +330,51 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
   for (int k = 0; k < count; ++k) {
     const int item = first + k * stride;
     const int fl = item / p.n_groups, g = item - fl * p.n_groups;
-    const int j0 = g * CP_G;
-    const int ncols = min(CP_G, p.n_act - j0);
+    const int j0 = g * G;
+    const int ncols = min(G, p.n_act - j0);
     const int buf = k & 1;
-    cf* cur = sm + buf * CP_BUF;
-    full_wait(&full_bar[buf], (uses[buf] + (k >> 1)) & 1, CP_BAR_FULL + buf, CP_WS_T);
+    cf* cur = sm + buf * BUF;
+    full_wait(&full_bar[buf], (uses[buf] + (k >> 1)) & 1, BAR_FULL + buf, CP_WS_T);
 
     const int ncols_c = MRIACL_DBG_SKIP(p, 2) ? 0 : ncols;
-    // Full item (8 columns): each thread owns columns sub, sub+2, sub+4, sub+6 and keeps all four butterflies of a
-    // pass in flight (4-way instruction-level parallelism between the team barriers); ragged items take the loop below.
-    if (ncols_c == CP_G && p.unit_mask) {
+    // Full item: each thread owns columns sub, sub+2, ... (G / 2 of them) and keeps all their butterflies of a pass in
+    // flight (instruction-level parallelism between the team barriers); ragged items take the loop below.
+    if (ncols_c == G && p.unit_mask) {
       cf* col0 = cur + sub * CP_PITCH;
       {
-        cf v[4][8];
+        cf v[NC][8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
           for (int n1 = 0; n1 < 8; ++n1) v[c][n1] = col0[2 * c * CP_PITCH + pos + n1 * CP_BLK];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) radix8<true>(v[c]);
+        for (int c = 0; c < NC; ++c) radix8<true>(v[c]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NC; ++c) {
           cf* col = col0 + 2 * c * CP_PITCH + pos;
           col[0] = v[c][0];
 #pragma unroll
           for (int m1 = 1; m1 < 8; ++m1) col[m1 * CP_BLK] = cmul(v[c][m1], tw1[m1]);
         }
       }
-      named_bar_sync(CP_BAR_COMPUTE, CP_T);
+      named_bar_sync(BAR_COMPUTE, CP_T);
       {
-        cf v[4][8];
+        cf v[NC][8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
           for (int n2 = 0; n2 < 8; ++n2) v[c][n2] = col0[2 * c * CP_PITCH + base2 + n2 * 10];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) radix8<true>(v[c]);
+        for (int c = 0; c < NC; ++c) radix8<true>(v[c]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NC; ++c) {
           cf* col = col0 + 2 * c * CP_PITCH + base2;
           col[0] = v[c][0];
 #pragma unroll
           for (int m2 = 1; m2 < 8; ++m2) col[m2 * 10] = cmul(v[c][m2], tw2[m2]);
         }
       }
-      named_bar_sync(CP_BAR_COMPUTE, CP_T);
+      named_bar_sync(BAR_COMPUTE, CP_T);
     } else {
     // ---- pass 1: radix-8 over n1 (stride 90), mask multiply, twiddle w640^{pos * m1}; two columns in flight ----
     for (int kc = sub; kc < ncols_c; kc += 4) {
@@ -392,7 +400,7 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
         for (int m1 = 1; m1 < 8; ++m1) colB[m1 * CP_BLK] = cmul(vb[m1], tw1[m1]);
       }
     }
-    named_bar_sync(CP_BAR_COMPUTE, CP_T);
+    named_bar_sync(BAR_COMPUTE, CP_T);
 
     // ---- pass 2: radix-8 over n2 (stride 10), twiddle w80^{n3 * m2} ----
     for (int kc = sub; kc < ncols_c; kc += 4) {
@@ -413,7 +421,7 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
         for (int m2 = 1; m2 < 8; ++m2) colB[m2 * 10] = cmul(vb[m2], tw2[m2]);
       }
     }
-    named_bar_sync(CP_BAR_COMPUTE, CP_T);
+    named_bar_sync(BAR_COMPUTE, CP_T);
 
     }
     // ---- pass 3: radix-10 over n3 (contiguous), crop/shift/flip on the way out ----
@@ -423,7 +431,7 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
       t_frame = (sl % p.ring) * fpf + (fl - sl * fpf);
       if (sl >= p.ring) {
         if (tid == 0) wait_count_ge(p.rows_done + (sl - p.ring), p.rows_target);
-        named_bar_sync(CP_BAR_COMPUTE, CP_T);
+        named_bar_sync(BAR_COMPUTE, CP_T);
       }
     }
     if (tid < 128) {
@@ -451,12 +459,22 @@ __device__ __forceinline__ void colpass_ws_run(const ColPassParams& p, cf* sm, F
     }
     if (p.done) {
       __threadfence();
-      named_bar_sync(CP_BAR_COMPUTE, CP_T);
+      named_bar_sync(BAR_COMPUTE, CP_T);
       if (tid == 0) atomicAdd(p.done + fl / (p.A * p.C), 1);
     }
-    if (k + 2 < count) named_bar_arrive(CP_BAR_EMPTY + buf, CP_WS_T);   // producer may refill
+    if (k + 2 < count) named_bar_arrive(BAR_EMPTY + buf, CP_WS_T);   // producer may refill
   }
 }
+
+// The product kernel works on FOUR-column items (p.n_groups counts groups of CP_GW), two persistent CTAs per SM.
+// The 8-byte LDGSTS gather stages its in-flight lines in L1, and L1 is whatever the CTAs' shared memory leaves of the
+// SM's 256 KB: with eight-column items (2 x 92 KB -> the 196 KB configuration, 60 KB of L1) the column pass takes
+// 0.381 ms per 64 slices, with four-column items (2 x 46 KB -> 100 KB configuration, 156 KB of L1) 0.315 ms; forcing
+// the carveout shows the dependence directly: 28 KB of L1 0.65 ms, 92 KB 0.40 ms, 124 KB 0.33 ms, 156 KB 0.315 ms
+// (profiles/r02t_*).  Two-column items (0.33 ms) and three or four CTAs per SM (87 / 80 registers: 0.36 / 0.42 ms) lose
+// more in the transform than the larger L1 gives.
+constexpr int CP_GW = 4;
+constexpr int CP_SMEM_BYTES_WS = 2 * CP_GW * CP_PITCH * 8;
 
 __global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams p) {
   MRIACL_DYN_SMEM(cf, sm);
@@ -467,7 +485,24 @@ __global__ void __launch_bounds__(CP_WS_T, 2) colpass640_ws_kernel(ColPassParams
   int uses[2] = {0, 0};
   const int first = blockIdx.x;
   if (first < n_items)
-    colpass_ws_run(p, sm, full_bar, threadIdx.x, first, gridDim.x, (n_items - first + gridDim.x - 1) / gridDim.x, uses);
+    colpass_ws_run<CP_GW, 0>(p, sm, full_bar, threadIdx.x, first, gridDim.x, (n_items - first + gridDim.x - 1) / gridDim.x, uses);
 }
+
+#ifdef MRIACL_EXPERIMENTAL
+// stand-alone column pass on G-column items with MINB CTAs per SM (A/B of item size against L1 capacity: the smaller the
+// CTAs' shared memory, the larger the L1 left for the gather's in-flight lines)
+template <int G, int MINB>
+__global__ void __launch_bounds__(CP_WS_T, MINB) colpass640_ws_g_kernel(ColPassParams p) {
+  MRIACL_DYN_SMEM(cf, sm);
+  __shared__ FullBarrier full_bar[2];
+  const int n_items = p.n_frames * p.n_groups;
+  if (threadIdx.x == 0) { full_init(&full_bar[0], 32); full_init(&full_bar[1], 32); }
+  __syncthreads();
+  int uses[2] = {0, 0};
+  const int first = blockIdx.x;
+  if (first < n_items)
+    colpass_ws_run<G, 0>(p, sm, full_bar, threadIdx.x, first, gridDim.x, (n_items - first + gridDim.x - 1) / gridDim.x, uses);
+}
+#endif
 
 }  // namespace mriacl

@@ -172,4 +172,57 @@ __global__ void __launch_bounds__(KS_T, 1) knee_coresident_split_kernel(CoresPar
   }
 }
 
+// ---- two column teams + one row team -------------------------------------------------------------------------------
+// The column pass needs TWO gather streams per SM to keep HBM busy (stand-alone it runs two CTAs per SM; one team per SM,
+// as in the kernels above, takes 0.44-0.50 ms on its own), and it needs >= 60 KB of L1 for the in-flight lines of its
+// 8-byte LDGSTS gather, i.e. the CTA must stay inside the 196 KB shared-memory configuration.  Both fit
+// when the column items shrink to FOUR columns: two teams x two 23 KB buffers = the 92 KB one eight-column team used,
+// and a transform thread keeps two butterflies in flight instead of four (~85 registers), so 24 warps fit the register file.
+//   threads   0-191  column team A (items 2 b, 2 b + 2 grid, ...)    192-383  column team B (items 2 b + 1, ...)
+//   threads 384-767  row team (12 warps on a named barrier), fed by the per-slice counters the column teams bump
+constexpr int K2_T = 2 * CP_WS_T + KC_ROW_T;     // 768
+constexpr int K2_G = 4;
+constexpr int K2_COL_SMEM = 2 * 2 * K2_G * CP_PITCH * 8;     // two teams, two buffers each
+constexpr int K2_BAR_ROW = 11;                   // team A uses named barriers 1-5, team B 6-10
+
+template <int P, int Q>
+__global__ void __launch_bounds__(K2_T, 1) knee_coresident2_kernel(CoresParams p) {
+  MRIACL_DYN_SMEM(unsigned char, smem);
+  __shared__ FullBarrier full_bar[4];
+  __shared__ float red[KC_ROW_W];
+  __shared__ float s_stat[2];
+  __shared__ int s_ready, s_last;
+  const int tid = threadIdx.x;
+  if (tid < 4) full_init(&full_bar[tid], 32);
+  __syncthreads();
+
+  if (tid < 2 * CP_WS_T) {
+    const int team = tid / CP_WS_T, t = tid - team * CP_WS_T;
+    const int n_items = p.cp.n_frames * p.cp.n_groups;
+    int uses[2] = {0, 0};
+    const int first = 2 * blockIdx.x + team, stride = 2 * gridDim.x;
+    cf* tsm = reinterpret_cast<cf*>(smem) + (size_t)team * 2 * K2_G * CP_PITCH;
+    if (first < n_items) {
+      const int count = (n_items - first + stride - 1) / stride;
+      if (team == 0) colpass_ws_run<K2_G, 0>(p.cp, tsm, full_bar, t, first, stride, count, uses);
+      else colpass_ws_run<K2_G, 5>(p.cp, tsm, full_bar + 2, t, first, stride, count, uses);
+    }
+    return;
+  }
+  const int t = tid - 2 * CP_WS_T;
+  unsigned char* rsm = smem + K2_COL_SMEM;
+  const RowPass16Params& r = p.rp;
+  {
+    Rp16Smem<P, Q> S(rsm, r);
+    rp16_load_tables<KC_ROW_T>(r, S.sptw, S.sch, S.tbuf, t);
+  }
+  rp16_sync<K2_BAR_ROW, KC_ROW_T>();
+  const int n_items = r.n_slices * r.n_tiles;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    rowpass16_item<P, Q, KC_ROW_W, K2_BAR_ROW>(r, rsm, item, t, red, &s_ready);
+    if (r.done && !s_ready) return;
+    if (r.tiles_done) rowpass16_finish_slice<KC_ROW_W, K2_BAR_ROW>(r, item, t, s_stat, &s_last);
+  }
+}
+
 }  // namespace mriacl

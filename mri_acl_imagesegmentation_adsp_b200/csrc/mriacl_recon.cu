@@ -96,7 +96,7 @@ int ensure_smem_attrs(int dev) {
   if (d.smem_set) return 0;
   int bad = 0;
   bad |= rt_allow_smem((const void*)generic_fft_kernel, GEN_SMEM_BYTES);
-  bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB);   // default carveout: 2 CTAs -> 196 KB, 60 KB of L1 left for the gather
+  bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_WS);   // default carveout: 2 CTAs x 46 KB -> 100 KB, 156 KB of L1 left for the gather
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<W372_P, W372_Q, W372_NW, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<W400_P, W400_Q, W400_NW, 2>, SMEM_MAX / 2);
@@ -104,7 +104,8 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)rowpass_generic_kernel, SMEM_MAX);
 #ifdef MRIACL_EXPERIMENTAL
   const int cp_carve = env_int("MRIACL_CP_CARVEOUT", -1);
-  if (cp_carve >= 0) bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_DB, cp_carve);
+  if (cp_carve >= 0) bad |= rt_allow_smem((const void*)colpass640_ws_kernel, CP_SMEM_BYTES_WS, cp_carve);
+  bad |= rt_allow_smem((const void*)colpass640_ws_g_kernel<8, 2>, CP_SMEM_BYTES_DB, cp_carve);
   bad |= rt_allow_smem((const void*)colpass640_kernel<true>, CP_SMEM_BYTES_DB, cp_carve);
   bad |= rt_allow_smem((const void*)colpass640_kernel<false>, CP_SMEM_BYTES_SB, 100);   // co-resident with rowpass<8>: same carveout
   bad |= rt_allow_smem((const void*)rowpass_kernel<FUSED_P, FUSED_Q, RP_NW_SEQ>, SMEM_MAX);
@@ -430,7 +431,7 @@ int run_fused_pq(const FusedArgs& a, const ReconGeom& g) {
   PlanPtr pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
   if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
   const int n_act = (int)pl->host.act_w.size();
-  const int n_groups = (n_act + CP_G - 1) / CP_G;
+  const int n_groups = (n_act + CP_GW - 1) / CP_GW;
   const int ohp = g.n_tiles * RP_ROWS;
   const int row0 = crop_start(a.H, a.oh), col0 = crop_start(a.Wp, a.ow);
   const bool want_norm = (a.flags & MRIACL_NORM_INSTANCE) != 0;
@@ -453,7 +454,7 @@ int run_fused_pq(const FusedArgs& a, const ReconGeom& g) {
     const long long col_items = (long long)cp.n_frames * n_groups;
     if (col_items > 0) {
       const int grid = (int)std::min<long long>(col_items, (long long)a.sms * 2);
-      MRIACL_LAUNCH(colpass640_ws_kernel, grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+      MRIACL_LAUNCH(colpass640_ws_kernel, grid, CP_WS_T, CP_SMEM_BYTES_WS, a.st, cp);
     }
     RowPass16Params q{};
     q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
@@ -485,7 +486,7 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
   const bool wide640 = a.Wp == CP_N;
   if (!pl || (wide640 ? !pl->r640_off : !pl->act_logical)) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
   const int n_act = (int)pl->host.act_w.size();
-  const int n_groups = (n_act + CP_G - 1) / CP_G;
+  const int n_groups = (n_act + CP_GW - 1) / CP_GW;
   const int ohp = g.n_tiles * RP_ROWS;
   const int row0 = crop_start(a.H, a.oh), col0 = crop_start(a.Wp, a.ow);
   const bool want_norm = (a.flags & MRIACL_NORM_INSTANCE) != 0;
@@ -514,7 +515,7 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
     const long long col_items = (long long)cp.n_frames * n_groups;
     if (col_items > 0) {
       const int grid = (int)std::min<long long>(col_items, (long long)a.sms * 2);
-      MRIACL_LAUNCH(colpass640_ws_kernel, grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+      MRIACL_LAUNCH(colpass640_ws_kernel, grid, CP_WS_T, CP_SMEM_BYTES_WS, a.st, cp);
     } else if (rt_memset_async(T, 0, g.t_bytes * (size_t)ns, a.st)) {
       return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
     }
@@ -758,7 +759,19 @@ int run_fused_experimental(const FusedArgs& a, const ReconGeom& g) {
       if (kc_only == 1) kp.rp.n_slices = 0;
       if (kc_only == 2) { kp.cp.n_frames = 0; kp.rp.done = nullptr; }
       static const int kc_split = env_int("MRIACL_KC_SPLIT", 1);   // 1: warp-group register split (setmaxnreg), 0: uniform 96 registers
-      if (kc_split) {
+      static const int kc_teams = env_int("MRIACL_KC_TEAMS", 1);   // 2: two column teams on 4-column items + the row team
+      if (kc_teams == 2) {
+        const int groups4 = (n_act + K2_G - 1) / K2_G;
+        kp.cp.n_groups = groups4;
+        kp.rp.done_target = a.A * a.C * groups4;
+        if (kc_only == 2) kp.rp.done = nullptr;
+        const long long items4 = (long long)kp.cp.n_frames * groups4;
+        const int grid2 = (int)std::min<long long>((items4 + 1) / 2, (long long)a.sms);
+        auto kfn = knee_coresident2_kernel<FUSED_P, FUSED_Q>;
+        static bool once = false;
+        if (!once) { if (rt_allow_smem((const void*)kfn, SMEM_MAX)) return fail(MRIACL_ERR_CUDA, "smem attr"); once = true; }
+        MRIACL_LAUNCH(kfn, std::max(1, grid2), K2_T, K2_COL_SMEM + smem16, a.st, kp);
+      } else if (kc_split) {
         auto kfn = knee_coresident_split_kernel<FUSED_P, FUSED_Q>;
         MRIACL_LAUNCH(kfn, grid, KS_T, CP_SMEM_BYTES_DB + smem16, a.st, kp);
       } else {
@@ -807,9 +820,34 @@ int run_fused_experimental(const FusedArgs& a, const ReconGeom& g) {
         // tuning knobs: MRIACL_CP_DB=0 single-buffer CTAs, MRIACL_CP_PER_SM=k persistent CTAs per SM (0 = one item per CTA)
         static const int cp_db = env_int("MRIACL_CP_DB", 1), cp_per_sm = env_int("MRIACL_CP_PER_SM", 2);
         static const int cp_ws = env_int("MRIACL_CP_WS", 1);    // warp-specialised gather (default)
-        if (cp_ws && cp_db) {
+        static const int cp_g = env_int("MRIACL_CP_G", 8);      // 4: half-size items (A/B against L1 capacity)
+        if (cp_ws && cp_db && (cp_g == 4 || cp_g == 2)) {
+          ColPassParams c4 = cp;
+          c4.n_groups = (n_act + cp_g - 1) / cp_g;
+          const long long items4 = (long long)c4.n_frames * c4.n_groups;
+          const int per = std::max(2, std::min(4, cp_per_sm));
+          const int grid = (int)std::min<long long>(items4, (long long)a.sms * per);
+          const int sm4 = 2 * cp_g * CP_PITCH * 8;
+          static const int carve4 = env_int("MRIACL_CP_CARVEOUT", -1);
+          static bool once4 = false;
+          if (!once4) {
+            rt_allow_smem((const void*)colpass640_ws_g_kernel<4, 2>, sm4, carve4);
+            rt_allow_smem((const void*)colpass640_ws_g_kernel<4, 3>, sm4, carve4);
+            rt_allow_smem((const void*)colpass640_ws_g_kernel<4, 4>, sm4, carve4);
+            rt_allow_smem((const void*)colpass640_ws_g_kernel<2, 2>, sm4, carve4);
+            rt_allow_smem((const void*)colpass640_ws_g_kernel<2, 3>, sm4, carve4);
+            rt_allow_smem((const void*)colpass640_ws_g_kernel<2, 4>, sm4, carve4);
+            once4 = true;
+          }
+          if (cp_g == 4 && per == 2) MRIACL_LAUNCH((colpass640_ws_g_kernel<4, 2>), grid, CP_WS_T, sm4, a.st, c4);
+          else if (cp_g == 4 && per == 3) MRIACL_LAUNCH((colpass640_ws_g_kernel<4, 3>), grid, CP_WS_T, sm4, a.st, c4);
+          else if (cp_g == 4) MRIACL_LAUNCH((colpass640_ws_g_kernel<4, 4>), grid, CP_WS_T, sm4, a.st, c4);
+          else if (per == 2) MRIACL_LAUNCH((colpass640_ws_g_kernel<2, 2>), grid, CP_WS_T, sm4, a.st, c4);
+          else if (per == 3) MRIACL_LAUNCH((colpass640_ws_g_kernel<2, 3>), grid, CP_WS_T, sm4, a.st, c4);
+          else MRIACL_LAUNCH((colpass640_ws_g_kernel<2, 4>), grid, CP_WS_T, sm4, a.st, c4);
+        } else if (cp_ws && cp_db) {
           const int grid = (int)std::min<long long>(col_items, (long long)a.sms * std::max(1, cp_per_sm));
-          MRIACL_LAUNCH(colpass640_ws_kernel, grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+          MRIACL_LAUNCH((colpass640_ws_g_kernel<8, 2>), grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
         } else if (cp_db) {
           const int grid = (int)std::min<long long>(col_items, (long long)a.sms * std::max(1, cp_per_sm));
           MRIACL_LAUNCH(colpass640_kernel<true>, grid, CP_T, CP_SMEM_BYTES_DB, a.st, cp);
@@ -920,13 +958,13 @@ int run_fused_experimental(const FusedArgs& a, const ReconGeom& g) {
       const int col_grid = (int)std::min<long long>(col_items, (long long)a.sms * col_per_sm);
       auto kfn = rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>;
 #ifdef MRIACL_EMU   // the emulator runs launches one after another: producer first
-      MRIACL_LAUNCH(colpass640_ws_kernel, col_grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+      MRIACL_LAUNCH((colpass640_ws_g_kernel<8, 2>), col_grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
       MRIACL_LAUNCH(kfn, row_grid, 12 * 32, smem16, ov->side, q);
 #else
       // the row pass goes first so that its CTAs are resident when the column-pass CTAs arrive; a few SMs are
       // left without a row-pass CTA, so the column pass can always make progress whatever the block scheduler does
       MRIACL_LAUNCH(kfn, row_grid, 12 * 32, smem16, ov->side, q);
-      MRIACL_LAUNCH(colpass640_ws_kernel, col_grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+      MRIACL_LAUNCH((colpass640_ws_g_kernel<8, 2>), col_grid, CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
 #endif
       if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, ov->side, np);
       if (rt_event_record(ov->ev_row[wb], ov->side)) return fail(MRIACL_ERR_CUDA, "event record failed");
@@ -959,7 +997,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
   PlanPtr pl = get_fused_plan(a.dev, a.H, a.W, a.pad_left, a.Wp, a.oh, a.ow, a.mask, true);
   if (!pl) return fail(MRIACL_ERR_CUDA, "plan upload failed: %s", rt_last_error_string());
   const int n_act = (int)pl->host.act_w.size();
-  const int n_groups = (n_act + CP_G - 1) / CP_G;
+  const int n_groups = (n_act + CP_GW - 1) / CP_GW;
   const int ohp = g.n_tiles * RP_ROWS;
   const int row0 = crop_start(a.H, a.oh), col0 = crop_start(a.Wp, a.ow);
   const bool want_norm = (a.flags & MRIACL_NORM_INSTANCE) != 0;
@@ -988,7 +1026,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
       cp.tw = pl->twH; cp.T = T; cp.oh = a.oh; cp.ohp = ohp; cp.row0 = row0; cp.flip = flip;
       cp.frame0 = s0 * a.A * a.C; cp.n_frames = ns * a.A * a.C; cp.done = nullptr;
       const long long col_items = (long long)cp.n_frames * n_groups;
-      MRIACL_LAUNCH(colpass640_ws_kernel, (int)std::min<long long>(col_items, 2LL * a.sms), CP_WS_T, CP_SMEM_BYTES_DB, a.st, cp);
+      MRIACL_LAUNCH(colpass640_ws_kernel, (int)std::min<long long>(col_items, 2LL * a.sms), CP_WS_T, CP_SMEM_BYTES_WS, a.st, cp);
     }
     if (do_row) {
       RowPass16Params q{};
