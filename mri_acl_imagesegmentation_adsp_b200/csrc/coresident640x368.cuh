@@ -29,7 +29,7 @@ struct CoresParams {
   RowPass16Params rp;        // rp.done = the same counters; rp.tiles_done / mean_std / eps / normalize: fused normalisation
 };
 
-template <int P, int Q>
+template <int P, int Q, int G = CP_G>
 __global__ void __launch_bounds__(KC_T, 1) knee_coresident_kernel(CoresParams p) {
   MRIACL_DYN_SMEM(unsigned char, smem);
   __shared__ FullBarrier full_bar[2];
@@ -46,14 +46,14 @@ __global__ void __launch_bounds__(KC_T, 1) knee_coresident_kernel(CoresParams p)
     int uses[2] = {0, 0};
     const int first = blockIdx.x;
     if (first < n_items)
-      colpass_ws_run(p.cp, reinterpret_cast<cf*>(smem), full_bar, tid, first, gridDim.x,
+      colpass_ws_run<G, 0>(p.cp, reinterpret_cast<cf*>(smem), full_bar, tid, first, gridDim.x,
                      (n_items - first + gridDim.x - 1) / gridDim.x, uses);
     return;
   }
 
   // ------------------------------ row team ------------------------------
   const int t = tid - CP_WS_T;
-  unsigned char* rsm = smem + CP_SMEM_BYTES_DB;
+  unsigned char* rsm = smem + 2 * G * CP_PITCH * 8;
   const RowPass16Params& r = p.rp;
   {
     Rp16Smem<P, Q> S(rsm, r);

@@ -771,6 +771,16 @@ int run_fused_experimental(const FusedArgs& a, const ReconGeom& g) {
         static bool once = false;
         if (!once) { if (rt_allow_smem((const void*)kfn, SMEM_MAX)) return fail(MRIACL_ERR_CUDA, "smem attr"); once = true; }
         MRIACL_LAUNCH(kfn, std::max(1, grid2), K2_T, K2_COL_SMEM + smem16, a.st, kp);
+      } else if (kc_teams == 4) {       // one column team on 4-column items + the row team: 116-131 KB of shared memory, 124 KB of L1
+        const int groups4 = (n_act + 3) / 4;
+        kp.cp.n_groups = groups4;
+        kp.rp.done_target = a.A * a.C * groups4;
+        if (kc_only == 2) kp.rp.done = nullptr;
+        const long long items4 = (long long)kp.cp.n_frames * groups4;
+        auto kfn = knee_coresident_kernel<FUSED_P, FUSED_Q, 4>;
+        static bool once = false;
+        if (!once) { if (rt_allow_smem((const void*)kfn, SMEM_MAX)) return fail(MRIACL_ERR_CUDA, "smem attr"); once = true; }
+        MRIACL_LAUNCH(kfn, (int)std::min<long long>(items4, (long long)a.sms), KC_T, CP_SMEM_BYTES_WS + smem16, a.st, kp);
       } else if (kc_split) {
         auto kfn = knee_coresident_split_kernel<FUSED_P, FUSED_Q>;
         MRIACL_LAUNCH(kfn, grid, KS_T, CP_SMEM_BYTES_DB + smem16, a.st, kp);
