@@ -1,6 +1,7 @@
 // colpass640.cuh -- fused column pass of the k-space -> image stage for H = 640.
 //
-// One work item = (frame, group of <= 8 sampled phase-encode columns).  The CTA gathers the
+// One work item = (frame, group of <= G sampled phase-encode columns; G = 4 in the product kernel, see the end of
+// this file for why).  The CTA gathers the
 // group's columns from all 640 readout rows of complex64 k-space (the only HBM read of the
 // path; every 32-byte sector of a row that holds a sampled column is touched exactly once)
 // with 8-byte cp.async straight into shared memory, one item ahead of the arithmetic (double
