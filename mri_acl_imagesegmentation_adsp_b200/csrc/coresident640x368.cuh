@@ -16,6 +16,7 @@
 #include "colpass640.cuh"
 #include "rowpass16.cuh"
 #include "rowpair.cuh"
+#include "colpass640_tma.cuh"
 
 namespace mriacl {
 
@@ -224,5 +225,144 @@ __global__ void __launch_bounds__(K2_T, 1) knee_coresident2_kernel(CoresParams p
     if (r.tiles_done) rowpass16_finish_slice<KC_ROW_W, K2_BAR_ROW>(r, item, t, s_stat, &s_last);
   }
 }
+
+#ifndef MRIACL_EMU
+// ---- TMA-fed column teams + one row team ---------------------------------------------------------------------------
+// The gather of the kernels above needs L1 (8-byte LDGSTS.ca), and a CTA that also holds a row team leaves it 28-92 KB:
+// every co-resident variant so far had a starved column side.  Here the TMA unit streams whole bands of k-space into
+// raw slots (colpass640_tma.cuh): no L1, no load instructions, and the two transform teams only read shared memory.
+// T still goes through global memory (a ring of `ring` slices keeps it in L2).
+//   threads   0-319  two column transform teams      320-703  row team (12 warps)
+constexpr int KT_COL_T = 2 * CP_T;               // 320
+constexpr int KT_T = KT_COL_T + KC_ROW_T;        // 704
+constexpr int KT_BAR_ROW = 6;                    // the column teams use named barriers 1 and 2
+
+struct CoresTmaParams {
+  ColTmaParams ct;           // ct.cp.done = per-slice counters (zeroed before the launch)
+  RowPass16Params rp;        // rp.done = the same counters
+  int* rows_done;            // [n_slices] row tiles consumed per slice (ring), or nullptr
+};
+
+template <int P, int Q>
+__global__ void __launch_bounds__(KT_T, 1) knee_coresident_tma_kernel(const __grid_constant__ CUtensorMap map, CoresTmaParams p) {
+  MRIACL_DYN_SMEM(unsigned char, smem0);
+  __shared__ unsigned long long full[CT_MAX_SLOTS];
+  __shared__ float red[KC_ROW_W];
+  __shared__ int s_ready;
+  unsigned char* raw = smem0 + ((1024u - (ct_s32(smem0) & 1023u)) & 1023u);
+  cf* work = reinterpret_cast<cf*>(raw + (size_t)p.ct.n_slots * CT_SLOT_BYTES);
+  int* tabs = reinterpret_cast<int*>(work + 2 * p.ct.work_bufs * CT_WORK_CF);
+  unsigned char* rsm = reinterpret_cast<unsigned char*>(tabs) + coltma_table_bytes(p.ct.cp.n_groups, p.ct.cp.n_act);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < p.ct.n_slots; ++s) ct_mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  ColTmaTables tb{};
+  if (tid < KT_COL_T) tb = coltma_load_tables(p.ct, tabs, tid, KT_COL_T);
+  __syncthreads();
+
+  if (tid < KT_COL_T) {
+    const int n_items = p.ct.cp.n_frames * p.ct.cp.n_groups;
+    const int first = blockIdx.x;
+    if (first >= n_items) return;
+    const int count = (n_items - first + gridDim.x - 1) / gridDim.x;
+    if (tid < CP_T) coltma_team<1>(&map, p.ct, tb, raw, work, full, tid, 0, 2, first, gridDim.x, count);
+    else coltma_team<2>(&map, p.ct, tb, raw, work + p.ct.work_bufs * CT_WORK_CF, full, tid - CP_T, 1, 2, first, gridDim.x, count);
+    return;
+  }
+
+  const int t = tid - KT_COL_T;
+  const RowPass16Params& r = p.rp;
+  {
+    Rp16Smem<P, Q> S(rsm, r);
+    rp16_load_tables<KC_ROW_T>(r, S.sptw, S.sch, S.tbuf, t);
+  }
+  rp16_sync<KT_BAR_ROW, KC_ROW_T>();
+  const int n_items = r.n_slices * r.n_tiles;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    rowpass16_item<P, Q, KC_ROW_W, KT_BAR_ROW>(r, rsm, item, t, red, &s_ready);
+    if (r.done && !s_ready) return;                  // the wait for the slice timed out (error flag is set)
+    if (p.rows_done && t == 0) atomicAdd(p.rows_done + item / r.n_tiles, 1);   // (the item's last T read is behind a team barrier)
+  }
+}
+
+// ---- SM-role split: column SMs and row SMs -------------------------------------------------------------------------
+// Every variant above shares each SM between the two passes, and each time the teams slowed each other down as much as
+// the overlap gained (issue slots, the shared-memory pipe, barriers of a latency-bound row team).  Here the SMs are split
+// instead: one CTA per SM (grid <= number of SMs, the CTA's shared memory allows no second one), CTAs 0 .. n_col-1 are
+// COLUMN CTAs (four transform teams, each feeding its own raw slot by TMA: the TMA gather reaches 6.3-6.9 TB/s from
+// 56-74 SMs, tools/microbench/gather_modes.cu), the others are ROW CTAs (two 12-warp row teams, exactly the two CTAs per
+// SM of the stand-alone row pass).  Slices flow from the column SMs to the row SMs through a ring of T slots that stays
+// in L2; per-slice counters in both directions.  Nobody shares an SM, so each side runs at its stand-alone speed and
+// the step is max(column side, row side) + one row item of tail instead of their sum.
+constexpr int KX_T = 768;
+constexpr int KX_COL_TEAMS = 4;
+
+struct SplitParams {
+  ColTmaParams ct;           // ct.cp.done = per-slice counters (zeroed before the launch)
+  RowPass16Params rp;        // rp.done = the same counters
+  int* rows_done;            // [n_slices] row tiles consumed per slice (ring), or nullptr
+  int n_col;                 // CTAs 0 .. n_col-1 are column CTAs
+  int row_smem;              // bytes of one row team's shared memory (16-byte multiple)
+};
+
+template <int P, int Q>
+__global__ void __launch_bounds__(KX_T, 1) knee_split_kernel(const __grid_constant__ CUtensorMap map, SplitParams p) {
+  MRIACL_DYN_SMEM(unsigned char, smem0);
+  __shared__ unsigned long long full[CT_MAX_SLOTS];
+  __shared__ float red[2][KC_ROW_W];
+  __shared__ int s_ready[2];
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x < p.n_col) {
+    // ------------------------------ column CTA ------------------------------
+    unsigned char* raw = smem0 + ((1024u - (ct_s32(smem0) & 1023u)) & 1023u);
+    cf* work = reinterpret_cast<cf*>(raw + (size_t)p.ct.n_slots * CT_SLOT_BYTES);
+    int* tabs = reinterpret_cast<int*>(work + (size_t)KX_COL_TEAMS * p.ct.work_bufs * CT_WORK_CF);
+    if (tid == 0) {
+      for (int s = 0; s < p.ct.n_slots; ++s) ct_mbar_init(&full[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const ColTmaTables tb = coltma_load_tables(p.ct, tabs, tid, KX_T);
+    __syncthreads();
+    const int n_items = p.ct.cp.n_frames * p.ct.cp.n_groups;
+    const int first = blockIdx.x;
+    if (first >= n_items || tid >= KX_COL_TEAMS * CP_T) return;
+    const int count = (n_items - first + p.n_col - 1) / p.n_col;
+    const int team = tid / CP_T, tt = tid - team * CP_T;
+    cf* wk = work + (size_t)team * p.ct.work_bufs * CT_WORK_CF;
+    if (team == 0) coltma_team<1>(&map, p.ct, tb, raw, wk, full, tt, 0, KX_COL_TEAMS, first, p.n_col, count);
+    else if (team == 1) coltma_team<2>(&map, p.ct, tb, raw, wk, full, tt, 1, KX_COL_TEAMS, first, p.n_col, count);
+    else if (team == 2) coltma_team<3>(&map, p.ct, tb, raw, wk, full, tt, 2, KX_COL_TEAMS, first, p.n_col, count);
+    else coltma_team<4>(&map, p.ct, tb, raw, wk, full, tt, 3, KX_COL_TEAMS, first, p.n_col, count);
+    return;
+  }
+  // ------------------------------ row CTA: two independent row teams ------------------------------
+  const int team = tid / KC_ROW_T, t = tid - team * KC_ROW_T;
+  unsigned char* rsm = smem0 + (size_t)team * p.row_smem;
+  const RowPass16Params& r = p.rp;
+  const int n_items = r.n_slices * r.n_tiles;
+  const int first = 2 * ((int)blockIdx.x - p.n_col) + team, stride = 2 * ((int)gridDim.x - p.n_col);
+  {
+    Rp16Smem<P, Q> S(rsm, r);
+    rp16_load_tables<KC_ROW_T>(r, S.sptw, S.sch, S.tbuf, t);
+  }
+  if (team == 0) {
+    rp16_sync<1, KC_ROW_T>();
+    for (int item = first; item < n_items; item += stride) {
+      rowpass16_item<P, Q, KC_ROW_W, 1>(r, rsm, item, t, red[0], &s_ready[0]);
+      if (r.done && !s_ready[0]) return;
+      if (p.rows_done && t == 0) atomicAdd(p.rows_done + item / r.n_tiles, 1);
+    }
+  } else {
+    rp16_sync<2, KC_ROW_T>();
+    for (int item = first; item < n_items; item += stride) {
+      rowpass16_item<P, Q, KC_ROW_W, 2>(r, rsm, item, t, red[1], &s_ready[1]);
+      if (r.done && !s_ready[1]) return;
+      if (p.rows_done && t == 0) atomicAdd(p.rows_done + item / r.n_tiles, 1);
+    }
+  }
+}
+#endif
 
 }  // namespace mriacl

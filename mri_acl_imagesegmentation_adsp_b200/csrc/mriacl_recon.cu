@@ -17,6 +17,7 @@
 #include "hostpack.h"
 #include "generic_kernels.cuh"
 #include "colpass640.cuh"
+#include "colpass640_tma.cuh"
 #include "rowpass.cuh"
 #include "rowpass16.cuh"
 #include "rowpass640.cuh"
@@ -224,6 +225,8 @@ struct FusedPlanDev {
   std::vector<DevPtr> owned;
   int* act_w = nullptr; float* act_m = nullptr;
   int* act_ident = nullptr;        // 0 .. n_act-1: the column list of packed k-space (MRIACL_PACKED_COLUMNS)
+  std::vector<int> band_of_item, j0_of_item;   // TMA column pass: bands of 8 raw columns holding a sampled column, and each
+  int* item_band = nullptr; int* item_j0 = nullptr;   //            band's first active column (j0_of_item has one entry more)
   int* sched_p8 = nullptr; int* sched_p12 = nullptr; cf* sptw16_dev = nullptr; int* rp16_slot_dev = nullptr;
   int* act_logical = nullptr;      // pruned generic row pass: logical index of active column j in the padded line
   int* r640_off = nullptr; int* r640_ent = nullptr; int* r640_perm = nullptr;
@@ -278,6 +281,14 @@ PlanPtr get_fused_plan(int dev, int H, int W, int pad_left, int Wp, int oh, int 
       for (size_t j = 0; j < ident.size(); ++j) ident[j] = (int)j;
       if (!pl->put(ident, pl->act_ident)) return nullptr;
     }
+#ifndef MRIACL_EMU
+    for (size_t j = 0; j < h.act_w.size(); ++j) {
+      const int band = h.act_w[j] / CT_BW;
+      if (pl->band_of_item.empty() || pl->band_of_item.back() != band) { pl->band_of_item.push_back(band); pl->j0_of_item.push_back((int)j); }
+    }
+    pl->j0_of_item.push_back((int)h.act_w.size());
+    if (!pl->band_of_item.empty() && (!pl->put(pl->band_of_item, pl->item_band) || !pl->put(pl->j0_of_item, pl->item_j0))) return nullptr;
+#endif
     build_pair_schedule(pl->host, 12, pl->pairs12, pl->sptw16, &pl->rp16_slot_of_j, &pl->rp16_slots);
     build_pair_schedule(pl->host, Wp == W400_P * W400_Q ? W400_NW : 8, pl->pairs8, pl->sptw16);   // (8 warps; 7 for the 400-wide plans)
     if (!pl->put(pl->rp16_slot_of_j, pl->rp16_slot_dev) || !pl->put(pl->sptw16, pl->sptw16_dev) ||
@@ -412,6 +423,37 @@ int generic_fft2c(const cf* in, long long sb, long long sa, int A, int C, cf* ou
   c.inverse = inverse; c.scale = (float)(1.0 / std::sqrt((double)H));
   return launch_generic_pass(c, dev, st);
 }
+
+#ifndef MRIACL_EMU
+// ---- TMA descriptor of a k-space batch: (2 W floats) x (C H rows) x A x B, boxes of one band x 128 rows ---------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (TensorMapEncodeFn)p;
+  }();
+  return fn;
+}
+// false: this batch cannot be described (alignment, strides) -- the caller takes the cp.async gather
+bool kspace_tensor_map(CUtensorMap* map, const cf* ksp, long long sb, long long sa, int B, int A, int C, int H, int W) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc || H != CP_N || (W & 1) || ((uintptr_t)ksp & 15)) return false;
+  const long long frame = (long long)C * H * W;
+  if (A == 1) sa = frame;
+  if (B == 1) sb = frame * A;
+  if (sa <= 0 || sb <= 0 || (sa & 1) || (sb & 1)) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)W * 2, (cuuint64_t)C * H, (cuuint64_t)A, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 8, (cuuint64_t)sa * 8, (cuuint64_t)sb * 8};
+  const cuuint32_t box[4] = {2 * CT_BW, CT_BOX_ROWS, 1, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ksp, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#endif
 
 struct FusedArgs {
   const cf* ksp; long long slice_stride, avg_stride; const float* mask; float* out; float* mean_std;
@@ -692,7 +734,97 @@ int run_fused_experimental(const FusedArgs& a, const ReconGeom& g) {
     const bool run_norm = (want_norm || a.mean_std) && do_norm;
 
     static const int kc_pair = env_int("MRIACL_KC_PAIR", 1);      // co-resident schedule: pair row team when the mask allows
-    if (coresident && kc_pair && a.A == 1 && pl->rpp.ok) {
+#ifndef MRIACL_EMU
+    static const int kc_tma = env_int("MRIACL_KC_TMA", 0);        // co-resident schedule with TMA-fed column teams
+    static const int kc_split_sm = env_int("MRIACL_KC_SPLIT_SM", 0);   // > 0: SM-role split with this many column SMs
+    CUtensorMap kc_map;
+#endif
+    if (false) {
+#ifndef MRIACL_EMU
+    } else if (coresident && kc_tma && !(a.flags & MRIACL_PACKED_COLUMNS) && pl->item_band &&
+               coltma_smem_bytes(2, 2, 1) + coltma_table_bytes((int)pl->band_of_item.size(), n_act) + rowpass16_smem_bytes(FUSED_P, FUSED_Q, (int)pl->sptw16.size(), (int)pl->pairs12.size(), pl->rp16_slots, 1, a.ow, a.A) <= SMEM_MAX &&
+               kspace_tensor_map(&kc_map, a.ksp, a.slice_stride, a.avg_stride, a.B, a.A, a.C, a.H, a.W)) {
+      if (rt_memset_async(counters, 0, 256 * (size_t)ns, a.st)) return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
+      CoresTmaParams kp{};
+      const int n_bands = (int)pl->band_of_item.size();
+      kp.ct.cp = cp; kp.ct.cp.n_groups = n_bands; kp.ct.cp.done = counters;
+      kp.ct.item_band = pl->item_band; kp.ct.item_j0 = pl->item_j0;
+      kp.ct.n_slots = std::max(2, std::min(CT_MAX_SLOTS, env_int("MRIACL_CT_SLOTS", 2)));
+      kp.ct.work_bufs = std::max(1, std::min(2, env_int("MRIACL_CT_WORK", 2)));
+      RowPass16Params& q = kp.rp;
+      q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+      q.sched = pl->sched_p12; q.sched_len = (int)pl->pairs12.size();
+      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size(); q.n_slots = pl->rp16_slots; q.slot_of_j = pl->rp16_slot_dev;
+      q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
+      q.n_slices = ns; q.n_tiles = g.n_tiles16;
+      q.done = counters; q.done_target = a.A * a.C * n_bands; q.error_flag = ov->error_flag;
+      q.n_buf = std::max(1, std::min(3, env_int("MRIACL_KC_NBUF", 2)));
+      const int kc_ring = std::max(0, env_int("MRIACL_KC_RING", 0));
+      if (kc_ring > 0 && kc_ring < ns) {
+        kp.ct.cp.ring = kc_ring; kp.ct.cp.rows_done = counters + ns; kp.ct.cp.rows_target = g.n_tiles16;
+        q.ring = kc_ring; kp.rows_done = counters + ns;
+      }
+      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, q.n_buf, a.ow, a.A);
+      const int tab_b = coltma_table_bytes(n_bands, n_act);
+      int smem = coltma_smem_bytes(kp.ct.n_slots, 2, kp.ct.work_bufs) + tab_b + smem16;
+      if (smem > SMEM_MAX) {   // smallest configuration
+        kp.ct.n_slots = 2; kp.ct.work_bufs = 1; q.n_buf = 1;
+        smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, 1, a.ow, a.A);
+        smem = coltma_smem_bytes(2, 2, 1) + tab_b + smem16;
+      }
+      if (smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "co-resident TMA kernel: %d B of shared memory do not fit (slots %d work %d n_buf %d)", smem, kp.ct.n_slots, kp.ct.work_bufs, q.n_buf);
+      static const int kc_only = env_int("MRIACL_KC_ONLY", 0);
+      if (kc_only == 1) { q.n_slices = 0; if (env_int("MRIACL_KC_NOPUB", 0)) kp.ct.cp.done = nullptr; }
+      if (kc_only == 2) { kp.ct.cp.n_frames = 0; q.done = nullptr; }
+      np.n_part = g.n_tiles16;
+      auto kfn = knee_coresident_tma_kernel<FUSED_P, FUSED_Q>;
+      static bool once = false;
+      if (!once) { if (rt_allow_smem((const void*)kfn, SMEM_MAX)) return fail(MRIACL_ERR_CUDA, "smem attr"); once = true; }
+      const long long items = (long long)cp.n_frames * n_bands;
+      MRIACL_LAUNCH(kfn, (int)std::min<long long>(std::max<long long>(items, 1), (long long)a.sms), KT_T, smem, a.st, kc_map, kp);
+      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
+    } else if (coresident && kc_split_sm > 0 && !(a.flags & MRIACL_PACKED_COLUMNS) && pl->item_band &&
+               2 * rowpass16_smem_bytes(FUSED_P, FUSED_Q, (int)pl->sptw16.size(), (int)pl->pairs12.size(), pl->rp16_slots, 1, a.ow, a.A) <= SMEM_MAX &&
+               kspace_tensor_map(&kc_map, a.ksp, a.slice_stride, a.avg_stride, a.B, a.A, a.C, a.H, a.W)) {
+      // SM-role split (coresident640x368.cuh): kc_split_sm column CTAs, the other SMs run two row teams each
+      if (rt_memset_async(counters, 0, 256 * (size_t)ns, a.st)) return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
+      SplitParams kp{};
+      const int n_bands = (int)pl->band_of_item.size();
+      kp.ct.cp = cp; kp.ct.cp.n_groups = n_bands; kp.ct.cp.done = counters;
+      kp.ct.item_band = pl->item_band; kp.ct.item_j0 = pl->item_j0;
+      kp.ct.n_slots = KX_COL_TEAMS;
+      kp.ct.work_bufs = std::max(1, std::min(2, env_int("MRIACL_CT_WORK", 1)));
+      RowPass16Params& q = kp.rp;
+      q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
+      q.sched = pl->sched_p12; q.sched_len = (int)pl->pairs12.size();
+      q.sptw = pl->sptw16_dev; q.sptw_len = (int)pl->sptw16.size(); q.n_slots = pl->rp16_slots; q.slot_of_j = pl->rp16_slot_dev;
+      q.out = rp.out; q.partials = partials; q.ow = a.ow; q.col0 = col0; q.A = a.A; q.C = a.C; q.scale = rp.scale;
+      q.n_slices = ns; q.n_tiles = g.n_tiles16;
+      q.done = counters; q.done_target = a.A * a.C * n_bands; q.error_flag = ov->error_flag;
+      q.n_buf = std::max(1, std::min(3, env_int("MRIACL_KC_NBUF", 3)));
+      int smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, q.n_buf, a.ow, a.A);
+      while (2 * align_up(smem16, 16) > (size_t)SMEM_MAX && q.n_buf > 1) { --q.n_buf; smem16 = rowpass16_smem_bytes(FUSED_P, FUSED_Q, q.sptw_len, q.sched_len, pl->rp16_slots, q.n_buf, a.ow, a.A); }
+      kp.row_smem = (int)align_up(smem16, 16);
+      const int smem = std::max(coltma_smem_bytes(kp.ct.n_slots, KX_COL_TEAMS, kp.ct.work_bufs) + coltma_table_bytes(n_bands, n_act), 2 * kp.row_smem);
+      if (smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "split kernel: %d B of shared memory do not fit", smem);
+      const int grid = a.sms;
+      kp.n_col = std::max(1, std::min(grid - 1, kc_split_sm));
+      const int kc_ring = std::max(0, env_int("MRIACL_KC_RING", 16));
+      if (kc_ring > 0 && kc_ring < ns) {
+        kp.ct.cp.ring = kc_ring; kp.ct.cp.rows_done = counters + ns; kp.ct.cp.rows_target = g.n_tiles16;
+        q.ring = kc_ring; kp.rows_done = counters + ns;
+      }
+      static const int kc_only = env_int("MRIACL_KC_ONLY", 0);
+      if (kc_only == 1) { q.n_slices = 0; kp.ct.cp.ring = 0; }
+      if (kc_only == 2) { kp.ct.cp.n_frames = 0; q.done = nullptr; }
+      np.n_part = g.n_tiles16;
+      auto kfn = knee_split_kernel<FUSED_P, FUSED_Q>;
+      static bool once = false;
+      if (!once) { if (rt_allow_smem((const void*)kfn, SMEM_MAX)) return fail(MRIACL_ERR_CUDA, "smem attr"); once = true; }
+      MRIACL_LAUNCH(kfn, grid, KX_T, smem, a.st, kc_map, kp);
+      if (run_norm) MRIACL_LAUNCH(normalize_instance_kernel, ns * np.n_split, 256, 0, a.st, np);
+#endif
+    } else if (coresident && kc_pair && a.A == 1 && pl->rpp.ok) {
       using L = RowPairLayout<FUSED_P, FUSED_Q, RPP_STEP, RPP_NE>;
       if (rt_memset_async(counters, 0, 256 * (size_t)ns, a.st)) return fail(MRIACL_ERR_CUDA, "memset failed: %s", rt_last_error_string());
       CoresPairParams kp{};
@@ -831,7 +963,31 @@ int run_fused_experimental(const FusedArgs& a, const ReconGeom& g) {
         static const int cp_db = env_int("MRIACL_CP_DB", 1), cp_per_sm = env_int("MRIACL_CP_PER_SM", 2);
         static const int cp_ws = env_int("MRIACL_CP_WS", 1);    // warp-specialised gather (default)
         static const int cp_g = env_int("MRIACL_CP_G", 8);      // 4: half-size items (A/B against L1 capacity)
-        if (cp_ws && cp_db && (cp_g == 4 || cp_g == 2)) {
+        static const int cp_tma = env_int("MRIACL_CP_TMA", 0);  // n: TMA band gather with n transform teams per CTA
+        CUtensorMap kmap;
+        if (cp_tma > 0 && !(a.flags & MRIACL_PACKED_COLUMNS) && pl->item_band &&
+            kspace_tensor_map(&kmap, a.ksp, a.slice_stride, a.avg_stride, a.B, a.A, a.C, a.H, a.W)) {
+          static const int ct_slots = std::max(cp_tma >= 2 ? 2 : 1, std::min(CT_MAX_SLOTS, env_int("MRIACL_CT_SLOTS", 2)));
+          static const int ct_per_sm = std::max(1, std::min(2, env_int("MRIACL_CT_PER_SM", cp_tma == 1 ? 2 : 1)));
+          ColTmaParams tp{};
+          tp.cp = cp; tp.cp.n_groups = (int)pl->band_of_item.size();
+          tp.item_band = pl->item_band; tp.item_j0 = pl->item_j0; tp.n_slots = ct_slots; tp.work_bufs = 2;
+          const long long items = (long long)tp.cp.n_frames * tp.cp.n_groups;
+          const int nt = cp_tma >= 2 ? 2 : 1;
+          const int smem = coltma_smem_bytes(ct_slots, nt) + coltma_table_bytes(tp.cp.n_groups, n_act);
+          if (smem > SMEM_MAX / ct_per_sm) return fail(MRIACL_ERR_UNSUPPORTED, "TMA column pass: %d slots x %d teams x %d CTAs/SM do not fit", ct_slots, nt, ct_per_sm);
+          static bool once_t = false;
+          if (!once_t) {
+            rt_allow_smem((const void*)colpass640_tma_kernel<1, 1>, SMEM_MAX); rt_allow_smem((const void*)colpass640_tma_kernel<1, 2>, SMEM_MAX / 2);
+            rt_allow_smem((const void*)colpass640_tma_kernel<2, 1>, SMEM_MAX); rt_allow_smem((const void*)colpass640_tma_kernel<2, 2>, SMEM_MAX / 2);
+            once_t = true;
+          }
+          const int grid = (int)std::min<long long>(items, (long long)a.sms * ct_per_sm);
+          if (nt == 1 && ct_per_sm == 1) MRIACL_LAUNCH((colpass640_tma_kernel<1, 1>), grid, CP_T, smem, a.st, kmap, tp);
+          else if (nt == 1) MRIACL_LAUNCH((colpass640_tma_kernel<1, 2>), grid, CP_T, smem, a.st, kmap, tp);
+          else if (ct_per_sm == 1) MRIACL_LAUNCH((colpass640_tma_kernel<2, 1>), grid, 2 * CP_T, smem, a.st, kmap, tp);
+          else MRIACL_LAUNCH((colpass640_tma_kernel<2, 2>), grid, 2 * CP_T, smem, a.st, kmap, tp);
+        } else if (cp_ws && cp_db && (cp_g == 4 || cp_g == 2)) {
           ColPassParams c4 = cp;
           c4.n_groups = (n_act + cp_g - 1) / cp_g;
           const long long items4 = (long long)c4.n_frames * c4.n_groups;
@@ -998,7 +1154,7 @@ int run_fused(const FusedArgs& a, const ReconGeom& g) {
                                     MRIACL_SCHED_PIPELINED;
 #ifdef MRIACL_EXPERIMENTAL
   if ((a.flags & experimental) || getenv("MRIACL_SCHEDULE") || getenv("MRIACL_RP16_CFG") || getenv("MRIACL_CP_DEBUG_SKIP") ||
-      getenv("MRIACL_RP_DEBUG_SKIP") || getenv("MRIACL_CP_PER_SM") || getenv("MRIACL_FUSE_NORM"))
+      getenv("MRIACL_RP_DEBUG_SKIP") || getenv("MRIACL_CP_PER_SM") || getenv("MRIACL_FUSE_NORM") || getenv("MRIACL_CP_TMA"))
     return run_fused_experimental(a, g);
 #else
   if ((a.flags & experimental) && !(a.flags & MRIACL_SEQUENTIAL))

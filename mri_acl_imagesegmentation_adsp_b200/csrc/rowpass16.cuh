@@ -47,6 +47,7 @@ struct RowPass16Params {
   int debug_skip;        // profiling only (results are garbage): 1 = no stage 1, 2 = no stage 2, 4 = no T prefetch
   int reverse;           // 1: take the slices last-to-first: the column pass wrote them first-to-last, so the most
                          //    recently written part of T is still in L2 when the row pass starts (sequential schedule)
+  int ring;              // co-resident schedule: T holds `ring` slices, slice s lives in slot s % ring (0: one slot per slice)
 };
 
 inline int rowpass16_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n_slots, int n_buf, int ow, int A) {
@@ -149,7 +150,7 @@ __device__ __forceinline__ void rowpass16_item(const RowPass16Params& p, void* s
 
     const int s_fwd = item / p.n_tiles, tile = item - s_fwd * p.n_tiles;
     const int s = p.reverse ? p.n_slices - 1 - s_fwd : s_fwd;
-    const cf* Tit = p.T + (long long)s * n_frames * frame_elems + tile * RP16_ROWS;
+    const cf* Tit = p.T + (long long)(p.ring ? s % p.ring : s) * n_frames * frame_elems + tile * RP16_ROWS;
 
     const cf* src0 = Tit + (long long)(tid >> 3) * p.ohp + 2 * (tid & 7);
     cf* dst0 = tbuf + 2 * (tid & 7);
