@@ -105,11 +105,10 @@ __device__ __forceinline__ void coltma_issue(const CUtensorMap* map, const ColPa
 // its thread 0 issues the TMA of a later item into a slot right after the team barrier that ends the slot's last pass 1
 // (a separate TMA thread serving every slot of the CTA in turn was the bottleneck of the first version: one thread's
 // index arithmetic, at the issue rate a warp gets on a busy SM, capped the CTA at one item per ~1.4 us).
-// BAR = the team's named barrier.
-template <int BAR>
-__device__ __forceinline__ void coltma_team(const CUtensorMap* map, const ColTmaParams& p, const ColTmaTables& tb,
-                                            unsigned char* raw, cf* work, unsigned long long* full, int tid, int team,
-                                            int n_teams, int first, int stride, int count) {
+// BAR = the team's named barrier (a run-time value: every team of a CTA runs the same ~30 KB copy of this code).
+__device__ __forceinline__ void coltma_team(const int BAR, const CUtensorMap* map, const ColTmaParams& p, const ColTmaTables& tb,
+                                         unsigned char* raw, cf* work, unsigned long long* full, int tid, int team,
+                                         int n_teams, int first, int stride, int count) {
   const ColPassParams& cp = p.cp;
   const int ns = p.n_slots;
   const int owned = (ns - team + n_teams - 1) / n_teams;           // >= 1: the launch code keeps n_slots >= n_teams
@@ -270,8 +269,7 @@ __global__ void __launch_bounds__(NT * CP_T, MINB) colpass640_tma_kernel(const _
   const int count = (n_items - first + gridDim.x - 1) / gridDim.x;
   const int team = tid / CP_T, t = tid - team * CP_T;
   cf* wk = work + (size_t)team * p.work_bufs * CT_WORK_CF;
-  if (team == 0) coltma_team<1>(&map, p, tb, raw, wk, full, t, 0, NT, first, gridDim.x, count);
-  else coltma_team<2>(&map, p, tb, raw, wk, full, t, 1, NT, first, gridDim.x, count);
+  coltma_team(1 + team, &map, p, tb, raw, wk, full, t, team, NT, first, gridDim.x, count);
 }
 
 }  // namespace mriacl

@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(KT_T, 1) knee_coresident_tma_kernel(const __gr
     const int first = blockIdx.x;
     if (first >= n_items) return;
     const int count = (n_items - first + gridDim.x - 1) / gridDim.x;
-    if (tid < CP_T) coltma_team<1>(&map, p.ct, tb, raw, work, full, tid, 0, 2, first, gridDim.x, count);
-    else coltma_team<2>(&map, p.ct, tb, raw, work + p.ct.work_bufs * CT_WORK_CF, full, tid - CP_T, 1, 2, first, gridDim.x, count);
+    const int team = tid / CP_T;
+    coltma_team(1 + team, &map, p.ct, tb, raw, work + team * p.ct.work_bufs * CT_WORK_CF, full, tid - team * CP_T, team, 2, first, gridDim.x, count);
     return;
   }
 
@@ -331,10 +331,7 @@ __global__ void __launch_bounds__(KX_T, 1) knee_split_kernel(const __grid_consta
     const int count = (n_items - first + p.n_col - 1) / p.n_col;
     const int team = tid / CP_T, tt = tid - team * CP_T;
     cf* wk = work + (size_t)team * p.ct.work_bufs * CT_WORK_CF;
-    if (team == 0) coltma_team<1>(&map, p.ct, tb, raw, wk, full, tt, 0, KX_COL_TEAMS, first, p.n_col, count);
-    else if (team == 1) coltma_team<2>(&map, p.ct, tb, raw, wk, full, tt, 1, KX_COL_TEAMS, first, p.n_col, count);
-    else if (team == 2) coltma_team<3>(&map, p.ct, tb, raw, wk, full, tt, 2, KX_COL_TEAMS, first, p.n_col, count);
-    else coltma_team<4>(&map, p.ct, tb, raw, wk, full, tt, 3, KX_COL_TEAMS, first, p.n_col, count);
+    coltma_team(1 + team, &map, p.ct, tb, raw, wk, full, tt, team, KX_COL_TEAMS, first, p.n_col, count);
     return;
   }
   // ------------------------------ row CTA: two independent row teams ------------------------------
@@ -347,20 +344,12 @@ __global__ void __launch_bounds__(KX_T, 1) knee_split_kernel(const __grid_consta
     Rp16Smem<P, Q> S(rsm, r);
     rp16_load_tables<KC_ROW_T>(r, S.sptw, S.sch, S.tbuf, t);
   }
-  if (team == 0) {
-    rp16_sync<1, KC_ROW_T>();
-    for (int item = first; item < n_items; item += stride) {
-      rowpass16_item<P, Q, KC_ROW_W, 1>(r, rsm, item, t, red[0], &s_ready[0]);
-      if (r.done && !s_ready[0]) return;
-      if (p.rows_done && t == 0) atomicAdd(p.rows_done + item / r.n_tiles, 1);
-    }
-  } else {
-    rp16_sync<2, KC_ROW_T>();
-    for (int item = first; item < n_items; item += stride) {
-      rowpass16_item<P, Q, KC_ROW_W, 2>(r, rsm, item, t, red[1], &s_ready[1]);
-      if (r.done && !s_ready[1]) return;
-      if (p.rows_done && t == 0) atomicAdd(p.rows_done + item / r.n_tiles, 1);
-    }
+  // one copy of the row-pass code for both teams (BAR = -1: named barrier 1 + team)
+  rp16_sync<-1, KC_ROW_T>();
+  for (int item = first; item < n_items; item += stride) {
+    rowpass16_item<P, Q, KC_ROW_W, -1>(r, rsm, item, t, red[team], &s_ready[team]);
+    if (r.done && !s_ready[team]) return;
+    if (p.rows_done && t == 0) atomicAdd(p.rows_done + item / r.n_tiles, 1);
   }
 }
 #endif

@@ -17,7 +17,6 @@
 #include "hostpack.h"
 #include "generic_kernels.cuh"
 #include "colpass640.cuh"
-#include "colpass640_tma.cuh"
 #include "rowpass.cuh"
 #include "rowpass16.cuh"
 #include "rowpass640.cuh"
@@ -31,6 +30,7 @@
 // results for the emulator tests and for A/B runs, not part of the product library
 #include "rowpair.cuh"
 #include "fused640x368.cuh"
+#include "colpass640_tma.cuh"
 #include "coresident640x368.cuh"
 #endif
 
@@ -281,8 +281,8 @@ PlanPtr get_fused_plan(int dev, int H, int W, int pad_left, int Wp, int oh, int 
       for (size_t j = 0; j < ident.size(); ++j) ident[j] = (int)j;
       if (!pl->put(ident, pl->act_ident)) return nullptr;
     }
-#ifndef MRIACL_EMU
-    for (size_t j = 0; j < h.act_w.size(); ++j) {
+#if defined(MRIACL_EXPERIMENTAL) && !defined(MRIACL_EMU)
+    for (size_t j = 0; j < h.act_w.size(); ++j) {      // TMA column pass: bands of CT_BW raw columns that hold a sampled column
       const int band = h.act_w[j] / CT_BW;
       if (pl->band_of_item.empty() || pl->band_of_item.back() != band) { pl->band_of_item.push_back(band); pl->j0_of_item.push_back((int)j); }
     }
@@ -424,7 +424,7 @@ int generic_fft2c(const cf* in, long long sb, long long sa, int A, int C, cf* ou
   return launch_generic_pass(c, dev, st);
 }
 
-#ifndef MRIACL_EMU
+#if defined(MRIACL_EXPERIMENTAL) && !defined(MRIACL_EMU)
 // ---- TMA descriptor of a k-space batch: (2 W floats) x (C H rows) x A x B, boxes of one band x 128 rows ---------------
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -963,9 +963,13 @@ int run_fused_experimental(const FusedArgs& a, const ReconGeom& g) {
         static const int cp_db = env_int("MRIACL_CP_DB", 1), cp_per_sm = env_int("MRIACL_CP_PER_SM", 2);
         static const int cp_ws = env_int("MRIACL_CP_WS", 1);    // warp-specialised gather (default)
         static const int cp_g = env_int("MRIACL_CP_G", 8);      // 4: half-size items (A/B against L1 capacity)
+#ifndef MRIACL_EMU
         static const int cp_tma = env_int("MRIACL_CP_TMA", 0);  // n: TMA band gather with n transform teams per CTA
         CUtensorMap kmap;
-        if (cp_tma > 0 && !(a.flags & MRIACL_PACKED_COLUMNS) && pl->item_band &&
+#endif
+        if (false) {
+#ifndef MRIACL_EMU
+        } else if (cp_tma > 0 && !(a.flags & MRIACL_PACKED_COLUMNS) && pl->item_band &&
             kspace_tensor_map(&kmap, a.ksp, a.slice_stride, a.avg_stride, a.B, a.A, a.C, a.H, a.W)) {
           static const int ct_slots = std::max(cp_tma >= 2 ? 2 : 1, std::min(CT_MAX_SLOTS, env_int("MRIACL_CT_SLOTS", 2)));
           static const int ct_per_sm = std::max(1, std::min(2, env_int("MRIACL_CT_PER_SM", cp_tma == 1 ? 2 : 1)));
@@ -987,6 +991,7 @@ int run_fused_experimental(const FusedArgs& a, const ReconGeom& g) {
           else if (nt == 1) MRIACL_LAUNCH((colpass640_tma_kernel<1, 2>), grid, CP_T, smem, a.st, kmap, tp);
           else if (ct_per_sm == 1) MRIACL_LAUNCH((colpass640_tma_kernel<2, 1>), grid, 2 * CP_T, smem, a.st, kmap, tp);
           else MRIACL_LAUNCH((colpass640_tma_kernel<2, 2>), grid, 2 * CP_T, smem, a.st, kmap, tp);
+#endif
         } else if (cp_ws && cp_db && (cp_g == 4 || cp_g == 2)) {
           ColPassParams c4 = cp;
           c4.n_groups = (n_act + cp_g - 1) / cp_g;

@@ -56,8 +56,12 @@ inline int rowpass16_smem_bytes(int P, int Q, int sptw_len, int sched_len, int n
 }
 
 // team barrier: BAR = 0 is the CTA barrier; BAR > 0 a named barrier over the NT threads of a sub-CTA team
+// BAR = -1: several identical teams of NT threads in one CTA share ONE copy of the code (the row pass is ~100 KB of
+// instructions: a copy per team would thrash the instruction cache); team k = threadIdx.x / NT uses named barrier 1 + k
 template <int BAR, int NT> __device__ __forceinline__ void rp16_sync() {
-  if constexpr (BAR == 0) __syncthreads(); else named_bar_sync(BAR, NT);
+  if constexpr (BAR == 0) __syncthreads();
+  else if constexpr (BAR < 0) named_bar_sync(1 + (int)threadIdx.x / NT, NT);
+  else named_bar_sync(BAR, NT);
 }
 template <int NW, int BAR> __device__ __forceinline__ float rp16_team_sum(float v, float* red /* NW floats */, int tid) {
 #pragma unroll

@@ -3,6 +3,10 @@ the public Python API (which calls the C ABI).  Run on the B200 box: pytest -m g
 
 Bar (BASELINE.json): rel-L2 <= 1e-5 for floating point; mask and crop indexing bit-exact.
 """
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -532,3 +536,23 @@ def test_reference_signature_twins():
     oa, ob = O.center_crop_to_smallest(a.numpy(), b.numpy())
     np.testing.assert_array_equal(ra.numpy(), oa)
     np.testing.assert_array_equal(rb.numpy(), ob)
+
+
+_EXP_LIB = os.path.join(os.path.dirname(cabi.DEFAULT_LIBRARY), "libmriacl_recon_exp.so")
+
+
+@pytest.mark.skipif(not os.path.exists(_EXP_LIB), reason="experimental library not built (make -C csrc experimental)")
+@pytest.mark.parametrize("env", [
+    {"MRIACL_CP_TMA": "2", "MRIACL_CT_SLOTS": "4"},                         # stand-alone TMA column pass, two teams
+    {"MRIACL_CP_TMA": "1"},                                                 # one team per CTA, two CTAs per SM
+    {"MRIACL_SCHEDULE": "coresident", "MRIACL_KC_TMA": "1"},                # TMA column teams + row team in one CTA
+    {"MRIACL_SCHEDULE": "coresident", "MRIACL_KC_TMA": "1", "MRIACL_KC_RING": "12"},
+    {"MRIACL_SCHEDULE": "coresident", "MRIACL_KC_SPLIT_SM": "64"},          # column SMs / row SMs, ring of 16 T slots
+], ids=["tma2", "tma1", "cores_tma", "cores_tma_ring", "sm_split"])
+def test_tma_experimental_schedules(env):
+    """the TMA band gather (colpass640_tma.cuh) under the three schedules built on it gives the oracle's images: the
+    schedules read their knobs once per process, so each runs in its own interpreter (tests/_tma_schedule_check.py)."""
+    e = dict(os.environ, MRIACL_RECON_LIBRARY=_EXP_LIB, **env)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_tma_schedule_check.py")],
+                       env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().startswith("OK"), r.stdout[-2000:] + r.stderr[-4000:]
