@@ -101,7 +101,8 @@ int ensure_smem_attrs(int dev) {
   bad |= rt_allow_smem((const void*)rowpass16_kernel<FUSED_P, FUSED_Q, 12, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<W372_P, W372_Q, W372_NW, 2>, SMEM_MAX / 2);
   bad |= rt_allow_smem((const void*)rowpass16_kernel<W400_P, W400_Q, W400_NW, 2>, SMEM_MAX / 2);
-  bad |= rt_allow_smem((const void*)rowpass640_kernel, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass640_kernel<false>, SMEM_MAX);
+  bad |= rt_allow_smem((const void*)rowpass640_kernel<true>, SMEM_MAX);
   bad |= rt_allow_smem((const void*)rowpass_generic_kernel, SMEM_MAX);
 #ifdef MRIACL_EXPERIMENTAL
   const int cp_carve = env_int("MRIACL_CP_CARVEOUT", -1);
@@ -229,7 +230,7 @@ struct FusedPlanDev {
   int* item_band = nullptr; int* item_j0 = nullptr;   //            band's first active column (j0_of_item has one entry more)
   int* sched_p8 = nullptr; int* sched_p12 = nullptr; cf* sptw16_dev = nullptr; int* rp16_slot_dev = nullptr;
   int* act_logical = nullptr;      // pruned generic row pass: logical index of active column j in the padded line
-  int* r640_off = nullptr; int* r640_ent = nullptr; int* r640_perm = nullptr;
+  int* r640_off = nullptr; int* r640_ent = nullptr; int* r640_perm = nullptr; int* r640_upos = nullptr;
   cf* twH = nullptr; cf* twW = nullptr; cf* twW_fwd = nullptr;     // (shared twiddle cache entries, kept alive by `owned`)
 #ifdef MRIACL_EXPERIMENTAL
   FusedPlanHost host_ovl;        // schedule for RP_NW_OVL warps (same columns, same sptw)
@@ -302,6 +303,7 @@ PlanPtr get_fused_plan(int dev, int H, int W, int pad_left, int Wp, int oh, int 
       build_row640_plan(pl->host, pl->r640);
       if (!pl->put(pl->r640.pos_off, pl->r640_off) || !pl->put(pl->r640.ent, pl->r640_ent) ||
           !pl->put(pl->r640.perm, pl->r640_perm)) return nullptr;
+      if (!pl->r640.upos.empty() && !pl->put(pl->r640.upos, pl->r640_upos)) return nullptr;
     }
 #ifdef MRIACL_EXPERIMENTAL
     build_fused_plan(H, W, pad_left, Wp, oh, ow, mask, planP, planQ, RP_NW_OVL, RP_MAX_SPARSE, /*split_dense=*/true, pl->host_ovl);
@@ -537,7 +539,9 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
   int rg_lines = 8;        // pruned generic row pass: lines per item, halved until the two line buffers + tiles fit
   const std::vector<int> rad = generic_radices(a.Wp);
   while (!wide640 && rg_lines > 1 && rowgen_smem_bytes(a.Wp, rg_lines, a.ow, (int)rad.size()) > SMEM_MAX / 3) rg_lines /= 2;
-  const int smem = wide640 ? row640_smem_bytes(std::max(1, n_act), n_ent, a.ow) : rowgen_smem_bytes(a.Wp, rg_lines, a.ow, (int)rad.size());
+  // balanced first pass when at most three quarters of the 80 butterfly positions hold samples (undersampled + padded plans)
+  const int n_upos = wide640 && pl->r640_upos && pl->r640.upos.size() <= 60 ? (int)pl->r640.upos.size() : 0;
+  const int smem = wide640 ? row640_smem_bytes(std::max(1, n_act), n_ent, a.ow, n_upos) : rowgen_smem_bytes(a.Wp, rg_lines, a.ow, (int)rad.size());
   if (smem > SMEM_MAX) return fail(MRIACL_ERR_UNSUPPORTED, "row pass does not fit shared memory (Wp=%d n_act=%d ow=%d)", a.Wp, n_act, a.ow);
   if (!wide640 && (int)rad.size() > RG_MAX_STAGES) return fail(MRIACL_ERR_UNSUPPORTED, "too many FFT stages for N=%d", a.Wp);
   const int n_tiles_row = wide640 ? g.n_tiles8 : (a.oh + rg_lines - 1) / rg_lines;
@@ -568,10 +572,12 @@ int run_fused640(const FusedArgs& a, const ReconGeom& g) {
       Row640Params q{};
       q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;
       q.pos_off = pl->r640_off; q.ent = pl->r640_ent; q.n_ent = n_ent; q.perm = pl->r640_perm; q.tw = pl->twW;
+      q.upos = pl->r640_upos; q.n_upos = n_upos;
       q.out = out_s0; q.partials = partials; q.ow = a.ow; q.col0 = col0;
       q.A = a.A; q.C = a.C; q.scale = scale;
       q.n_slices = ns; q.n_tiles = n_tiles_row;
-      MRIACL_LAUNCH(rowpass640_kernel, std::min(ns * n_tiles_row, per_sm * a.sms), R640_T, smem, a.st, q);
+      if (n_upos > 0) MRIACL_LAUNCH(rowpass640_kernel<true>, std::min(ns * n_tiles_row, per_sm * a.sms), R640_T, smem, a.st, q);
+      else MRIACL_LAUNCH(rowpass640_kernel<false>, std::min(ns * n_tiles_row, per_sm * a.sms), R640_T, smem, a.st, q);
     } else {
       RowGenParams q{};
       q.T = T; q.n_act = n_act; q.oh = a.oh; q.ohp = ohp;

@@ -369,6 +369,7 @@ struct Row640PlanHost {
   std::vector<int> pos_off;   // [81]
   std::vector<int> ent;
   std::vector<int> perm;      // [160] first-pass position of thread tid: warps see one kind of butterfly where possible
+  std::vector<int> upos;      // non-empty positions, most entries first: first-pass unit u = (upos[u / 8], line u % 8)
 };
 
 inline void build_row640_plan(const FusedPlanHost& pl, Row640PlanHost& rp) {
@@ -416,6 +417,14 @@ inline void build_row640_plan(const FusedPlanHost& pl, Row640PlanHost& rp) {
     for (int i = 0; i < 80; ++i) if (order[i] < 0) { while (seen[fill]) ++fill; order[i] = fill; seen[fill] = 1; }
     for (int i = 0; i < 80; ++i) rp.perm[80 * sub + i] = order[i];
   }
+  // Balanced first pass (undersampled plans): only the non-empty positions are work, and there are few of them (8x mask
+  // + padding: 26 of 80), so (position, line) units are dealt round-robin to ALL threads instead of a fixed position per
+  // thread; sorted by entry count so that the threads of a warp run the same number of inner iterations.
+  rp.upos.clear();
+  for (int pos = 0; pos < 80; ++pos) if (rp.pos_off[pos + 1] > rp.pos_off[pos]) rp.upos.push_back(pos);
+  std::stable_sort(rp.upos.begin(), rp.upos.end(), [&](int a, int b) {
+    return rp.pos_off[a + 1] - rp.pos_off[a] > rp.pos_off[b + 1] - rp.pos_off[b];
+  });
 }
 
 // FNV-1a over the plan-defining inputs: cache key for device-resident plans

@@ -33,6 +33,8 @@ struct Row640Params {
   const int* ent;              // per entry: n1 | (j << 3)
   int n_ent;
   const int* perm;             // [160] first-pass position of thread tid (plan.h: kinds of butterfly grouped per warp)
+  const int* upos;             // [n_upos] non-empty first-pass positions, most entries first (plan.h)
+  int n_upos;                  // 0: fixed position per thread (dense plans); > 0: balanced first pass over (position, line) units
   const cf* tw;                // w640^k = exp(+2 pi i k / 640)
   float* out;                  // [n_slices][oh][ow]
   float* partials;             // [n_slices][n_tiles][3] or nullptr
@@ -42,9 +44,12 @@ struct Row640Params {
   int n_slices, n_tiles;       // n_tiles = ceil(oh / 8)
 };
 
-__host__ __device__ inline int row640_smem_bytes(int n_act, int n_ent, int ow) {
-  return CP_BUF * 8 + 2 * n_act * R640_ROWS * 8 + R640_ROWS * (ow + 1) * 4 + ((81 + n_ent + 3) / 4) * 16 + 8 * 8;   // (perm is read once from global)
+__host__ __device__ inline int row640_smem_bytes(int n_act, int n_ent, int ow, int n_upos = 0) {
+  return CP_BUF * 8 + 2 * n_act * R640_ROWS * 8 + R640_ROWS * (ow + 1) * 4 + ((81 + n_ent + 3) / 4) * 16 + 8 * 8 +   // (perm is read once from global)
+         n_upos * (8 * 8 + 16);      // balanced first pass: per non-empty position 8 twiddles + (pos, e0, e1, -)
 }
+
+struct __align__(16) R640Unit { int pos, e0, e1, pad; };     // one non-empty first-pass position: entries ent[e0 .. e1)
 
 template <int NW> __device__ __forceinline__ float r640_block_sum(float v, float* red) {
 #pragma unroll
@@ -58,6 +63,8 @@ template <int NW> __device__ __forceinline__ float r640_block_sum(float v, float
   return t;
 }
 
+// BAL: balanced first pass over (non-empty position, line) units (p.n_upos > 0); otherwise a fixed position per thread
+template <bool BAL>
 __global__ void __launch_bounds__(R640_T, 3) rowpass640_kernel(Row640Params p) {
   MRIACL_DYN_SMEM(unsigned char, smem_raw);
   cf* buf = reinterpret_cast<cf*>(smem_raw);                                  // transform buffer, 8 lines
@@ -65,6 +72,8 @@ __global__ void __launch_bounds__(R640_T, 3) rowpass640_kernel(Row640Params p) {
   float* avsm = reinterpret_cast<float*>(stage + 2 * (size_t)p.n_act * R640_ROWS);   // [8][ow + 1]
   int* plan = reinterpret_cast<int*>(avsm + R640_ROWS * (p.ow + 1));          // pos_off[81] | ent[n_ent]
   cf* w8sm = reinterpret_cast<cf*>(plan + ((81 + p.n_ent + 3) / 4) * 4);      // w8^k, k = 0..7
+  cf* utw = w8sm + 8;                                                         // [n_upos][8]: w640^{pos m}, m = 0..7
+  R640Unit* uinfo = reinterpret_cast<R640Unit*>(utw + 8 * (size_t)p.n_upos);  // [n_upos]
   __shared__ float red[R640_T / 32];
 
   const int tid = threadIdx.x;
@@ -72,14 +81,20 @@ __global__ void __launch_bounds__(R640_T, 3) rowpass640_kernel(Row640Params p) {
   for (int i = tid; i < 81; i += R640_T) plan[i] = p.pos_off[i];
   for (int i = tid; i < p.n_ent; i += R640_T) plan[81 + i] = p.ent[i];
   if (tid < 8) w8sm[tid] = p.tw[80 * tid];
+  for (int i = tid; i < 8 * p.n_upos; i += R640_T) utw[i] = p.tw[(p.upos[i >> 3] * (i & 7)) % CP_N];
+  for (int i = tid; i < p.n_upos; i += R640_T) {
+    const int ps = p.upos[i];
+    uinfo[i] = R640Unit{ps, p.pos_off[ps], p.pos_off[ps + 1], 0};
+  }
+  const int n_units = p.n_upos * R640_ROWS;
   cf tw1[8], tw2[8];
-  const int pos1 = p.perm[tid];                                // first pass: my butterfly position (grouped by kind)
+  const int pos1 = BAL ? 0 : p.perm[tid];                      // first pass: my butterfly position (grouped by kind)
   const int base2 = (pos / 10) * CP_BLK + (pos % 10);          // second pass: (m1, n3) = (pos / 10, pos % 10)
   {
     const int n3 = pos % 10;
 #pragma unroll
     for (int m = 1; m < 8; ++m) {
-      tw1[m] = p.tw[(pos1 * m) % CP_N];
+      if (!BAL) tw1[m] = p.tw[(pos1 * m) % CP_N];
       tw2[m] = p.tw[(8 * n3 * m) % CP_N];
     }
   }
@@ -135,6 +150,41 @@ __global__ void __launch_bounds__(R640_T, 3) rowpass640_kernel(Row640Params p) {
       const cf* st = stage + (size_t)(f & 1) * tile_elems;
 
       // ---- pass 1: expanding radix-8 over n1 (stride 90), twiddle w640^{pos * m1} ----
+      if (BAL) {
+        // balanced: (non-empty position, line) units dealt to all threads; the unit's twiddles come from shared memory
+        for (int u = tid; u < n_units; u += R640_T) {
+          const int q = u >> 3, kc = u & 7;
+          const R640Unit inf = uinfo[q];
+          const cf* twq = utw + 8 * q;
+          cf* col = buf + kc * CP_PITCH + inf.pos;
+          if (inf.e1 - inf.e0 == 8) {
+            cf v[8];
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) v[n1] = st[(ent[inf.e0 + n1] >> 3) * R640_ROWS + kc];
+            radix8<true>(v);
+            col[0] = v[0];
+#pragma unroll
+            for (int m1 = 1; m1 < 8; ++m1) col[m1 * CP_BLK] = cmul(v[m1], twq[m1]);
+          } else {
+            cf y[8];
+#pragma unroll
+            for (int m1 = 0; m1 < 8; ++m1) y[m1] = cf_make(0.f, 0.f);
+            for (int e = inf.e0; e < inf.e1; ++e) {
+              const int n1 = ent[e] & 7;
+              const cf x = st[(ent[e] >> 3) * R640_ROWS + kc];
+              y[0] = cadd(y[0], x);
+#pragma unroll
+              for (int m1 = 1; m1 < 8; ++m1) {
+                const cf w = w8sm[(n1 * m1) & 7];
+                y[m1] = pk_fma(mul_i<true>(x), bc(w.y), pk_fma(x, bc(w.x), y[m1]));
+              }
+            }
+            col[0] = y[0];
+#pragma unroll
+            for (int m1 = 1; m1 < 8; ++m1) col[m1 * CP_BLK] = cmul(y[m1], twq[m1]);
+          }
+        }
+      } else
       for (int kc = sub; kc < R640_ROWS; kc += 2) {
         cf* col = buf + kc * CP_PITCH + pos1;
         if (cnt == 0) {
