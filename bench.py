@@ -542,12 +542,16 @@ def ours(args) -> None:
         packed_ranks = int(sum_over_ranks(1.0 if pipe.pack else 0.0))
     else:
         packed_ranks = world if pipe.pack else 0
-    e2e_modes = {("packed" if pipe.pack else "direct"): head}
+    head_mode = "direct" if not pipe.pack else ("packed" if not pipe.direct_every else "mixed")
+    e2e_modes = {head_mode: head}
     if pack_arg == "auto":
-        other = HostPipeline((C, H, W), CROP, "instance", 0.0, sub_batch=args.sub_batch, n_streams=args.e2e_streams,
-                             pack=not pipe.pack, pack_threads=args.pack_threads)
-        e2e_modes["direct" if pipe.pack else "packed"] = e2e_run(other, max(2, e2e_steps // 2))
-        del other
+        for name, pk in (("direct", False), ("packed", True)):      # the pure modes beside the one "auto" chose
+            if name in e2e_modes:
+                continue
+            other = HostPipeline((C, H, W), CROP, "instance", 0.0, sub_batch=args.sub_batch, n_streams=args.e2e_streams,
+                                 pack=pk, pack_threads=args.pack_threads)
+            e2e_modes[name] = e2e_run(other, max(2, e2e_steps // 2))
+            del other
         pipe(k_host, mask, out_host, ms_host)          # the parity check below reads the headline mode's output
         torch.cuda.synchronize()
     e2e_ms, e2e_value = head["ms_per_step"] * e2e_steps, head["value"]
@@ -628,8 +632,9 @@ def ours(args) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "sub_batch": args.sub_batch, "streams": args.e2e_streams,
                     "api": "recon.pipeline.HostPipeline (pinned host k-space -> host images), one cudaMemcpyAsync per sub-batch; "
-                           "packed = host threads gather the sampled columns first, so only they cross PCIe (bit-identical images)",
-                    "mode": "packed" if pipe.pack else "direct", "pack_arg": args.e2e_pack, "ranks_packed": packed_ranks,
+                           "packed = host threads gather the sampled columns first, so only they cross PCIe (bit-identical images); "
+                           "mixed = every direct_every-th sub-batch goes across full width while the host gathers the others",
+                    "mode": head_mode, "direct_every": pipe.direct_every, "pack_arg": args.e2e_pack, "ranks_packed": packed_ranks,
                     "pack_calibration": pipe.calibration, "modes": e2e_modes,
                     "host_kspace_gbs": e2e_value * C * H * W * 8 / 1e9,
                     "h2d_gbs": h2d_gbs, "h2d_ceiling_gbs": h2d_ceiling,
@@ -779,7 +784,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--chunk", type=int, default=0, help="slices in flight per launch group (0 = library default)")
-    ap.add_argument("--sub-batch", type=int, default=32, help="slices per host->device copy in the e2e pipeline")
+    ap.add_argument("--sub-batch", type=int, default=16, help="slices per host->device copy in the e2e pipeline")
     ap.add_argument("--e2e-streams", type=int, default=2)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--pack-threads", type=int, default=0, help="host threads of the column gather (0 = one per core)")

@@ -15,7 +15,10 @@ Two ways of getting a sub-batch onto the device (``pack``):
   packed layout (``MRIACL_PACKED_COLUMNS``).  The arithmetic sees the same values: images are bit-identical.  The
   host gather is bound by host memory bandwidth, so which mode wins depends on the box and on how many ranks share
   its memory system;
-* ``"auto"`` (default) times both on the first call and keeps the faster.
+* mixed       packing is bound by host memory reads and leaves PCIe half idle, the direct copy is bound by PCIe and leaves
+  the host idle: with ``direct_every = k`` every k-th sub-batch (the first of each group) goes across full width while the
+  host threads gather the columns of the following ones, so both resources work at the same time;
+* ``"auto"`` (default) times direct, packed and the mixed patterns on the first call and keeps the fastest.
 """
 from __future__ import annotations
 
@@ -32,7 +35,7 @@ from .cartesian import zero_filled_rss
 class HostPipeline:
     def __init__(self, slice_shape: Tuple[int, int, int], crop: Tuple[int, int] = (320, 320),
                  normalize: Optional[str] = "instance", eps: float = 0.0, sub_batch: int = 8, n_streams: int = 2,
-                 pack: Any = "auto", pack_threads: int = 0, collective_calibration: bool = False):
+                 pack: Any = "auto", pack_threads: int = 0, collective_calibration: bool = False, direct_every: int = 0):
         dev = D.require_cuda()
         if pack not in (True, False, "auto"):
             raise ValueError("pack must be True, False or 'auto'")
@@ -50,7 +53,8 @@ class HostPipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.pack_s = self.wait_s = 0.0   # host seconds of the last call spent gathering columns / waiting for a staging buffer
-        self.calibration = None      # {"direct_s": ..., "packed_s": ...} once "auto" has decided
+        self.direct_every = int(direct_every) if pack is True else 0   # packed mode: every direct_every-th sub-batch is copied full width instead (0 = none)
+        self.calibration = None      # {"direct_s": ..., "packed_s": ..., "mixed_s": {k: ...}} once "auto" has decided
 
     # ---- buffers -------------------------------------------------------------------------------------------------
     def _full_stage(self):
@@ -72,7 +76,7 @@ class HostPipeline:
         return self.pstage
 
     # ---- one pass over the batch ---------------------------------------------------------------------------------
-    def _run(self, kspace_host, m, out_host, mean_std_host, packed: bool):
+    def _run(self, kspace_host, m, out_host, mean_std_host, packed: bool, direct_every: int = 0):
         S = kspace_host.shape[0]
         c, h, w = self.slice_shape
         cur = torch.cuda.current_stream()
@@ -83,12 +87,14 @@ class HostPipeline:
         if packed:
             _, pinned, device, events, n_act = self._packed_stage(m)
             self.pack_s = self.wait_s = 0.0
-        else:
+        if not packed or direct_every:
             stage = self._full_stage()
+        all_packed = packed
         for i, s0 in enumerate(range(0, S, self.sub)):
             n = min(self.sub, S - s0)
             b = i % len(self.streams)
             st = self.streams[b]
+            packed = all_packed and not (direct_every and i % direct_every == 0)
             if packed:
                 t0 = time.perf_counter()
                 if events[b] is not None:
@@ -133,26 +139,37 @@ class HostPipeline:
 
     def _calibrate(self, kspace_host, m, out_host, mean_std_host):
         """Time one pass of each mode on (at most) the first four sub-batches; keep the faster."""
-        n = min(kspace_host.shape[0], 4 * self.sub)
-        times = {}
-        for packed in (False, True):
-            self._run(kspace_host[:n], m, out_host[:n], None if mean_std_host is None else mean_std_host[:n], packed)   # warm
+        n_sub = (kspace_host.shape[0] + self.sub - 1) // self.sub
+        n = min(kspace_host.shape[0], (8 if n_sub >= 8 else 4) * self.sub)
+        n_sub = (n + self.sub - 1) // self.sub
+        # candidates: (packed, direct_every); a mixed pattern needs at least one packed sub-batch per direct one
+        cands = [(False, 0), (True, 0)] + [(True, k) for k in (8, 6, 4, 3, 2) if 2 <= k <= n_sub]
+        times = []
+        ms = None if mean_std_host is None else mean_std_host[:n]
+        for packed, k in cands:
+            self._run(kspace_host[:n], m, out_host[:n], ms, packed, k)   # warm
             torch.cuda.current_stream().synchronize()
             t0 = time.perf_counter()
-            self._run(kspace_host[:n], m, out_host[:n], None if mean_std_host is None else mean_std_host[:n], packed)
+            self._run(kspace_host[:n], m, out_host[:n], ms, packed, k)
             torch.cuda.current_stream().synchronize()
-            times[packed] = time.perf_counter() - t0
-        self.calibration = {"direct_s": times[False], "packed_s": times[True], "slices": n}
+            times.append(time.perf_counter() - t0)
+        self.calibration = {"direct_s": times[0], "packed_s": times[1], "mixed_s": {str(k): t for (_, k), t in zip(cands[2:], times[2:])},
+                            "slices": n}
         if self.collective:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
-                t = torch.tensor([times[False], times[True]], dtype=torch.float64, device=self.dev)
+                t = torch.tensor(times, dtype=torch.float64, device=self.dev)
                 dist.all_reduce(t)
-                times = {False: float(t[0]), True: float(t[1])}
-                self.calibration.update(direct_s_all_ranks=times[False], packed_s_all_ranks=times[True])
-        self.pack = times[True] < times[False]
+                times = [float(x) for x in t]
+                self.calibration.update(direct_s_all_ranks=times[0], packed_s_all_ranks=times[1],
+                                        mixed_s_all_ranks={str(k): tt for (_, k), tt in zip(cands[2:], times[2:])})
+        best = min(range(len(cands)), key=lambda i: times[i])
+        self.pack, self.direct_every = cands[best]
+        self.calibration["chosen"] = "direct" if not self.pack else ("packed" if not self.direct_every else f"mixed, every {self.direct_every}th sub-batch direct")
         if not self.pack:
             self.pstage = None                            # release the pinned staging buffers
+        elif not self.direct_every:
+            self.stage = None
 
     def __call__(self, kspace_host: torch.Tensor, mask: Any, out_host: torch.Tensor,
                  mean_std_host: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -173,7 +190,7 @@ class HostPipeline:
         if packed == "auto":
             self._calibrate(kspace_host, m, out_host, mean_std_host)
             packed = self.pack
-        return self._run(kspace_host, m, out_host, mean_std_host, bool(packed))
+        return self._run(kspace_host, m, out_host, mean_std_host, bool(packed), self.direct_every if packed else 0)
 
 
 def zero_filled_rss_host(kspace_host: Any, mask: Any = None, crop: Tuple[int, int] = (320, 320),

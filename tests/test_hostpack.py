@@ -50,18 +50,24 @@ def test_packed_pipeline_is_bit_identical():
     outs = {}
     for m in (synth.knee_mask(), synth.equispaced_mask(368, 8, 0.04), synth.equispaced_mask(368, 4, 0.08, 3)):
         dev_img, dev_mean, dev_std = zero_filled_rss(torch.from_numpy(k_np).cuda(), m, synth.CROP, "instance")
-        for pack in (False, True, "auto"):
+        for pack, every in ((False, 0), (True, 0), ("auto", 0), (True, 2), (True, 3)):
+            # (True, k): mixed transfer, sub-batches 0, k, 2k, ... go across full width, the others packed
             out = torch.empty((11,) + synth.CROP, dtype=torch.float32).pin_memory()
             ms = torch.empty((11, 2), dtype=torch.float32).pin_memory()
-            pipe = HostPipeline(synth.KNEE_SHAPE, synth.CROP, "instance", 0.0, sub_batch=4, n_streams=2, pack=pack)
-            pipe(k_host.pin_memory() if pack is False else k_host, m, out, ms)
+            pipe = HostPipeline(synth.KNEE_SHAPE, synth.CROP, "instance", 0.0, sub_batch=2 if every else 4, n_streams=2, pack=pack,
+                                direct_every=every)
+            pipe(k_host.pin_memory() if pack is False or every else k_host, m, out, ms)
+            if every:
+                n_direct = len(range(0, 6, every))                  # six sub-batches of two slices (the last holds one)
+                n_act = int(np.count_nonzero(m))
+                assert pipe.h2d_bytes == (2 * n_direct * 368 + (11 - 2 * n_direct) * n_act) * 15 * 640 * 8
             torch.cuda.synchronize()
             assert torch.equal(out, dev_img.cpu()), f"pack={pack}"
             assert torch.equal(ms[:, 0], dev_mean.cpu()) and torch.equal(ms[:, 1], dev_std.cpu())
-            if pack is True:
+            if pack is True and not every:
                 assert pipe.h2d_bytes == 11 * 15 * 640 * int(np.count_nonzero(m)) * 8
             if pack == "auto":
-                assert pipe.calibration is not None and pipe.pack in (True, False)
+                assert pipe.calibration is not None and pipe.pack in (True, False) and "chosen" in pipe.calibration
         want, _, _ = O.knee_chain_numpy(k_np[10], m, synth.CROP, "instance")
         assert O.rel_l2(out[10].numpy(), want) <= 1e-5
 
