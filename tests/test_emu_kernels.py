@@ -197,6 +197,24 @@ def test_fused_640_wide_plan(emu):
     assert O.rel_l2(raw[0], oracle(synth.prostate_mask(), (77, 200))) <= TOL
 
 
+def test_640_wide_balanced_first_pass_mixed_kinds(emu):
+    """640-wide plan without padding whose mask makes the balanced first pass (at most 60 of the 80 butterfly positions hold
+    samples) meet both kinds of unit: positions with all eight inputs (regular radix-8) and positions with a few (direct sum),
+    weighted columns included."""
+    k = synth.gaussian_kspace((1, 1, 2, 640, 640), 43)
+    m = np.zeros(640, np.float32)
+    for pos in range(0, 10):                       # logical n = 80 n1 + pos for every n1: full positions
+        for n1 in range(8):
+            m[(80 * n1 + pos + 320) % 640] = 1.0
+    for pos in range(20, 45):                      # three inputs each, weighted
+        for n1 in (1, 4, 6):
+            m[(80 * n1 + pos + 320) % 640] = 0.5 + 0.01 * pos
+    out, _ = recon(emu, k, m, (48, 320), 0)
+    kk = O.apply_mask(k[0, 0], m)
+    want = O.center_crop(np.sqrt((O.complex_abs(O.ifft2c(kk)) ** 2).sum(0)), (48, 320)).astype(np.float32)
+    assert O.rel_l2(out[0], want) <= TOL
+
+
 @pytest.mark.parametrize("W", [372, 400, 320])
 def test_other_knee_widths(emu, W):
     """H = 640 with the other knee widths: 372 = 31 x 12 and 400 = 25 x 16 run the 16-row row pass with a 31- / 25-point

@@ -556,3 +556,24 @@ def test_tma_experimental_schedules(env):
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_tma_schedule_check.py")],
                        env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().startswith("OK"), r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_640_wide_balanced_first_pass_mixed_kinds():
+    """the balanced first pass of rowpass640_kernel<true> (at most 60 of the 80 butterfly positions hold samples) with both
+    kinds of unit in one plan: positions with all eight inputs and positions with three weighted ones; several slices and
+    coils so that every CTA takes more than one item."""
+    k = synth.gaussian_kspace((3, 4, 640, 640), 43)
+    m = np.zeros(640, np.float32)
+    for pos in range(0, 10):
+        for n1 in range(8):
+            m[(80 * n1 + pos + 320) % 640] = 1.0
+    for pos in range(20, 45):
+        for n1 in (1, 4, 6):
+            m[(80 * n1 + pos + 320) % 640] = 0.5 + 0.01 * pos
+    img, mean, std = zero_filled_rss(torch.from_numpy(k).cuda(), m, synth.CROP, "instance")
+    ref, rmean, rstd = O.knee_chain_numpy(k, m, synth.CROP, "instance")
+    for s in range(3):
+        assert O.rel_l2(img[s].cpu().numpy(), ref[s]) <= TOL
+    np.testing.assert_allclose(mean.cpu().numpy(), rmean, rtol=1e-5)
+    gen, _, _ = zero_filled_rss(torch.from_numpy(k).cuda(), m, synth.CROP, "instance", force_generic=True)
+    torch.testing.assert_close(gen, img, rtol=0, atol=2e-5)
