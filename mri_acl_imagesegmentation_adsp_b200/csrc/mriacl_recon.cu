@@ -1421,9 +1421,27 @@ static int post_allow_smem() {          // once per device: the percentile kerne
   const int dev = rt_device();
   std::lock_guard<std::mutex> lk(mu);
   if (done[dev]) return 0;
-  if (rt_allow_smem((const void*)percentile_clip_kernel, POST_HIST_BYTES)) return 1;
+  if (rt_allow_smem((const void*)percentile_clip_kernel<1>, POST_HIST_BYTES) || rt_allow_smem((const void*)percentile_clip_kernel<2>, POST_HIST_BYTES) ||
+      rt_allow_smem((const void*)percentile_clip_kernel<4>, POST_HIST_BYTES)) return 1;
   done[dev] = true;
   return 0;
+}
+// CTAs per image of the one-image kernels (thread-block cluster size): as many as keep B clusters within one wave
+static int post_cluster_size(int B) {
+  const int sms = device_sms(rt_device());
+  return 4 * B <= sms ? 4 : 2 * B <= sms ? 2 : 1;
+}
+static void launch_percentile(const PercentileParams& p, int B, rt_stream_t st) {
+  const int cl = post_cluster_size(B);
+  if (cl == 4) MRIACL_LAUNCH(percentile_clip_kernel<4>, 4 * B, POST_T, POST_HIST_BYTES, st, p);
+  else if (cl == 2) MRIACL_LAUNCH(percentile_clip_kernel<2>, 2 * B, POST_T, POST_HIST_BYTES, st, p);
+  else MRIACL_LAUNCH(percentile_clip_kernel<1>, B, POST_T, POST_HIST_BYTES, st, p);
+}
+static void launch_zscore(const ZscoreParams& p, int B, rt_stream_t st) {
+  const int cl = post_cluster_size(B);
+  if (cl == 4) MRIACL_LAUNCH(zscore_preview_kernel<4>, 4 * B, POST_T, 0, st, p);
+  else if (cl == 2) MRIACL_LAUNCH(zscore_preview_kernel<2>, 2 * B, POST_T, 0, st, p);
+  else MRIACL_LAUNCH(zscore_preview_kernel<1>, B, POST_T, 0, st, p);
 }
 #endif
 
@@ -1437,7 +1455,7 @@ int mriacl_percentile_clip_f32(const float* in, float* out, float* lo_hi, int B,
   if (!in || (!out && !lo_hi)) return fail(MRIACL_ERR_INVALID, "null pointer");
   PercentileParams p{in, out, lo_hi, (long long)n, pmin, pmax};
   if (post_allow_smem()) return fail(MRIACL_ERR_CUDA, "cudaFuncSetAttribute failed: %s", rt_last_error_string());
-  MRIACL_LAUNCH(percentile_clip_kernel, B, POST_T, POST_HIST_BYTES, (rt_stream_t)cuda_stream, p);
+  launch_percentile(p, B, (rt_stream_t)cuda_stream);
   if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
   return MRIACL_OK;
 #endif
@@ -1477,7 +1495,7 @@ int mriacl_zscore_preview_f32(const float* in, const uint8_t* mask, float* out_z
   if (B == 0) return MRIACL_OK;
   if (!in || (!out_z && !out_01 && !stats)) return fail(MRIACL_ERR_INVALID, "null pointer");
   ZscoreParams p{in, mask, out_z, out_01, stats, (long long)n};
-  MRIACL_LAUNCH(zscore_preview_kernel, B, POST_T, 0, (rt_stream_t)cuda_stream, p);
+  launch_zscore(p, B, (rt_stream_t)cuda_stream);
   if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
   return MRIACL_OK;
 #endif
@@ -1497,7 +1515,7 @@ int mriacl_clip_resize_zscore_f32(const float* img, const uint8_t* body_mask, fl
   // 1. exact percentiles of every full-resolution image (the clipped image itself is never materialised)
   PercentileParams pp{img, nullptr, clip_lo_hi, (long long)H * W, pmin, pmax};
   if (post_allow_smem()) return fail(MRIACL_ERR_CUDA, "cudaFuncSetAttribute failed: %s", rt_last_error_string());
-  MRIACL_LAUNCH(percentile_clip_kernel, B, POST_T, POST_HIST_BYTES, st, pp);
+  launch_percentile(pp, B, st);
   // 2. clip every tap, interpolate to (out_h, out_w); the mask goes through the same interpolation and a 0.5 threshold
   ResizeParams ri{img, nullptr, out_z, nullptr, clip_lo_hi, B, H, W, out_h, out_w};
   MRIACL_LAUNCH(resize_bilinear_kernel, grid_for((long long)B * out_h * out_w, 256), 256, 0, st, ri);
@@ -1507,7 +1525,7 @@ int mriacl_clip_resize_zscore_f32(const float* img, const uint8_t* body_mask, fl
   }
   // 3. statistics inside the resized mask, z-score in place, preview
   ZscoreParams zp{out_z, body_mask ? out_mask : nullptr, out_z, out_01, stats, (long long)out_h * out_w};
-  MRIACL_LAUNCH(zscore_preview_kernel, B, POST_T, 0, st, zp);
+  launch_zscore(zp, B, st);
   if (rt_check()) return fail(MRIACL_ERR_CUDA, "kernel launch failed: %s", rt_last_error_string());
   return MRIACL_OK;
 #endif

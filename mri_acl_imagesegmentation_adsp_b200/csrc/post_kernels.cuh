@@ -15,10 +15,18 @@
 //  * z-score: mean and POPULATION standard deviation of the pixels inside the mask (of the whole image when fewer than
 //    ten are inside), std <= 1e-6 replaced by 1; preview: (x - lo) / float32(hi - lo + 1e-6) with lo / hi the extrema
 //    inside the mask (of the whole image when the mask is empty).  Statistics are accumulated in double.
+//
+// Both one-image kernels are bound by a single CTA's sweep of its image, and a batch of 64 images fills 64 of 148 SMs, so
+// they run as thread-block CLUSTERS: CL CTAs (1, 2 or 4, chosen so that B x CL fills the machine) share one image, each
+// sweeps 1/CL of it, and the per-CTA results (histograms, partial sums, extrema) are combined through distributed shared
+// memory -- every CTA reads its peers' shared memory (cluster.map_shared_rank) in rank order, so all of them continue from
+// bit-identical totals without a trip through global memory.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace mriacl {
+namespace cg = cooperative_groups;
 
 constexpr int POST_T = 1024;          // threads of the one-CTA-per-image kernels
 constexpr int POST_HIST_BYTES = 4 * 256 * 32 * 4;   // dynamic shared memory of percentile_clip_kernel
@@ -46,17 +54,22 @@ struct PercentileParams {
   float pmin, pmax;     // percent, 0..100
 };
 
-// one CTA per image
-__global__ void __launch_bounds__(POST_T) percentile_clip_kernel(PercentileParams p) {
+// one cluster of CL CTAs per image (grid = B * CL)
+template <int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(POST_T) percentile_clip_kernel(PercentileParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = CL > 1 ? (int)cluster.block_rank() : 0;
+  const int img = (int)blockIdx.x / CL;
   MRIACL_DYN_SMEM(unsigned, hist);          // [4 ranks][256 bins][32 lanes]: a lane owns its column, so the lanes of a warp never
                                             // meet on an address or a bank however the values cluster (POST_HIST_BYTES)
-  __shared__ unsigned folded[4][256];
+  __shared__ unsigned folded[4][256];       // this CTA's share of the image
+  __shared__ unsigned merged[4][256];       // the whole image (sum over the cluster, same values in every CTA)
   __shared__ unsigned prefix[4];
   __shared__ unsigned long long rank[4];
   __shared__ int alias[4];
   __shared__ float s_lo_hi[2];
   const int tid = threadIdx.x, lane = tid & 31;
-  const float* x = p.in + (long long)blockIdx.x * p.n;
+  const float* x = p.in + (long long)img * p.n;
   const long long n = p.n;
 
   // virtual indices in float32, exactly as numpy computes them
@@ -99,14 +112,15 @@ __global__ void __launch_bounds__(POST_T) percentile_clip_kernel(PercentileParam
     const bool vec = (n & 3) == 0 && ((reinterpret_cast<unsigned long long>(x) & 15ull) == 0);
     if (vec) {
       const float4* x4 = reinterpret_cast<const float4*>(x);
-      const long long n4 = n >> 2;
-      const long long n_iter = (n4 + (long long)POST_T * POST_ILP - 1) / ((long long)POST_T * POST_ILP);
+      const long long n4_all = n >> 2;
+      const long long lo4 = n4_all * crank / CL, n4 = n4_all * (crank + 1) / CL;     // this CTA's share [lo4, n4)
+      const long long n_iter = (n4 - lo4 + (long long)POST_T * POST_ILP - 1) / ((long long)POST_T * POST_ILP);
       for (long long it = 0; it < n_iter; ++it) {
         float4 v[POST_ILP];
         bool ok[POST_ILP];
 #pragma unroll
         for (int u = 0; u < POST_ILP; ++u) {
-          const long long i4 = (it * POST_ILP + u) * POST_T + tid;
+          const long long i4 = lo4 + (it * POST_ILP + u) * POST_T + tid;
           ok[u] = i4 < n4;
           v[u] = ok[u] ? x4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -117,10 +131,11 @@ __global__ void __launch_bounds__(POST_T) percentile_clip_kernel(PercentileParam
         }
       }
     } else {
-      const long long n_iter = (n + POST_T - 1) / POST_T;
+      const long long lo = n * crank / CL, hi = n * (crank + 1) / CL;
+      const long long n_iter = (hi - lo + POST_T - 1) / POST_T;
       for (long long it = 0; it < n_iter; ++it) {
-        const long long i = it * POST_T + tid;
-        count(i < n ? post_key(x[i]) : 0u, i < n);
+        const long long i = lo + it * POST_T + tid;
+        count(i < hi ? post_key(x[i]) : 0u, i < hi);
       }
     }
     __syncthreads();
@@ -130,14 +145,48 @@ __global__ void __launch_bounds__(POST_T) percentile_clip_kernel(PercentileParam
       for (int c = 0; c < 32; ++c) sum += hist[i * 32 + ((c + lane) & 31)];
       folded[i >> 8][i & 255] = sum;
     }
-    __syncthreads();
-    if (tid < 4) {
-      const unsigned* h = folded[alias[tid]];
-      unsigned long long r = rank[tid];
-      int b = 0;
-      for (; b < 255; ++b) { if (r < h[b]) break; r -= h[b]; }
-      rank[tid] = r;
-      prefix[tid] = (prefix[tid] << 8) | (unsigned)b;
+    if (CL > 1) {
+      cluster.sync();                                    // every CTA's folded histogram is complete
+      for (int i = tid; i < 4 * 256; i += POST_T) {
+        unsigned sum = 0;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) sum += cluster.map_shared_rank(&folded[0][0], r)[i];
+        merged[i >> 8][i & 255] = sum;
+      }
+      cluster.sync();                                    // ... and has been read by every peer before the next pass refills it
+    } else {
+      __syncthreads();
+      for (int i = tid; i < 4 * 256; i += POST_T) merged[i >> 8][i & 255] = folded[i >> 8][i & 255];
+      __syncthreads();
+    }
+    // bin of each rank: warp t scans histogram t (8 bins per lane, shuffle prefix sum) -- the bin b with
+    // cum(b) <= r < cum(b + 1), the last bin if r is beyond the total
+    if (tid < 128) {
+      const int t = tid >> 5;
+      const unsigned* h = merged[alias[t]];
+      unsigned c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = h[8 * lane + j]; sum += c[j]; }
+      unsigned inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      const unsigned long long r = rank[t];
+      const unsigned long long exc = (unsigned long long)(inc - sum);
+      const bool beyond = r >= (unsigned long long)__shfl_sync(0xffffffffu, inc, 31);
+      const bool here = beyond ? lane == 31 : (r >= exc && r < (unsigned long long)inc);
+      __syncwarp();
+      if (here) {
+        unsigned long long rr = r - exc;
+        int j = 0;
+        for (; j < 7; ++j) { if (rr < c[j]) break; rr -= c[j]; }
+        if (beyond) {                                    // (cannot happen with exact counts; same answer as the serial scan)
+          rr = r - exc; j = 0;
+          for (; j < 7; ++j) rr -= c[j];
+          j = 7;
+        }
+        rank[t] = rr;
+        prefix[t] = (prefix[t] << 8) | (unsigned)(8 * lane + j);
+      }
     }
     __syncthreads();
   }
@@ -145,13 +194,14 @@ __global__ void __launch_bounds__(POST_T) percentile_clip_kernel(PercentileParam
     const float a0 = post_unkey(prefix[0]), b0 = post_unkey(prefix[1]), a1 = post_unkey(prefix[2]), b1 = post_unkey(prefix[3]);
     s_lo_hi[0] = post_lerp(a0, b0, __fsub_rn(v_lo, f_lo));
     s_lo_hi[1] = post_lerp(a1, b1, __fsub_rn(v_hi, f_hi));
-    if (p.lo_hi) { p.lo_hi[2 * blockIdx.x] = s_lo_hi[0]; p.lo_hi[2 * blockIdx.x + 1] = s_lo_hi[1]; }
+    if (p.lo_hi && crank == 0) { p.lo_hi[2 * img] = s_lo_hi[0]; p.lo_hi[2 * img + 1] = s_lo_hi[1]; }
   }
   __syncthreads();
   if (p.out) {
     const float lo = s_lo_hi[0], hi = s_lo_hi[1];
-    float* y = p.out + (long long)blockIdx.x * n;
-    for (long long i = tid; i < n; i += POST_T) y[i] = fminf(fmaxf(x[i], lo), hi);      // np.clip = minimum(maximum(x, lo), hi)
+    float* y = p.out + (long long)img * n;
+    const long long i0 = n * crank / CL, i1 = n * (crank + 1) / CL;
+    for (long long i = i0 + tid; i < i1; i += POST_T) y[i] = fminf(fmaxf(x[i], lo), hi);      // np.clip = minimum(maximum(x, lo), hi)
   }
 }
 
@@ -219,21 +269,29 @@ template <class T, class Op> __device__ __forceinline__ T post_block_reduce(T v,
   return r;
 }
 
-// one CTA per image: three sweeps (count / sum / extrema -> mean; squared deviations -> std; outputs)
-__global__ void __launch_bounds__(POST_T) zscore_preview_kernel(ZscoreParams p) {
+// one cluster of CL CTAs per image (grid = B * CL): three sweeps (count / sum / extrema -> mean; squared deviations -> std;
+// outputs), each CTA over its share of the image; the partial results meet through distributed shared memory
+template <int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(POST_T) zscore_preview_kernel(ZscoreParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = CL > 1 ? (int)cluster.block_rank() : 0;
+  const int img = (int)blockIdx.x / CL;
   __shared__ double sd[32];
   __shared__ float sf[32];
+  __shared__ double xd[4];        // this CTA's partial count / sums, read by the peers
+  __shared__ float xf[4];         // ... and extrema
   const int tid = threadIdx.x;
   const long long n = p.n;
-  const float* x = p.in + (long long)blockIdx.x * n;
-  const unsigned char* m = p.mask ? p.mask + (long long)blockIdx.x * n : nullptr;
+  const long long i0 = n * crank / CL, i1 = n * (crank + 1) / CL;      // this CTA's share
+  const float* x = p.in + (long long)img * n;
+  const unsigned char* m = p.mask ? p.mask + (long long)img * n : nullptr;
   auto add = [](double a, double b) { return a + b; };
   auto fmn = [](float a, float b) { return fminf(a, b); };
   auto fmx = [](float a, float b) { return fmaxf(a, b); };
 
   double cnt_in = 0.0, sum_in = 0.0, sum_all = 0.0;
   float mn_in = INFINITY, mx_in = -INFINITY, mn_all = INFINITY, mx_all = -INFINITY;
-  for (long long i = tid; i < n; i += POST_T) {
+  for (long long i = i0 + tid; i < i1; i += POST_T) {
     const float v = x[i];
     sum_all += (double)v; mn_all = fminf(mn_all, v); mx_all = fmaxf(mx_all, v);
     if (!m || m[i] > 0) { cnt_in += 1.0; sum_in += (double)v; mn_in = fminf(mn_in, v); mx_in = fmaxf(mx_in, v); }
@@ -245,25 +303,47 @@ __global__ void __launch_bounds__(POST_T) zscore_preview_kernel(ZscoreParams p) 
   mx_in = post_block_reduce(mx_in, sf, fmx, -INFINITY);
   mn_all = post_block_reduce(mn_all, sf, fmn, INFINITY);
   mx_all = post_block_reduce(mx_all, sf, fmx, -INFINITY);
+  if (CL > 1) {                      // combine over the cluster, in rank order (every CTA arrives at the same values)
+    if (tid == 0) { xd[0] = cnt_in; xd[1] = sum_in; xd[2] = sum_all; xf[0] = mn_in; xf[1] = mx_in; xf[2] = mn_all; xf[3] = mx_all; }
+    cluster.sync();
+    cnt_in = sum_in = sum_all = 0.0;
+    mn_in = mn_all = INFINITY; mx_in = mx_all = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < CL; ++r) {
+      const double* rd = cluster.map_shared_rank(xd, r);
+      const float* rf = cluster.map_shared_rank(xf, r);
+      cnt_in += rd[0]; sum_in += rd[1]; sum_all += rd[2];
+      mn_in = fminf(mn_in, rf[0]); mx_in = fmaxf(mx_in, rf[1]); mn_all = fminf(mn_all, rf[2]); mx_all = fmaxf(mx_all, rf[3]);
+    }
+    cluster.sync();                  // the peers have read xd / xf: it may be rewritten below
+  }
   const bool use_mask = cnt_in >= 10.0;                     // `vals.size < 10` -> statistics of the whole image
   const double mean_d = use_mask ? sum_in / cnt_in : sum_all / (double)n;
   double m2 = 0.0;
-  for (long long i = tid; i < n; i += POST_T) {
+  for (long long i = i0 + tid; i < i1; i += POST_T) {
     if (!use_mask || !m || m[i] > 0) { const double d = (double)x[i] - mean_d; m2 += d * d; }
   }
   m2 = post_block_reduce(m2, sd, add, 0.0);
+  if (CL > 1) {
+    if (tid == 0) xd[3] = m2;
+    cluster.sync();
+    m2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < CL; ++r) m2 += cluster.map_shared_rank(xd, r)[3];
+    cluster.sync();                  // no CTA leaves (and frees its shared memory) while a peer still reads it
+  }
   const float mean = (float)mean_d;
   float stdv = (float)sqrt(m2 / (use_mask ? cnt_in : (double)n));   // np.std: population
   stdv = stdv > 1e-6f ? stdv : 1.0f;
   const float lo = cnt_in > 0.0 ? mn_in : mn_all, hi = cnt_in > 0.0 ? mx_in : mx_all;
   const float den = (float)((double)hi - (double)lo + 1e-6);
-  if (tid == 0 && p.stats) {
-    float* s = p.stats + 6 * (long long)blockIdx.x;
+  if (tid == 0 && p.stats && crank == 0) {
+    float* s = p.stats + 6 * (long long)img;
     s[0] = mean; s[1] = stdv; s[2] = lo; s[3] = hi; s[4] = (float)cnt_in; s[5] = use_mask ? 1.f : 0.f;
   }
-  float* z = p.out_z ? p.out_z + (long long)blockIdx.x * n : nullptr;
-  float* q = p.out_01 ? p.out_01 + (long long)blockIdx.x * n : nullptr;
-  for (long long i = tid; i < n; i += POST_T) {
+  float* z = p.out_z ? p.out_z + (long long)img * n : nullptr;
+  float* q = p.out_01 ? p.out_01 + (long long)img * n : nullptr;
+  for (long long i = i0 + tid; i < i1; i += POST_T) {
     const float v = x[i];
     if (q) q[i] = __fdiv_rn(__fsub_rn(v, lo), den);
     if (z) z[i] = __fdiv_rn(__fsub_rn(v, mean), stdv);

@@ -120,6 +120,47 @@ def test_gpu_percentiles_exact_on_hard_inputs():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,n", [(3, 5003), (3, 102400), (40, 5003), (40, 10240), (80, 4099), (80, 4096)])
+def test_gpu_one_image_kernels_for_every_cluster_size(B, n):
+    """the percentile and z-score kernels run as clusters of 4 / 2 / 1 CTAs per image depending on the batch (B x CL within
+    one wave of SMs): bit-exact percentiles and clipped images, z-score / preview / statistics against the oracle, for
+    vector-aligned and odd image sizes (ragged shares per CTA) -- and the same answers whatever the cluster size, checked
+    by running each image again in a batch of another size."""
+    from mri_acl_imagesegmentation_adsp_b200.adapters import recon_cabi
+    lib = recon_cabi.library()
+    rng = np.random.default_rng(B * 7 + n)
+    imgs = (rng.standard_normal((B, n)).astype(np.float32) ** 3) * np.float32(4.0)
+    imgs[1] = np.round(imgs[1])                                      # ties
+    masks = (rng.uniform(size=(B, n)) < 0.6).astype(np.uint8)
+    masks[2] = 0                                                     # empty mask: statistics of the whole image
+    t, mk = torch.from_numpy(imgs).cuda(), torch.from_numpy(masks).cuda()
+    out, lh = torch.empty_like(t), torch.empty((B, 2), dtype=torch.float32, device="cuda")
+    z, q01, st = torch.empty_like(t), torch.empty_like(t), torch.empty((B, 6), dtype=torch.float32, device="cuda")
+    lib.percentile_clip(t.data_ptr(), out.data_ptr(), lh.data_ptr(), B, n, CLIP[0], CLIP[1], 0)
+    lib.zscore_preview(t.data_ptr(), mk.data_ptr(), z.data_ptr(), q01.data_ptr(), st.data_ptr(), B, n, 0)
+    torch.cuda.synchronize()
+    for b in sorted({0, 1, 2, B // 2, B - 1}):
+        lo, hi = np.percentile(imgs[b], CLIP[0]), np.percentile(imgs[b], CLIP[1])
+        assert lh[b, 0].item() == lo and lh[b, 1].item() == hi, b
+        assert np.array_equal(out[b].cpu().numpy(), np.clip(imgs[b], lo, hi))
+        zr, pr = O.zscore_in_mask(imgs[b], masks[b]), O.preview_01(imgs[b], masks[b])
+        scale = float(np.abs(zr).max())
+        assert np.abs(z[b].cpu().numpy() - zr).max() <= 2e-6 * max(1.0, scale)
+        assert np.abs(q01[b].cpu().numpy() - pr).max() <= 2e-6 * max(1.0, float(np.abs(pr).max()))
+    # the same images in a batch that takes another cluster size: identical percentiles, statistics within rounding
+    B2 = 2 if B > 3 else 80
+    idx = np.arange(B2) % B
+    t2, mk2 = t[torch.from_numpy(idx).cuda()].contiguous(), mk[torch.from_numpy(idx).cuda()].contiguous()
+    lh2, st2 = torch.empty((B2, 2), dtype=torch.float32, device="cuda"), torch.empty((B2, 6), dtype=torch.float32, device="cuda")
+    z2 = torch.empty_like(t2)
+    lib.percentile_clip(t2.data_ptr(), 0, lh2.data_ptr(), B2, n, CLIP[0], CLIP[1], 0)
+    lib.zscore_preview(t2.data_ptr(), mk2.data_ptr(), z2.data_ptr(), 0, st2.data_ptr(), B2, n, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(lh2, lh[torch.from_numpy(idx).cuda()])
+    torch.testing.assert_close(st2, st[torch.from_numpy(idx).cuda()], rtol=1e-6, atol=0)
+
+
+@pytest.mark.gpu
 def test_gpu_preprocess_records_contract():
     """the k-space branch of preprocess_records on the device: slice_keep band, (S,1,H,W) float32 tensor, previews, masks."""
     from mri_acl_imagesegmentation_adsp_b200.preprocess.mri_preprocess import MRIKneePreprocessor
