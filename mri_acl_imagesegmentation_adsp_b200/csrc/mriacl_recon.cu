@@ -1517,12 +1517,9 @@ int mriacl_clip_resize_zscore_f32(const float* img, const uint8_t* body_mask, fl
   if (post_allow_smem()) return fail(MRIACL_ERR_CUDA, "cudaFuncSetAttribute failed: %s", rt_last_error_string());
   launch_percentile(pp, B, st);
   // 2. clip every tap, interpolate to (out_h, out_w); the mask goes through the same interpolation and a 0.5 threshold
-  ResizeParams ri{img, nullptr, out_z, nullptr, clip_lo_hi, B, H, W, out_h, out_w};
+  // (one launch: a thread computes its source coordinates and weights once and applies them to both planes)
+  ResizeParams ri{img, nullptr, out_z, nullptr, clip_lo_hi, B, H, W, out_h, out_w, body_mask, body_mask ? out_mask : nullptr};
   MRIACL_LAUNCH(resize_bilinear_kernel, grid_for((long long)B * out_h * out_w, 256), 256, 0, st, ri);
-  if (body_mask) {
-    ResizeParams rm{nullptr, body_mask, nullptr, out_mask, nullptr, B, H, W, out_h, out_w};
-    MRIACL_LAUNCH(resize_bilinear_kernel, grid_for((long long)B * out_h * out_w, 256), 256, 0, st, rm);
-  }
   // 3. statistics inside the resized mask, z-score in place, preview
   ZscoreParams zp{out_z, body_mask ? out_mask : nullptr, out_z, out_01, stats, (long long)out_h * out_w};
   launch_zscore(zp, B, st);

@@ -212,6 +212,9 @@ struct ResizeParams {
   unsigned char* out_u8;      // [B][oh][ow] uint8 = (resized > 0.5)
   const float* lo_hi;         // [B][2] clip applied to every tap before the interpolation, or nullptr
   int B, H, W, oh, ow;
+  // optional second plane through the same source coordinates and weights in the same launch (the body mask beside its image)
+  const unsigned char* mask_in;   // [B][H][W] uint8 or nullptr
+  unsigned char* mask_out;        // [B][oh][ow] uint8 = (resized > 0.5)
 };
 
 // thread = output pixel
@@ -246,6 +249,12 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(ResizeParams p) {
     const float top = __fadd_rn(__fmul_rn(hx, p00), __fmul_rn(lx, p01)), bot = __fadd_rn(__fmul_rn(hx, p10), __fmul_rn(lx, p11));
     const float v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
     if (p.out) p.out[i] = v; else p.out_u8[i] = v > 0.5f ? 1 : 0;
+    if (p.mask_in) {
+      const float m00 = (float)p.mask_in[base + (long long)y0 * p.W + x0], m01 = (float)p.mask_in[base + (long long)y0 * p.W + x1];
+      const float m10 = (float)p.mask_in[base + (long long)y1 * p.W + x0], m11 = (float)p.mask_in[base + (long long)y1 * p.W + x1];
+      const float mt = __fadd_rn(__fmul_rn(hx, m00), __fmul_rn(lx, m01)), mb = __fadd_rn(__fmul_rn(hx, m10), __fmul_rn(lx, m11));
+      p.mask_out[i] = __fadd_rn(__fmul_rn(hy, mt), __fmul_rn(ly, mb)) > 0.5f ? 1 : 0;
+    }
   }
 }
 
